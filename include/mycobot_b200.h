@@ -1,0 +1,196 @@
+/*
+ * mycobot_b200.h -- C ABI of the B200-native batched myCobot physics-and-task engine.
+ *
+ * Drop-in boundary for the hot path of matinmoezzi/MyCobotGym:
+ * every entry point replaces a piece of the reference's per-env Python/MuJoCo path and is
+ * what a ctypes / cffi binding on the reference side would bind.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in signatures.
+ *   - every function returns 0 on success, <0 on error; mcb_last_error() gives the text
+ *     (thread-local).  No exceptions cross the ABI.
+ *   - all array arguments of the non-`_host` functions are CALLER-OWNED DEVICE pointers
+ *     (e.g. torch `data_ptr()`), row-major, env-major.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream); all work is enqueued on it, nothing synchronises.
+ *   - the library owns only the opaque mcb_model / mcb_batch handles.
+ *   - a batch is not thread-safe; one batch per process per GPU is the intended use.
+ *
+ * Fixed topology: the myCobot 280 joint-variant model (mycobot280.xml) reduced to its 13
+ * jointed bodies (fixed children merged by the host-side loader, mycobotgym_b200/flatten.py).
+ */
+#ifndef MYCOBOT_B200_H_
+#define MYCOBOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_NB 13     /* jointed bodies: link1..6, rgear, rfinger, lgear, lfinger, rhinge, lhinge, object0 */
+#define MCB_NV 18     /* dofs (12 hinges + free cube) */
+#define MCB_NQ 19
+#define MCB_NU 7
+#define MCB_NHINGE 12
+#define MCB_NGEOM 5   /* plane, table box, right/left finger-layer boxes, cube box */
+#define MCB_MAXPAIR 12
+#define MCB_OBS_OBJECT 25
+#define MCB_OBS_REACH 10
+#define MCB_STATE_STRIDE 72 /* doubles per env in the resident state record */
+
+/* Flattened, reduced model (host memory; copied to the device by mcb_model_create).
+ * Replaces the compiled mjModel the reference builds in MujocoEnv.__init__ (mycobot.py:69-75). */
+typedef struct mcb_model_desc {
+  /* kinematic tree of jointed bodies, depth-first order == dof order */
+  int32_t parent[MCB_NB];        /* jointed parent body or -1 */
+  int32_t level[MCB_NB];         /* depth in the jointed tree */
+  int32_t subtree_size[MCB_NB];  /* bodies in the subtree rooted here (contiguous in DFS order) */
+  int32_t dof_body[MCB_NV];
+  uint32_t ancmask[MCB_NB];      /* bit j set: dof j moves this body */
+  double Tpos[MCB_NB][3];        /* parent-frame offset of the body frame (through merged fixed bodies) */
+  double Tmat[MCB_NB][9];        /* parent-frame orientation of the body frame at q = 0 */
+  double axis[MCB_NB][3];        /* hinge axis in the body frame (unused for the free body) */
+  double mass[MCB_NB];           /* composite (body + merged fixed children) */
+  double ipos[MCB_NB][3];        /* composite centre of mass, body frame */
+  double inertia[MCB_NB][6];     /* composite inertia about ipos, body axes: xx yy zz xy xz yz */
+  double armature[MCB_NV];
+  double damping[MCB_NV];
+  double dof_invweight0[MCB_NV];
+  double ref_robot[3];           /* world point the robot tree's spatial quantities refer to */
+  double qpos0[MCB_NQ];
+  /* joint limits (hinges only) */
+  int32_t jnt_limited[MCB_NHINGE];
+  double jnt_range[MCB_NHINGE][2];
+  double jnt_solref[MCB_NHINGE][2];
+  double jnt_solimp[MCB_NHINGE][5];
+  /* equality: two connects (four-bar closure) + one joint coupling */
+  int32_t con_body1[2], con_body2[2];
+  double con_anchor1[2][3], con_anchor2[2][3];
+  double con_diag[2];            /* body_invweight0 translational sum */
+  double con_solref[2][2], con_solimp[2][5];
+  int32_t jeq_dof1, jeq_dof2;
+  double jeq_polycoef[5];
+  double jeq_diag;
+  double jeq_solref[2], jeq_solimp[5];
+  /* collision geoms (primitives) */
+  int32_t geom_type[MCB_NGEOM];  /* 0 plane, 6 box (MuJoCo mjtGeom values) */
+  int32_t geom_body[MCB_NGEOM];  /* jointed body index or -1 (static) */
+  int32_t geom_condim[MCB_NGEOM];
+  double geom_pos[MCB_NGEOM][3]; /* in geom_body frame (world if static) */
+  double geom_mat[MCB_NGEOM][9];
+  double geom_size[MCB_NGEOM][3];
+  double geom_rbound[MCB_NGEOM];
+  double geom_friction[MCB_NGEOM][3];
+  double geom_solref[MCB_NGEOM][2];
+  double geom_solimp[MCB_NGEOM][5];
+  double geom_solmix[MCB_NGEOM];
+  double geom_invweight[MCB_NGEOM][2]; /* body_invweight0 (translational, rotational) of the geom's body */
+  int32_t npair;
+  int32_t pair_g1[MCB_MAXPAIR], pair_g2[MCB_MAXPAIR]; /* statically filtered candidate pairs, type1<=type2 */
+  /* sites used by the task layer */
+  int32_t eef_body;
+  double eef_pos[3];
+  int32_t obj_body;
+  /* actuators: general, no dynamics, fixed gain, affine bias */
+  double act_moment[MCB_NU][MCB_NV];
+  double act_gain[MCB_NU];
+  double act_bias[MCB_NU][3];
+  double act_ctrlrange[MCB_NU][2];
+  double act_forcerange[MCB_NU][2];
+  int32_t act_ctrllimited[MCB_NU];
+  int32_t act_forcelimited[MCB_NU];
+  /* options (mycobot280_main.xml:3-5 + MuJoCo defaults) */
+  double timestep, gravity[3], tolerance, ls_tolerance, meaninertia, impratio;
+  int32_t iterations, ls_iterations;
+  /* task constants captured by _env_setup (mycobot.py:450-481) */
+  double initial_gripper_xpos[3];
+  double height_offset;
+  double init_qpos[MCB_NQ];
+  double init_ctrl[MCB_NU];
+} mcb_model_desc;
+
+/* Task configuration == the reference constructor kwargs (mycobot.py:30-46) + TimeLimit (__init__.py:34). */
+typedef struct mcb_task_cfg {
+  int32_t has_object;          /* mycobot.py:33 */
+  int32_t block_gripper;       /* mycobot.py:34 */
+  int32_t target_in_the_air;   /* mycobot.py:38 */
+  int32_t reward_type;         /* 0 sparse (float32 out), 1 dense (float64 out); mycobot.py:289-295 */
+  int32_t max_episode_steps;   /* 50 */
+  int32_t frame_skip;          /* 20 */
+  int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
+  int32_t nefc_max;            /* constraint-row capacity per env: 32, 64 or 96 (0 = default for the task) */
+  double distance_threshold;   /* 0.01 */
+} mcb_task_cfg;
+
+typedef struct mcb_model mcb_model;
+typedef struct mcb_batch mcb_batch;
+
+const char* mcb_version(void);
+const char* mcb_last_error(void);
+int32_t mcb_model_desc_size(void); /* sizeof(mcb_model_desc) as compiled, for binding self-checks */
+int32_t mcb_task_cfg_size(void);
+
+/* replaces mujoco.MjModel.from_xml_path + MyCobotEnv._env_setup (mycobot.py:69-82,450-481) */
+int32_t mcb_model_create(const mcb_model_desc* host_desc, int32_t device, mcb_model** out);
+int32_t mcb_model_destroy(mcb_model* m);
+
+/* replaces constructing n_envs MyCobotEnv instances (train.py:80-85) */
+int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out);
+int32_t mcb_batch_destroy(mcb_batch* b);
+int32_t mcb_batch_num_envs(const mcb_batch* b);
+int32_t mcb_batch_obs_dim(const mcb_batch* b);
+
+/* replaces MyCobotEnv.reset / reset_model / _sample_goal (mycobot.py:207-243,506-514).
+ * mask: uint8[N] or NULL (= all).  obj_xy: double[N,2] or NULL (device sampler).  goals: double[N,3] or NULL.
+ * Injected values are what the reference's seeded sampler produced (bit-exact goals). */
+int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals,
+                  double* obs, double* achieved_goal, double* desired_goal, void* stream);
+
+/* replaces MyCobotEnv.step, joint controller (mycobot.py:132-133,190-205) incl. TimeLimit truncation.
+ * actions float32[N,7]; reward float32[N] (sparse) or float64[N] (dense); flags uint8[N].
+ * final_obs double[N,obs_dim] or NULL: terminal observation of envs that auto-reset in this call. */
+int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* achieved_goal, double* desired_goal,
+                 void* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* success, double* final_obs,
+                 void* stream);
+
+/* Same call with HOST buffers: actions are copied host->device and results device->host inside the call
+ * (pinned staging owned by the batch); synchronises `stream` before returning.  This is the call a
+ * reference-side VecEnv adapter holding numpy arrays makes. */
+int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, double* h_achieved_goal,
+                      double* h_desired_goal, void* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                      uint8_t* h_success, void* stream);
+
+/* state injection / extraction for parity replay: qpos[N,19] qvel[N,18] ctrl[N,7]
+ * qacc_warmstart[N,18] goal[N,3] elapsed int32[N]; any pointer may be NULL. */
+int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* qacc_warmstart, double* goal,
+                      int32_t* elapsed, void* stream);
+int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl,
+                      const double* qacc_warmstart, const double* goal, const int32_t* elapsed, void* stream);
+
+/* replaces mujoco.mj_forward on every env (mycobot.py:213,229,306); refreshes qacc_warmstart; optional obs out */
+int32_t mcb_forward(mcb_batch* b, double* obs, double* achieved_goal, double* desired_goal, void* stream);
+
+/* replaces MyCobotEnv.compute_reward for HER relabelling batches (mycobot.py:289-295, utils.py:24-26) */
+int32_t mcb_compute_reward(const double* achieved_goal, const double* goal, int64_t n, double distance_threshold,
+                           int32_t reward_type, void* out, void* stream);
+
+/* episode statistics accumulated on device since the last call with reset_after != 0:
+ * out[0]=episodes, [1]=successes, [2]=return_sum, [3]=length_sum, [4]=env_steps, [5]=constraint-row overflows,
+ * [6]=solver iterations, [7]=substeps.  `out` is a device pointer to 8 doubles. */
+int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream);
+
+/* debug taps for stage-level parity tests: copies the given quantity of env `env` after the most recent
+ * mcb_forward() into host memory.  what: 0 M[18*18], 1 qfrc_bias[18], 2 qacc_smooth[18], 3 qacc[18],
+ * 4 nefc/ncon (2 doubles), 5 efc_J[nefc*18], 6 efc_aref, 7 efc_D, 8 contact (dist,pos3,normal3)*ncon,
+ * 9 xpos[13*3], 10 xmat[13*9], 11 qfrc_smooth[18], 12 efc_pos. Returns number of doubles written. */
+int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out, int32_t cap, void* stream);
+
+/* measurement helpers used by bench.py */
+int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */
+int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out); /* DFMA micro-kernel, CUDA-event timed */
+int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYCOBOT_B200_H_ */

@@ -1,0 +1,92 @@
+"""Build + ctypes binding of the C-ABI library (include/mycobot_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or cannot be loaded the
+import of the binding raises, it never routes to oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from .flatten import ModelDesc, TaskCfg
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "libmycobot_b200.so")
+SRC = os.path.join(PKG_DIR, "csrc", "mcb_engine.cu")
+HDR = os.path.join(ROOT, "include", "mycobot_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=true",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = [
+    "mcb_version", "mcb_last_error", "mcb_model_desc_size", "mcb_task_cfg_size", "mcb_model_create",
+    "mcb_model_destroy", "mcb_batch_create", "mcb_batch_destroy", "mcb_batch_num_envs", "mcb_batch_obs_dim",
+    "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
+    "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
+    "mcb_time_step_kernel",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in (SRC, HDR))
+
+
+def build(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU; the .so is built in-tree so it travels with gpurun."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension must be built (python -c 'import __graft_entry__ as g; g.build()'); "
+            "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    L.mcb_version.restype = C.c_char_p
+    L.mcb_last_error.restype = C.c_char_p
+    L.mcb_model_create.argtypes = [C.POINTER(ModelDesc), i32, C.POINTER(vp)]
+    L.mcb_model_destroy.argtypes = [vp]
+    L.mcb_batch_create.argtypes = [vp, i32, C.POINTER(TaskCfg), u64, C.POINTER(vp)]
+    L.mcb_batch_destroy.argtypes = [vp]
+    L.mcb_batch_num_envs.argtypes = [vp]
+    L.mcb_batch_obs_dim.argtypes = [vp]
+    L.mcb_reset.argtypes = [vp] + [vp] * 7
+    L.mcb_step.argtypes = [vp] + [vp] * 10
+    L.mcb_step_host.argtypes = [vp] + [vp] * 9
+    L.mcb_get_state.argtypes = [vp] + [vp] * 7
+    L.mcb_set_state.argtypes = [vp] + [vp] * 7
+    L.mcb_forward.argtypes = [vp] + [vp] * 4
+    L.mcb_compute_reward.argtypes = [vp, vp, i64, dbl, i32, vp, vp]
+    L.mcb_stats.argtypes = [vp, vp, i32, vp]
+    L.mcb_debug_forward.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.mcb_last_step_launches.argtypes = [vp]
+    L.mcb_fp64_peak_probe.argtypes = [i32, i32, C.POINTER(dbl)]
+    assert L.mcb_model_desc_size() == C.sizeof(ModelDesc), (L.mcb_model_desc_size(), C.sizeof(ModelDesc))
+    assert L.mcb_task_cfg_size() == C.sizeof(TaskCfg), (L.mcb_task_cfg_size(), C.sizeof(TaskCfg))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise RuntimeError("mycobot_b200: " + load().mcb_last_error().decode())
+    return rc

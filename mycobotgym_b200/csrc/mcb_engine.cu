@@ -1,0 +1,1712 @@
+// mcb_engine.cu -- B200 (sm_100a) batched myCobot physics-and-task engine, C ABI in include/mycobot_b200.h.
+//
+// One environment per warp; the whole env-step (frame_skip substeps of the MuJoCo-equivalent
+// forward dynamics + semi-implicit Euler, then observation / reward / success / auto-reset) is one
+// kernel launch.  An env's working set (state, body frames, spatial inertias, M / H and their
+// Cholesky factors, the constraint Jacobian) lives in the warp's slice of shared memory; HBM sees one
+// 576-byte state record read and written per env-step plus the action and the outputs.
+// All arithmetic is fp64 on the CUDA cores (DFMA); tensor cores are deliberately unused: the per-env
+// matrices are 18x18 and smaller and the work is a sequence of tree recursions, not a dense contraction.
+//
+// Stage map (what each device function restates; the reference reaches all of it through
+// mujoco.mj_step, mycobotgym/envs/mycobot.py:193 -> gymnasium MujocoEnv.do_simulation):
+//   fk()              mj_kinematics              cinert_cdof()  mj_comPos
+//   crb_mass()        mj_crb                     chol()         mj_factorM (dense LL' instead of sparse L'DL)
+//   collide()         mj_collision (plane-box, box-box)
+//   make_rows()       mj_makeConstraint + mj_makeImpedance
+//   velocity_rne()    mj_comVel, mj_passive, mj_referenceConstraint, mj_rne
+//   actuation()       mj_fwdActuation            newton()       mj_solNewton (pyramidal cones)
+//   euler()           mj_Euler + mj_integratePos
+//   epilogue()        MyCobotEnv._get_obs / compute_reward / _is_success / reset_model (mycobot.py:207-298,342-400)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+
+#include "mycobot_b200.h"
+
+#define NB MCB_NB
+#define NV MCB_NV
+#define NQ MCB_NQ
+#define NU MCB_NU
+#define NH MCB_NHINGE
+#define LD 19           // row stride of the dense 18-wide matrices (odd => conflict-free column and row access)
+#define MAXCON 13
+#define FULLMASK 0xffffffffu
+#define MINVAL 1e-15
+#define MINIMP 0.0001
+#define MAXIMP 0.9999
+#define CUBE 12
+#define NMNZ_MAX 96
+#define WPB 1            // warps (= envs) per CTA; 1 keeps the per-SM env count limited only by shared memory
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const char* what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+  return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
+
+struct PairParam {
+  int g1, g2, dim;
+  double friction[3], solref[2], solimp[5], tran, rot;
+};
+
+struct DevModel {
+  mcb_model_desc d;
+  int nlevel;
+  int level_start[NB + 1];
+  int level_body[NB];
+  int nmnz;
+  unsigned char mnz_i[NMNZ_MAX], mnz_j[NMNZ_MAX];
+  PairParam pair[MCB_MAXPAIR];
+};
+
+enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_RESET = 2 };
+
+struct StepArgs {
+  const DevModel* m;
+  int n_envs, mode;
+  mcb_task_cfg cfg;
+  uint64_t seed;
+  double* state;             // [N, 72]
+  int* elapsed;              // [N]
+  double* ep_return;         // [N]
+  unsigned long long* rng_ctr;  // [N]
+  double* stats;             // [8]
+  const float* actions;      // [N, 7]
+  const uint8_t* mask;       // reset
+  const double* inj_xy;      // reset
+  const double* inj_goal;    // reset
+  double *obs, *ag, *dg, *final_obs;
+  void* reward;
+  uint8_t *terminated, *truncated, *success;
+  double* debug;             // optional debug dump of env debug_env
+  int debug_env;
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-env shared-memory working set
+template <int NEFC>
+struct EnvS {
+  double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
+  double lR[NB * 9], xpos[NB * 3], xmat[NB * 9];
+  double cdof[NV * 6], cdof_dot[NV * 6], cinert[NB * 10], crb[NB * 10];
+  double cvel[NB * 6], cacc[NB * 6], buf[NV * 6];
+  double M[NV * LD], L[NV * LD], H[NV * LD], Linv[NV], Hinv[NV];
+  double qfrc_bias[NV], qfrc_act[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV];
+  double Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV], qfrc_con[NV];
+  double refcube[4];
+  double J[NEFC * LD];
+  double ekp[NEFC], eB[NEFC], eD[NEFC], earef[NEFC], eJaref[NEFC], eJv[NEFC];
+  double cdist[MAXCON], cpos[MAXCON * 3], cframe[MAXCON * 9];
+  int etype[NEFC];   // 0 equality, 1 limit / contact (inequality)
+  int cpair[MAXCON], cefc[MAXCON];
+  int nefc, ncon, ne, nl, overflow, iters, pad0, pad1;
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(double* r, const double* a, const double* b) {
+  r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void mul_inert_vec(double* r, const double* i, const double* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+__device__ __forceinline__ void cross_motion(double* r, const double* vel, const double* v) {
+  r[0] = -vel[2] * v[1] + vel[1] * v[2];
+  r[1] = vel[2] * v[0] - vel[0] * v[2];
+  r[2] = -vel[1] * v[0] + vel[0] * v[1];
+  r[3] = -vel[2] * v[4] + vel[1] * v[5] - vel[5] * v[1] + vel[4] * v[2];
+  r[4] = vel[2] * v[3] - vel[0] * v[5] + vel[5] * v[0] - vel[3] * v[2];
+  r[5] = -vel[1] * v[3] + vel[0] * v[4] - vel[4] * v[0] + vel[3] * v[1];
+}
+__device__ __forceinline__ void cross_force(double* r, const double* vel, const double* f) {
+  r[0] = -vel[2] * f[1] + vel[1] * f[2] - vel[5] * f[4] + vel[4] * f[5];
+  r[1] = vel[2] * f[0] - vel[0] * f[2] + vel[5] * f[3] - vel[3] * f[5];
+  r[2] = -vel[1] * f[0] + vel[0] * f[1] - vel[4] * f[3] + vel[3] * f[4];
+  r[3] = -vel[2] * f[4] + vel[1] * f[5];
+  r[4] = vel[2] * f[3] - vel[0] * f[5];
+  r[5] = -vel[1] * f[3] + vel[0] * f[4];
+}
+__device__ __forceinline__ void quat2mat(double* m, const double* q) {
+  double q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  double q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
+  m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fk(): body frames of the 13 jointed bodies.  Lane b builds the local transform of body b
+// (Tmat * Rot(axis, q)); the chain is then composed level by level with lanes spread over the
+// 9 + 3 matrix / vector elements of every body on the level.
+template <class S>
+__device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
+  if (lane < NH) {
+    double ang = s.qpos[lane] - m->d.qpos0[lane];
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    const double* ax = m->d.axis[lane];
+    double oc = 1.0 - cs;
+    double R[9];
+    R[0] = cs + oc * ax[0] * ax[0];         R[1] = oc * ax[0] * ax[1] - sn * ax[2]; R[2] = oc * ax[0] * ax[2] + sn * ax[1];
+    R[3] = oc * ax[0] * ax[1] + sn * ax[2]; R[4] = cs + oc * ax[1] * ax[1];         R[5] = oc * ax[1] * ax[2] - sn * ax[0];
+    R[6] = oc * ax[0] * ax[2] - sn * ax[1]; R[7] = oc * ax[1] * ax[2] + sn * ax[0]; R[8] = cs + oc * ax[2] * ax[2];
+    const double* T = m->d.Tmat[lane];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) s.lR[lane * 9 + 3 * r + c] = T[3 * r] * R[c] + T[3 * r + 1] * R[3 + c] + T[3 * r + 2] * R[6 + c];
+  } else if (lane == CUBE && nba > CUBE) {
+    double* q = s.qpos + 15;
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { double inv = 1.0 / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
+    quat2mat(s.xmat + CUBE * 9, q);
+    s.xpos[CUBE * 3] = s.qpos[12]; s.xpos[CUBE * 3 + 1] = s.qpos[13]; s.xpos[CUBE * 3 + 2] = s.qpos[14];
+  }
+  __syncwarp();
+  for (int L = 0; L < m->nlevel; L++) {
+    int s0 = m->level_start[L], n = (m->level_start[L + 1] - s0) * 12;
+    for (int w = lane; w < n; w += 32) {
+      int b = m->level_body[s0 + w / 12], e = w % 12;
+      if (b == CUBE) continue;
+      int p = m->d.parent[b];
+      if (e < 9) {
+        int r = e / 3, c = e % 3;
+        double v;
+        if (p < 0) v = s.lR[b * 9 + e];
+        else v = s.xmat[p * 9 + 3 * r] * s.lR[b * 9 + c] + s.xmat[p * 9 + 3 * r + 1] * s.lR[b * 9 + 3 + c] + s.xmat[p * 9 + 3 * r + 2] * s.lR[b * 9 + 6 + c];
+        s.xmat[b * 9 + e] = v;
+      } else {
+        int r = e - 9;
+        const double* t = m->d.Tpos[b];
+        double v;
+        if (p < 0) v = t[r];
+        else v = s.xpos[p * 3 + r] + s.xmat[p * 9 + 3 * r] * t[0] + s.xmat[p * 9 + 3 * r + 1] * t[1] + s.xmat[p * 9 + 3 * r + 2] * t[2];
+        s.xpos[b * 3 + r] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// cinert_cdof(): spatial inertia of every (composite) body and motion axis of every dof, both expressed
+// about a per-tree reference point (robot: fixed world point; cube: its own centre of mass).
+template <class S>
+__device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+  if (lane < nba) {
+    int b = lane;
+    const double* R = s.xmat + b * 9;
+    const double* ip = m->d.ipos[b];
+    double com[3], off[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) com[r] = s.xpos[b * 3 + r] + R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];
+    if (b == CUBE) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) { s.refcube[r] = com[r]; off[r] = 0; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 3; r++) off[r] = com[r] - m->d.ref_robot[r];
+    }
+    const double* I = m->d.inertia[b];  // xx yy zz xy xz yz
+    double A[9];                         // A = R * Ib
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      A[3 * r + 0] = R[3 * r] * I[0] + R[3 * r + 1] * I[3] + R[3 * r + 2] * I[4];
+      A[3 * r + 1] = R[3 * r] * I[3] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[5];
+      A[3 * r + 2] = R[3 * r] * I[4] + R[3 * r + 1] * I[5] + R[3 * r + 2] * I[2];
+    }
+    double mass = m->d.mass[b];
+    double* ci = s.cinert + b * 10;
+    ci[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2] + mass * (off[1] * off[1] + off[2] * off[2]);
+    ci[1] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5] + mass * (off[0] * off[0] + off[2] * off[2]);
+    ci[2] = A[6] * R[6] + A[7] * R[7] + A[8] * R[8] + mass * (off[0] * off[0] + off[1] * off[1]);
+    ci[3] = A[0] * R[3] + A[1] * R[4] + A[2] * R[5] - mass * off[0] * off[1];
+    ci[4] = A[0] * R[6] + A[1] * R[7] + A[2] * R[8] - mass * off[0] * off[2];
+    ci[5] = A[3] * R[6] + A[4] * R[7] + A[5] * R[8] - mass * off[1] * off[2];
+    ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2]; ci[9] = mass;
+  }
+  if (lane < nva) {
+    int j = lane;
+    double* cd = s.cdof + j * 6;
+    if (j < NH) {
+      const double* R = s.xmat + j * 9;  // hinge j belongs to body j
+      const double* a = m->d.axis[j];
+      double ax[3], off[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) { ax[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; off[r] = m->d.ref_robot[r] - s.xpos[j * 3 + r]; }
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+      cross3(cd + 3, ax, off);
+    } else {
+      int k = j - 12;
+      if (k < 3) {
+        cd[0] = cd[1] = cd[2] = 0; cd[3] = (k == 0); cd[4] = (k == 1); cd[5] = (k == 2);
+      } else {
+        const double* R = s.xmat + CUBE * 9;
+        const double* ip = m->d.ipos[CUBE];
+        double ax[3] = {R[k - 3], R[k], R[k + 3]}, off[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) off[r] = R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];  // refcube - xpos
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        cross3(cd + 3, ax, off);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// crb_mass(): composite rigid-body inertias (subtree = contiguous DFS range) and the joint-space inertia M.
+template <class S>
+__device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+  for (int w = lane; w < nba * 10; w += 32) {
+    int b = w / 10, k = w % 10;
+    int e = b + m->d.subtree_size[b];
+    if (e > nba) e = nba;
+    double acc = s.cinert[w];
+    for (int c = b + 1; c < e; c++) acc += s.cinert[c * 10 + k];
+    s.crb[w] = acc;
+  }
+  __syncwarp();
+  if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + m->d.dof_body[lane] * 10, s.cdof + lane * 6);
+  __syncwarp();
+  for (int e = lane; e < m->nmnz; e += 32) {
+    int i = m->mnz_i[e], j = m->mnz_j[e];
+    if (i >= nva) continue;
+    const double* a = s.cdof + j * 6;
+    const double* b = s.buf + i * 6;
+    double v = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+    if (i == j) v += m->d.armature[i];
+    s.M[i * LD + j] = v;
+    s.M[j * LD + i] = v;
+  }
+  __syncwarp();
+}
+
+// chol(): dense Cholesky A = L L' of the leading n x n block, in place (lower triangle), lane i owns row i.
+// invd[k] = 1 / L[k][k].
+__device__ void chol(double* A, double* invd, int n, int lane) {
+  for (int j = 0; j < n; j++) {
+    double sv = 0;
+    if (lane >= j && lane < n) {
+      const double* ri = A + lane * LD;
+      const double* rj = A + j * LD;
+      double s0 = ri[j], s1 = 0;
+      int k = 0;
+      for (; k + 1 < j; k += 2) { s0 -= ri[k] * rj[k]; s1 -= ri[k + 1] * rj[k + 1]; }
+      if (k < j) s0 -= ri[k] * rj[k];
+      sv = s0 + s1;
+    }
+    double sjj = __shfl_sync(FULLMASK, sv, j);
+    if (sjj < MINVAL) sjj = MINVAL;
+    double inv = rsqrt(sjj);
+    if (lane == j) { A[j * LD + j] = sjj * inv; invd[j] = inv; }
+    else if (lane > j && lane < n) A[lane * LD + j] = sv * inv;
+    __syncwarp();
+  }
+}
+// chol_solve(): x = (L L')^-1 b ; every lane passes its b (lane >= n: ignored) and gets x for its row.
+__device__ double chol_solve(const double* L, const double* invd, int n, int lane, double b) {
+  for (int k = 0; k < n; k++) {
+    double yk = __shfl_sync(FULLMASK, b, k) * invd[k];
+    if (lane == k) b = yk;
+    else if (lane > k && lane < n) b -= L[lane * LD + k] * yk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    double xk = __shfl_sync(FULLMASK, b, k) * invd[k];
+    if (lane == k) b = xk;
+    else if (lane < k) b -= L[k * LD + lane] * xk;
+  }
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// collision: narrow phase for the statically filtered primitive pairs, one lane per pair
+struct RawCon { double dist, pos[3], normal[3]; };
+
+__device__ int plane_box(RawCon* out, const double* ppos, const double* pmat, const double* bpos, const double* bmat, const double* bsize) {
+  double norm[3] = {pmat[2], pmat[5], pmat[8]}, dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
+  double dist = dot3(dif, norm);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    double vec[3] = {(i & 1 ? bsize[0] : -bsize[0]), (i & 2 ? bsize[1] : -bsize[1]), (i & 4 ? bsize[2] : -bsize[2])};
+    double corner[3];
+    for (int r = 0; r < 3; r++) corner[r] = bmat[3 * r] * vec[0] + bmat[3 * r + 1] * vec[1] + bmat[3 * r + 2] * vec[2];
+    double ldist = dot3(norm, corner);
+    if (dist + ldist > 0 || ldist > 0) continue;
+    double cd = dist + ldist;
+    out[cnt].dist = cd;
+    for (int k = 0; k < 3; k++) { out[cnt].pos[k] = corner[k] + bpos[k] - norm[k] * cd * 0.5; out[cnt].normal[k] = norm[k]; }
+    if (++cnt >= 4) return 4;
+  }
+  return cnt;
+}
+
+__device__ int clip_poly(double* px, double* py, int n, double hx, double hy) {
+  double qx[16], qy[16];
+  for (int side = 0; side < 4; side++) {
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+      int j = (i + 1) % n;
+      double ax = px[i], ay = py[i], bx = px[j], by = py[j];
+      double da, db;
+      if (side == 0) { da = hx - ax; db = hx - bx; }
+      else if (side == 1) { da = hx + ax; db = hx + bx; }
+      else if (side == 2) { da = hy - ay; db = hy - by; }
+      else { da = hy + ay; db = hy + by; }
+      if (da >= 0) { qx[cnt] = ax; qy[cnt] = ay; cnt++; }
+      if ((da >= 0) != (db >= 0)) {
+        double t = da / (da - db);
+        qx[cnt] = ax + t * (bx - ax); qy[cnt] = ay + t * (by - ay); cnt++;
+      }
+    }
+    n = cnt;
+    for (int i = 0; i < n; i++) { px[i] = qx[i]; py[i] = qy[i]; }
+    if (n == 0) return 0;
+  }
+  return n;
+}
+
+// box_box(): 15-axis separating-axis test, then a clipped face manifold (<= 8 points) or one edge-edge point.
+// Normal points from box 1 to box 2.  Degenerate ties: first face axis wins (a later axis must be better by
+// 1e-10), an edge axis must beat the faces by 5%.
+__device__ int box_box(RawCon* out, const double* p1, const double* R1, const double* s1, const double* p2, const double* R2, const double* s2) {
+  double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double A[3][3], B[3][3], Cm[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { A[i][k] = R1[3 * k + i]; B[i][k] = R2[3 * k + i]; }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { Cm[i][j] = dot3(A[i], B[j]); Q[i][j] = fabs(Cm[i][j]); }
+  double best = -1e300; int code = -1; double bn[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) {
+    double t = dot3(d, A[i]);
+    double sp = fabs(t) - (s1[i] + s2[0] * Q[i][0] + s2[1] * Q[i][1] + s2[2] * Q[i][2]);
+    if (sp > 0) return 0;
+    if (sp > best + (code >= 0 ? 1e-10 : 0.0)) { best = sp; code = i; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -A[i][k] : A[i][k]); }
+  }
+  for (int j = 0; j < 3; j++) {
+    double t = dot3(d, B[j]);
+    double sp = fabs(t) - (s2[j] + s1[0] * Q[0][j] + s1[1] * Q[1][j] + s1[2] * Q[2][j]);
+    if (sp > 0) return 0;
+    if (sp > best + 1e-10) { best = sp; code = 3 + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -B[j][k] : B[j][k]); }
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double Lx[3];
+      cross3(Lx, A[i], B[j]);
+      double l = sqrt(dot3(Lx, Lx));
+      if (l < 1e-6) continue;
+      for (int k = 0; k < 3; k++) Lx[k] /= l;
+      double t = dot3(d, Lx);
+      double ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(A[k], Lx)); rb += s2[k] * fabs(dot3(B[k], Lx)); }
+      double sp = fabs(t) - (ra + rb);
+      if (sp > 0) return 0;
+      if (sp * 1.05 > best + 1e-10 && sp > best) { best = sp; code = 6 + 3 * i + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -Lx[k] : Lx[k]); }
+    }
+  if (code < 0) return 0;
+  if (code >= 6) {
+    int i = (code - 6) / 3, j = (code - 6) % 3;
+    double pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
+    for (int a = 0; a < 3; a++) {
+      if (a == i) continue;
+      double sg = dot3(A[a], bn) > 0 ? 1.0 : -1.0;
+      for (int k = 0; k < 3; k++) pa[k] += sg * s1[a] * A[a][k];
+    }
+    for (int b = 0; b < 3; b++) {
+      if (b == j) continue;
+      double sg = dot3(B[b], bn) > 0 ? -1.0 : 1.0;
+      for (int k = 0; k < 3; k++) pb[k] += sg * s2[b] * B[b][k];
+    }
+    double w[3] = {pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]};
+    double b_ = Cm[i][j], dd = dot3(A[i], w), e = dot3(B[j], w);
+    double den = 1 - b_ * b_;
+    double u = (b_ * e - dd) / den, v = (e - b_ * dd) / den;
+    for (int k = 0; k < 3; k++) {
+      double ca = pa[k] + u * A[i][k], cb = pb[k] + v * B[j][k];
+      out[0].pos[k] = 0.5 * (ca + cb);
+      out[0].normal[k] = bn[k];
+    }
+    out[0].dist = best;
+    return 1;
+  }
+  const double *pr, *pi_, *sr, *si; double (*Ar)[3], (*Ai)[3]; double nref[3]; int ax;
+  if (code < 3) { pr = p1; pi_ = p2; sr = s1; si = s2; Ar = A; Ai = B; ax = code; for (int k = 0; k < 3; k++) nref[k] = bn[k]; }
+  else { pr = p2; pi_ = p1; sr = s2; si = s1; Ar = B; Ai = A; ax = code - 3; for (int k = 0; k < 3; k++) nref[k] = -bn[k]; }
+  int ia = 0; double bestd = -1;
+  for (int a = 0; a < 3; a++) { double v = fabs(dot3(Ai[a], nref)); if (v > bestd) { bestd = v; ia = a; } }
+  double isg = dot3(Ai[ia], nref) > 0 ? -1.0 : 1.0;
+  int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3;
+  int r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
+  double fc[3];
+  for (int k = 0; k < 3; k++) fc[k] = pi_[k] + isg * si[ia] * Ai[ia][k] - pr[k];
+  double px[16], py[16];
+  const double sgn[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  for (int c = 0; c < 4; c++) {
+    double vz[3];
+    for (int k = 0; k < 3; k++) vz[k] = fc[k] + sgn[c][0] * si[i1] * Ai[i1][k] + sgn[c][1] * si[i2] * Ai[i2][k];
+    px[c] = dot3(vz, Ar[r1]); py[c] = dot3(vz, Ar[r2]);
+  }
+  double o_n = dot3(fc, nref);
+  double u1 = dot3(Ai[i1], nref), u2 = dot3(Ai[i2], nref);
+  double a11 = dot3(Ai[i1], Ar[r1]), a12 = dot3(Ai[i1], Ar[r2]), a21 = dot3(Ai[i2], Ar[r1]), a22 = dot3(Ai[i2], Ar[r2]);
+  double det = a11 * a22 - a12 * a21;
+  double fx = dot3(fc, Ar[r1]), fy = dot3(fc, Ar[r2]);
+  int n = clip_poly(px, py, 4, sr[r1], sr[r2]);
+  int cnt = 0;
+  for (int c = 0; c < n && cnt < 8; c++) {
+    double dx = px[c] - fx, dy = py[c] - fy, h;
+    if (fabs(det) > 1e-12) {
+      double al = (dx * a22 - dy * a21) / det, be = (dy * a11 - dx * a12) / det;
+      h = o_n + al * u1 + be * u2;
+    } else h = o_n;
+    double depth = sr[ax] - h;
+    if (-depth >= 0) continue;
+    double pt[3];
+    for (int k = 0; k < 3; k++) pt[k] = pr[k] + px[c] * Ar[r1][k] + py[c] * Ar[r2][k] + (h + 0.5 * depth) * nref[k];
+    int dup = 0;
+    for (int e = 0; e < cnt; e++) {
+      double q[3] = {pt[0] - out[e].pos[0], pt[1] - out[e].pos[1], pt[2] - out[e].pos[2]};
+      if (dot3(q, q) < 1e-20) dup = 1;
+    }
+    if (dup) continue;
+    for (int k = 0; k < 3; k++) { out[cnt].pos[k] = pt[k]; out[cnt].normal[k] = bn[k]; }
+    out[cnt].dist = -depth;
+    cnt++;
+  }
+  return cnt;
+}
+
+__device__ void geom_pose(const double* xpos, const double* xmat, const DevModel* __restrict__ m, int g, double* pos, double* mat) {
+  int b = m->d.geom_body[g];
+  const double* gp = m->d.geom_pos[g];
+  const double* gm = m->d.geom_mat[g];
+  if (b < 0) {
+    for (int k = 0; k < 3; k++) pos[k] = gp[k];
+    for (int k = 0; k < 9; k++) mat[k] = gm[k];
+  } else {
+    const double* R = xmat + b * 9;
+    for (int r = 0; r < 3; r++) {
+      pos[r] = xpos[b * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
+      for (int c = 0; c < 3; c++) mat[3 * r + c] = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c];
+    }
+  }
+}
+
+template <class S>
+__device__ void collide(S& s, const DevModel* __restrict__ m, int lane, int nba) {
+  RawCon rc[8];
+  int n = 0;
+  if (lane < m->d.npair) {
+    int g1 = m->d.pair_g1[lane], g2 = m->d.pair_g2[lane];
+    int b1 = m->d.geom_body[g1], b2 = m->d.geom_body[g2];
+    bool skip = (nba <= CUBE) && (b1 == CUBE || b2 == CUBE);
+    if (!skip) {
+      double p1[3], R1[9], p2[3], R2[9];
+      geom_pose(s.xpos, s.xmat, m, g1, p1, R1);
+      geom_pose(s.xpos, s.xmat, m, g2, p2, R2);
+      double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+      if (m->d.geom_type[g1] == 0) {
+        double nrm[3] = {R1[2], R1[5], R1[8]};
+        if (dot3(dif, nrm) <= m->d.geom_rbound[g2]) n = plane_box(rc, p1, R1, p2, R2, m->d.geom_size[g2]);
+      } else {
+        double bound = m->d.geom_rbound[g1] + m->d.geom_rbound[g2];
+        if (dot3(dif, dif) <= bound * bound) n = box_box(rc, p1, R1, m->d.geom_size[g1], p2, R2, m->d.geom_size[g2]);
+      }
+    }
+  }
+  // exclusive prefix over lanes (pair order == contact order)
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+  int base = incl - n;
+  int total = __shfl_sync(FULLMASK, incl, 31);
+  for (int c = 0; c < n; c++) {
+    int idx = base + c;
+    if (idx >= MAXCON) break;
+    s.cdist[idx] = rc[c].dist;
+    s.cpair[idx] = lane;
+    double f[9];
+    f[0] = rc[c].normal[0]; f[1] = rc[c].normal[1]; f[2] = rc[c].normal[2];
+    // mju_makeFrame
+    double nn = sqrt(dot3(f, f));
+    if (nn < MINVAL) { f[0] = 1; f[1] = f[2] = 0; } else { f[0] /= nn; f[1] /= nn; f[2] /= nn; }
+    f[3] = f[4] = f[5] = 0;
+    if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
+    double t = dot3(f, f + 3);
+    f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
+    nn = sqrt(dot3(f + 3, f + 3));
+    if (nn < MINVAL) { f[3] = 1; f[4] = f[5] = 0; } else { f[3] /= nn; f[4] /= nn; f[5] /= nn; }
+    cross3(f + 6, f, f + 3);
+    for (int k = 0; k < 9; k++) s.cframe[idx * 9 + k] = f[k];
+    for (int k = 0; k < 3; k++) s.cpos[idx * 3 + k] = rc[c].pos[k];
+  }
+  if (lane == 0) {
+    if (total > MAXCON) { s.overflow += total - MAXCON; total = MAXCON; }
+    s.ncon = total;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ double impedance(const double* solimp_in, double pos) {
+  double s0 = fmin(MAXIMP, fmax(MINIMP, solimp_in[0])), s1 = fmin(MAXIMP, fmax(MINIMP, solimp_in[1]));
+  double s2 = fmax(0.0, solimp_in[2]), s3 = fmin(MAXIMP, fmax(MINIMP, solimp_in[3])), s4 = fmax(1.0, solimp_in[4]);
+  if (s0 == s1 || s2 <= MINVAL) return 0.5 * (s0 + s1);
+  double x = fabs(pos / s2);
+  if (x >= 1 || x <= 0) return (x >= 1 ? s1 : s0);
+  double y;
+  if (s4 == 1) y = x;
+  else if (x <= s3) { double a = 1 / pow(s3, s4 - 1); y = a * pow(x, s4); }
+  else { double b = 1 / pow(1 - s3, s4 - 1); y = 1 - b * pow(1 - x, s4); }
+  return s0 + y * (s1 - s0);
+}
+
+// row_params(): R, D and the reference-acceleration coefficients of one row.  For the rows of a pyramidal
+// contact `diag` is the first row's diagApprox and `pyr_mu` > 0 (R = 2 mu^2 R_first); otherwise pyr_mu = 0.
+template <class S>
+__device__ __forceinline__ void row_params(S& s, int r, double timestep, const double* solref_in, const double* solimp, double pos, double diag, double pyr_mu, int type) {
+  double sr0 = solref_in[0], sr1 = solref_in[1];
+  if (sr0 > 0) sr0 = fmax(sr0, 2 * timestep);
+  double imp = impedance(solimp, pos);
+  double R = fmax(MINVAL, (1 - imp) * diag / imp);
+  if (pyr_mu > 0) R = 2 * pyr_mu * pyr_mu * R;
+  double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
+  double K, B;
+  if (sr0 > 0) { K = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmax(MINVAL, dmax * sr0); }
+  else { K = -sr0 / fmax(MINVAL, dmax * dmax); B = -sr1 / fmax(MINVAL, dmax); }
+  s.eD[r] = 1 / R;
+  s.ekp[r] = K * imp * pos;
+  s.eB[r] = B;
+  s.etype[r] = type;
+}
+
+// point Jacobian column of dof j for a world point attached to body b (0 if j does not move b)
+template <class S>
+__device__ __forceinline__ void jac_col(const S& s, const DevModel* __restrict__ m, int b, int j, const double* pt, double* lin, double* rot) {
+  if (b >= 0 && ((m->d.ancmask[b] >> j) & 1u)) {
+    const double* cd = s.cdof + j * 6;
+    double off[3];
+    if (b == CUBE) { off[0] = pt[0] - s.refcube[0]; off[1] = pt[1] - s.refcube[1]; off[2] = pt[2] - s.refcube[2]; }
+    else { off[0] = pt[0] - m->d.ref_robot[0]; off[1] = pt[1] - m->d.ref_robot[1]; off[2] = pt[2] - m->d.ref_robot[2]; }
+    double t[3];
+    cross3(t, cd, off);
+    lin[0] = cd[3] + t[0]; lin[1] = cd[4] + t[1]; lin[2] = cd[5] + t[2];
+    rot[0] = cd[0]; rot[1] = cd[1]; rot[2] = cd[2];
+  } else {
+    lin[0] = lin[1] = lin[2] = 0; rot[0] = rot[1] = rot[2] = 0;
+  }
+}
+
+// make_rows(): equality (7 rows), joint limits, pyramidal contact rows; J dense [nefc][LD].
+template <int NEFC, class S>
+__device__ void make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
+  const double h = m->d.timestep;
+  // --- connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1) -> stash in buf
+  if (lane < 4) {
+    int e = lane >> 1, side = lane & 1;
+    int b = side ? m->d.con_body2[e] : m->d.con_body1[e];
+    const double* a = side ? m->d.con_anchor2[e] : m->d.con_anchor1[e];
+    const double* R = s.xmat + b * 9;
+    for (int r = 0; r < 3; r++) s.buf[lane * 3 + r] = s.xpos[b * 3 + r] + R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
+  }
+  __syncwarp();
+  for (int w = lane; w < 6 * NV; w += 32) {
+    int row = w / NV, j = w % NV;
+    int e = row / 3, r = row % 3;
+    double l1[3], l2[3], rt[3];
+    jac_col(s, m, m->d.con_body1[e], j, s.buf + (2 * e) * 3, l1, rt);
+    jac_col(s, m, m->d.con_body2[e], j, s.buf + (2 * e + 1) * 3, l2, rt);
+    s.J[row * LD + j] = l1[r] - l2[r];
+  }
+  for (int j = lane; j < NV; j += 32) {
+    double v = 0;
+    if (j == m->d.jeq_dof1) v = 1;
+    if (j == m->d.jeq_dof2) {
+      double dif = s.qpos[j] - m->d.qpos0[j];
+      const double* pc = m->d.jeq_polycoef;
+      v = -(pc[1] + 2 * pc[2] * dif + 3 * pc[3] * dif * dif + 4 * pc[4] * dif * dif * dif);
+    }
+    s.J[6 * LD + j] = v;
+  }
+  if (lane < 6) {
+    int e = lane / 3, r = lane % 3;
+    double pos = s.buf[(2 * e) * 3 + r] - s.buf[(2 * e + 1) * 3 + r];
+    row_params(s, lane, h, m->d.con_solref[e], m->d.con_solimp[e], pos, m->d.con_diag[e], 0.0, 0);
+  } else if (lane == 6) {
+    int d1 = m->d.jeq_dof1, d2 = m->d.jeq_dof2;
+    double p1 = s.qpos[d1] - m->d.qpos0[d1], dif = s.qpos[d2] - m->d.qpos0[d2];
+    const double* pc = m->d.jeq_polycoef;
+    double pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
+    row_params(s, 6, h, m->d.jeq_solref, m->d.jeq_solimp, pos, m->d.jeq_diag, 0.0, 0);
+  }
+  // --- limits: lane j < 12, lower then upper (both can not be active for a positive-width range)
+  int lim = 0; double dist = 0; double sgn = 0;
+  if (lane < NH && m->d.jnt_limited[lane]) {
+    double v = s.qpos[lane];
+    double dl = v - m->d.jnt_range[lane][0], du = m->d.jnt_range[lane][1] - v;
+    if (dl < 0) { lim = 1; dist = dl; sgn = 1; }
+    else if (du < 0) { lim = 1; dist = du; sgn = -1; }
+  }
+  unsigned bal = __ballot_sync(FULLMASK, lim);
+  int nl = __popc(bal);
+  int ne = 7;
+  if (lim) {
+    int r = ne + __popc(bal & ((1u << lane) - 1));
+    for (int j = 0; j < NV; j++) s.J[r * LD + j] = (j == lane ? sgn : 0.0);
+    row_params(s, r, h, m->d.jnt_solref[lane], m->d.jnt_solimp[lane], dist, m->d.dof_invweight0[lane], 0.0, 1);
+  }
+  // --- contacts: row offsets (lane 0), then (contact, dof) items
+  if (lane == 0) {
+    int r = ne + nl, nc = 0;
+    for (int c = 0; c < s.ncon; c++) {
+      int rows = 2 * (m->pair[s.cpair[c]].dim - 1);
+      if (r + rows > NEFC) { s.overflow += s.ncon - c; break; }
+      s.cefc[c] = r; r += rows; nc++;
+    }
+    s.ncon = nc; s.nefc = r; s.ne = ne; s.nl = nl;
+  }
+  __syncwarp();
+  int ncon = s.ncon;
+  for (int w = lane; w < ncon * NV; w += 32) {
+    int c = w / NV, j = w % NV;
+    const PairParam& pp = m->pair[s.cpair[c]];
+    int b1 = m->d.geom_body[pp.g1], b2 = m->d.geom_body[pp.g2];
+    const double* pt = s.cpos + c * 3;
+    const double* f = s.cframe + c * 9;
+    double l1[3], r1[3], l2[3], r2[3];
+    jac_col(s, m, b1, j, pt, l1, r1);
+    jac_col(s, m, b2, j, pt, l2, r2);
+    double dl[3] = {l2[0] - l1[0], l2[1] - l1[1], l2[2] - l1[2]}, dr[3] = {r2[0] - r1[0], r2[1] - r1[1], r2[2] - r1[2]};
+    double Jn = dot3(f, dl), Jt1 = dot3(f + 3, dl), Jt2 = dot3(f + 6, dl), Jr = dot3(f, dr);
+    int r0 = s.cefc[c];
+    double mu = pp.friction[0];
+    s.J[(r0 + 0) * LD + j] = Jn + mu * Jt1;
+    s.J[(r0 + 1) * LD + j] = Jn + (-mu) * Jt1;
+    s.J[(r0 + 2) * LD + j] = Jn + mu * Jt2;
+    s.J[(r0 + 3) * LD + j] = Jn + (-mu) * Jt2;
+    if (pp.dim == 4) {
+      double mt = pp.friction[1];
+      s.J[(r0 + 4) * LD + j] = Jn + mt * Jr;
+      s.J[(r0 + 5) * LD + j] = Jn + (-mt) * Jr;
+    }
+  }
+  for (int w = lane; w < ncon * 6; w += 32) {
+    int c = w / 6, k = w % 6;
+    const PairParam& pp = m->pair[s.cpair[c]];
+    if (k >= 2 * (pp.dim - 1)) continue;
+    double mu = pp.friction[0];
+    double diag_first = pp.tran + mu * mu * pp.tran;
+    row_params(s, s.cefc[c] + k, h, pp.solref, pp.solimp, s.cdist[c], diag_first, mu / sqrt(m->d.impratio), 1);
+  }
+  __syncwarp();
+}
+
+// velocity_rne(): cvel, cdof_dot, bias forces (RNE with zero qacc), efc reference accelerations.
+template <class S>
+__device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+  // cvel[b] = sum over ancestor dofs (ascending) of cdof_j * qvel_j
+  for (int w = lane; w < nba * 6; w += 32) {
+    int b = w / 6, c = w % 6;
+    unsigned mask = m->d.ancmask[b];
+    double acc = 0;
+    while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j]; }
+    s.cvel[w] = acc;
+  }
+  __syncwarp();
+  if (lane < nva) {
+    int j = lane;
+    double vel[6];
+    if (j < NH) {
+      int p = m->d.parent[j];
+      for (int c = 0; c < 6; c++) vel[c] = (p >= 0 ? s.cvel[p * 6 + c] : 0.0);
+      cross_motion(s.cdof_dot + j * 6, vel, s.cdof + j * 6);
+    } else if (j < 15) {
+      for (int c = 0; c < 6; c++) s.cdof_dot[j * 6 + c] = 0;
+    } else {
+      vel[0] = vel[1] = vel[2] = 0;
+      for (int c = 3; c < 6; c++) vel[c] = s.cdof[12 * 6 + c] * s.qvel[12] + s.cdof[13 * 6 + c] * s.qvel[13] + s.cdof[14 * 6 + c] * s.qvel[14];
+      cross_motion(s.cdof_dot + j * 6, vel, s.cdof + j * 6);
+    }
+  }
+  __syncwarp();
+  for (int w = lane; w < nba * 6; w += 32) {
+    int b = w / 6, c = w % 6;
+    unsigned mask = m->d.ancmask[b];
+    double acc = (c >= 3 ? -m->d.gravity[c - 3] : 0.0);
+    while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j]; }
+    s.cacc[w] = acc;
+  }
+  __syncwarp();
+  double f[6];
+  if (lane < nba) {
+    double t[6], t1[6];
+    mul_inert_vec(f, s.cinert + lane * 10, s.cacc + lane * 6);
+    mul_inert_vec(t, s.cinert + lane * 10, s.cvel + lane * 6);
+    cross_force(t1, s.cvel + lane * 6, t);
+    for (int c = 0; c < 6; c++) f[c] += t1[c];
+  }
+  __syncwarp();
+  if (lane < nba) for (int c = 0; c < 6; c++) s.cacc[lane * 6 + c] = f[c];  // cacc now holds cfrc_body
+  __syncwarp();
+  for (int w = lane; w < nba * 6; w += 32) {
+    int b = w / 6, c = w % 6;
+    int e = b + m->d.subtree_size[b];
+    if (e > nba) e = nba;
+    double acc = 0;
+    for (int k = e - 1; k >= b; k--) acc += s.cacc[k * 6 + c];
+    s.cvel[w] = acc;  // cvel now holds the subtree-accumulated cfrc
+  }
+  __syncwarp();
+  if (lane < nva) {
+    const double* a = s.cdof + lane * 6;
+    const double* b = s.cvel + m->d.dof_body[lane] * 6;
+    s.qfrc_bias[lane] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+  }
+  // efc_vel and aref
+  for (int r = lane; r < s.nefc; r += 32) {
+    const double* Jr = s.J + r * LD;
+    double v = 0;
+    for (int k = 0; k < nva; k++) v += Jr[k] * s.qvel[k];
+    s.earef[r] = -s.eB[r] * v - s.ekp[r];
+  }
+  __syncwarp();
+}
+
+// actuation(): affine PD "general" actuators with ctrl and force clamps; then qfrc_smooth.
+template <class S>
+__device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane, int nva) {
+  double force = 0;
+  if (lane < NU) {
+    const double* mom = m->d.act_moment[lane];
+    double len = 0, vel = 0;
+    for (int i = 0; i < NH; i++) { double c = mom[i]; if (c != 0) { len += c * s.qpos[i]; vel += c * s.qvel[i]; } }
+    double ctrl = s.ctrl[lane];
+    if (m->d.act_ctrllimited[lane]) ctrl = fmax(m->d.act_ctrlrange[lane][0], fmin(m->d.act_ctrlrange[lane][1], ctrl));
+    const double* bp = m->d.act_bias[lane];
+    force = m->d.act_gain[lane] * ctrl + bp[0] + bp[1] * len + bp[2] * vel;
+    if (m->d.act_forcelimited[lane]) force = fmax(m->d.act_forcerange[lane][0], fmin(m->d.act_forcerange[lane][1], force));
+  }
+  double qa = 0;
+#pragma unroll
+  for (int a = 0; a < NU; a++) {
+    double fa = __shfl_sync(FULLMASK, force, a);
+    if (lane < NV) qa += m->d.act_moment[a][lane] * fa;
+  }
+  if (lane < nva) {
+    s.qfrc_act[lane] = qa;
+    s.qfrc_smooth[lane] = -m->d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// newton(): primal Newton solver with exact line search over the piecewise-quadratic cost (pyramidal cones).
+template <int NEFC, class S>
+struct Newton {
+  S& s; const DevModel* __restrict__ m; int lane, nva, nefc;
+  double gauss, cost, qg0, qg1, qg2;
+  double qa[3], qb[3], qc[3];  // per-lane quadratic coefficients of rows lane, lane+32, lane+64
+  int lsn;
+
+  __device__ double mulM_row(const double* v) const {
+    double acc = 0;
+    if (lane < nva) { const double* r = s.M + lane * LD; for (int k = 0; k < nva; k++) acc += r[k] * v[k]; }
+    return acc;
+  }
+  __device__ double jdot(int r, const double* v) const {
+    const double* Jr = s.J + r * LD;
+    double acc = 0;
+    for (int k = 0; k < nva; k++) acc += Jr[k] * v[k];
+    return acc;
+  }
+  // constraint cost at jar = J*x - aref for a trial vector x (no side effects)
+  __device__ double cost_of(const double* x) const {
+    double c = 0;
+    for (int r = lane; r < nefc; r += 32) {
+      double jar = jdot(r, x) - s.earef[r];
+      if (s.etype[r] == 0 || jar < 0) c += 0.5 * s.eD[r] * jar * jar;
+    }
+    return warp_sum(c);
+  }
+  // cost, gradient; optionally Hessian factor + Newton direction
+  __device__ void update(bool hessian) {
+    // constraint forces, cost
+    double c = 0;
+    for (int r = lane; r < nefc; r += 32) {
+      double jar = s.eJaref[r];
+      bool act = (s.etype[r] == 0 || jar < 0);
+      double f = act ? -s.eD[r] * jar : 0.0;
+      s.eJv[r] = f;  // eJv temporarily holds efc_force
+      if (act) c += 0.5 * s.eD[r] * jar * jar;
+    }
+    double g = 0;
+    if (lane < nva) g = 0.5 * (s.Ma[lane] - s.qfrc_smooth[lane]) * (s.qacc[lane] - s.qacc_smooth[lane]);
+    __syncwarp();
+    gauss = warp_sum(g);
+    cost = gauss + warp_sum(c);
+    if (lane < nva) {
+      double q = 0;
+      for (int r = 0; r < nefc; r++) q += s.J[r * LD + lane] * s.eJv[r];
+      s.qfrc_con[lane] = q;
+      s.grad[lane] = s.Ma[lane] - s.qfrc_smooth[lane] - q;
+    }
+    __syncwarp();
+    if (!hessian) return;
+    build_H();
+    chol(s.H, s.Hinv, nva, lane);
+    double mg = chol_solve(s.H, s.Hinv, nva, lane, lane < nva ? s.grad[lane] : 0.0);
+    if (lane < nva) { s.Mgrad[lane] = mg; s.search[lane] = -mg; }
+    __syncwarp();
+  }
+  // H = M + J' diag(D * active) J, lower triangle, 3x3 register tiles (21 lanes busy for 18 dofs)
+  __device__ void build_H() {
+    int nt = nva / 3;
+    int ti = -1, tj = -1;
+    {
+      int t = lane, i = 0;
+      while (i < nt && t > i) { t -= i + 1; i++; }
+      if (i < nt) { ti = i; tj = t; }
+    }
+    if (ti >= 0) {
+      double acc[9];
+      const double* Mi = s.M + (3 * ti) * LD + 3 * tj;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) acc[3 * a + b] = Mi[a * LD + b];
+      for (int r = 0; r < nefc; r++) {
+        if (!(s.etype[r] == 0 || s.eJaref[r] < 0)) continue;
+        const double* Jr = s.J + r * LD;
+        double D = s.eD[r];
+        double ji0 = D * Jr[3 * ti], ji1 = D * Jr[3 * ti + 1], ji2 = D * Jr[3 * ti + 2];
+        double jj0 = Jr[3 * tj], jj1 = Jr[3 * tj + 1], jj2 = Jr[3 * tj + 2];
+        acc[0] += ji0 * jj0; acc[1] += ji0 * jj1; acc[2] += ji0 * jj2;
+        acc[3] += ji1 * jj0; acc[4] += ji1 * jj1; acc[5] += ji1 * jj2;
+        acc[6] += ji2 * jj0; acc[7] += ji2 * jj1; acc[8] += ji2 * jj2;
+      }
+      double* Hi = s.H + (3 * ti) * LD + 3 * tj;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) Hi[a * LD + b] = acc[3 * a + b];
+    }
+    __syncwarp();
+  }
+  struct Pt { double alpha, cost, d0, d1; };
+  __device__ void ls_eval(Pt& p) {
+    double a = p.alpha, q0 = 0, q1 = 0, q2 = 0;
+#pragma unroll
+    for (int t = 0; t < (NEFC + 31) / 32; t++) {
+      int r = lane + 32 * t;
+      if (r < nefc) {
+        if (s.etype[r] == 0 || s.eJaref[r] + a * s.eJv[r] < 0) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
+      }
+    }
+    q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
+    p.cost = a * a * q2 + a * q1 + q0;
+    p.d0 = 2 * a * q2 + q1;
+    p.d1 = 2 * q2;
+    if (p.d1 <= 0) p.d1 = MINVAL;
+    lsn++;
+  }
+  __device__ double line_search(double scale) {
+    double sn = 0;
+    if (lane < nva) sn = s.search[lane] * s.search[lane];
+    double snorm = sqrt(warp_sum(sn));
+    if (snorm < MINVAL) return 0;
+    double gtol = m->d.tolerance * m->d.ls_tolerance * snorm / scale;
+    double mv = mulM_row(s.search);
+    if (lane < nva) s.Mv[lane] = mv;
+    for (int r = lane; r < nefc; r += 32) s.eJv[r] = jdot(r, s.search);
+    double g1 = 0, g2 = 0;
+    if (lane < nva) { g1 = s.search[lane] * (s.Ma[lane] - s.qfrc_smooth[lane]); g2 = s.search[lane] * mv; }
+    qg0 = gauss; qg1 = warp_sum(g1); qg2 = 0.5 * warp_sum(g2);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < (NEFC + 31) / 32; t++) {
+      int r = lane + 32 * t;
+      if (r < nefc) {
+        double D = s.eD[r], ja = s.eJaref[r], jv = s.eJv[r];
+        qa[t] = 0.5 * D * ja * ja; qb[t] = D * ja * jv; qc[t] = 0.5 * D * jv * jv;
+      } else { qa[t] = qb[t] = qc[t] = 0; }
+    }
+    const int lsmax = m->d.ls_iterations;
+    Pt p0, p1, p2, pmid, p1n, p2n;
+    p0.alpha = 0; ls_eval(p0);
+    p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(p1);
+    if (p0.cost < p1.cost) p1 = p0;
+    if (fabs(p1.d0) < gtol) return p1.alpha;
+    int dir = p1.d0 < 0 ? 1 : -1, iter = 0, p2update = 0;
+    p2 = p1;
+    while (p1.d0 * dir <= -gtol && iter < lsmax) {
+      p2 = p1; p2update = 1;
+      p1.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1); iter++;
+      if (fabs(p1.d0) < gtol) return p1.alpha;
+    }
+    if (iter >= lsmax || !p2update) return p1.alpha;
+    p2n = p1;
+    p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n);
+    while (iter < lsmax) {
+      pmid.alpha = 0.5 * (p1.alpha + p2.alpha); ls_eval(pmid); iter++;
+      Pt* cand[3] = {&p1n, &p2n, &pmid};
+      int besti = -1;
+      for (int i = 0; i < 3; i++)
+        if (fabs(cand[i]->d0) < gtol && (besti < 0 || cand[i]->cost < cand[besti]->cost)) besti = i;
+      if (besti >= 0) return cand[besti]->alpha;
+      int b1 = 0, b2 = 0;
+      for (int i = 0; i < 3; i++) {
+        Pt c = *cand[i];
+        if (c.d0 * dir < 0 && (c.alpha - p2.alpha) * dir > 0 && (p1.alpha - c.alpha) * dir > 0) { p2 = c; b2 = 1; }
+        else if (c.d0 * dir > 0 && (p1.alpha - c.alpha) * dir > 0 && (c.alpha - p2.alpha) * dir > 0) { p1 = c; b1 = 1; }
+      }
+      if (!b1 && !b2) break;
+      if (b1) { p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n); }
+      if (b2) { p2n.alpha = p2.alpha - p2.d0 / p2.d1; ls_eval(p2n); }
+    }
+    return (p1.cost < p2.cost ? p1.alpha : p2.alpha);
+  }
+
+  __device__ void solve() {
+    lsn = 0;
+    const double scale = 1.0 / (m->d.meaninertia * (double)NV);
+    // warmstart(): better of qacc_warmstart and qacc_smooth
+    {
+      double cw = cost_of(s.warm);
+      double ma = mulM_row(s.warm), g = 0;
+      if (lane < nva) g = 0.5 * (ma - s.qfrc_smooth[lane]) * (s.warm[lane] - s.qacc_smooth[lane]);
+      cw += warp_sum(g);
+      double cs = cost_of(s.qacc_smooth);
+      bool use_smooth = cw > cs;
+      if (lane < nva) {
+        s.qacc[lane] = use_smooth ? s.qacc_smooth[lane] : s.warm[lane];
+        s.Ma[lane] = use_smooth ? s.qfrc_smooth[lane] : ma;  // M*qacc_smooth == qfrc_smooth up to rounding; recomputed below
+      }
+      __syncwarp();
+      double ma2 = mulM_row(s.qacc);
+      if (lane < nva) s.Ma[lane] = ma2;
+    }
+    for (int r = lane; r < nefc; r += 32) s.eJaref[r] = jdot(r, s.qacc) - s.earef[r];
+    __syncwarp();
+    update(true);
+    int iter = 0;
+    const int maxiter = m->d.iterations;
+    while (iter < maxiter) {
+      double alpha = line_search(scale);
+      if (alpha == 0) break;
+      if (lane < nva) { s.qacc[lane] += alpha * s.search[lane]; s.Ma[lane] += alpha * s.Mv[lane]; }
+      for (int r = lane; r < nefc; r += 32) s.eJaref[r] += alpha * s.eJv[r];
+      __syncwarp();
+      double oldcost = cost;
+      update(false);
+      iter++;
+      double gn = 0;
+      if (lane < nva) gn = s.grad[lane] * s.grad[lane];
+      double improvement = scale * (oldcost - cost), gradient = scale * sqrt(warp_sum(gn));
+      if (improvement < m->d.tolerance || gradient < m->d.tolerance) break;
+      // continue: Hessian at the new point
+      build_H();
+      chol(s.H, s.Hinv, nva, lane);
+      double mg = chol_solve(s.H, s.Hinv, nva, lane, lane < nva ? s.grad[lane] : 0.0);
+      if (lane < nva) { s.Mgrad[lane] = mg; s.search[lane] = -mg; }
+      __syncwarp();
+    }
+    if (lane == 0) s.iters += iter;
+    if (lane < nva) s.warm[lane] = s.qacc[lane];
+    __syncwarp();
+  }
+};
+
+// forward(): everything mj_forward does for this model.
+template <int NEFC, class S>
+__device__ void forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+  fk(s, m, lane, nba);
+  cinert_cdof(s, m, lane, nba, nva);
+  crb_mass(s, m, lane, nba, nva);
+  for (int w = lane; w < nva * LD; w += 32) s.L[w] = s.M[w];
+  __syncwarp();
+  chol(s.L, s.Linv, nva, lane);
+  collide(s, m, lane, nba);
+  make_rows<NEFC>(s, m, lane, nva);
+  velocity_rne(s, m, lane, nba, nva);
+  actuation_smooth(s, m, lane, nva);
+  double qs = chol_solve(s.L, s.Linv, nva, lane, lane < nva ? s.qfrc_smooth[lane] : 0.0);
+  if (lane < nva) s.qacc_smooth[lane] = qs;
+  __syncwarp();
+  Newton<NEFC, S> nw{s, m, lane, nva, s.nefc};
+  nw.solve();
+}
+
+// euler(): (M + h*diag(damping))^-1 (qfrc_smooth + qfrc_constraint), semi-implicit advance.
+template <class S>
+__device__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
+  const double h = m->d.timestep;
+  for (int w = lane; w < nva * LD; w += 32) s.L[w] = s.M[w];
+  __syncwarp();
+  if (lane < nva) s.L[lane * LD + lane] += h * m->d.damping[lane];
+  __syncwarp();
+  chol(s.L, s.Linv, nva, lane);
+  double qacc = chol_solve(s.L, s.Linv, nva, lane, lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
+  if (lane < nva) s.qvel[lane] += h * qacc;
+  __syncwarp();
+  if (lane < NH) s.qpos[lane] += h * s.qvel[lane];
+  else if (lane < 15 && nva > NH) s.qpos[lane] += h * s.qvel[lane];
+  else if (lane == 15 && nva > NH) {
+    double ax[3] = {s.qvel[15], s.qvel[16], s.qvel[17]};
+    double n = sqrt(dot3(ax, ax));
+    if (n < MINVAL) { ax[0] = 1; ax[1] = ax[2] = 0; } else { ax[0] /= n; ax[1] /= n; ax[2] /= n; }
+    double ang = h * n;
+    double qr[4];
+    if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
+    else { double sn, cs; sincos(0.5 * ang, &sn, &cs); qr[0] = cs; qr[1] = ax[0] * sn; qr[2] = ax[1] * sn; qr[3] = ax[2] * sn; }
+    double* q = s.qpos + 15;
+    double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double a[4];
+    if (nq < MINVAL) { a[0] = 1; a[1] = a[2] = a[3] = 0; } else { a[0] = q[0] / nq; a[1] = q[1] / nq; a[2] = q[2] / nq; a[3] = q[3] / nq; }
+    q[0] = a[0] * qr[0] - a[1] * qr[1] - a[2] * qr[2] - a[3] * qr[3];
+    q[1] = a[0] * qr[1] + a[1] * qr[0] + a[2] * qr[3] - a[3] * qr[2];
+    q[2] = a[0] * qr[2] - a[1] * qr[3] + a[2] * qr[0] + a[3] * qr[1];
+    q[3] = a[0] * qr[3] + a[1] * qr[2] - a[2] * qr[1] + a[3] * qr[0];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG: one stream per env, key = seed, counter = (env, draw index)
+__device__ __forceinline__ void philox_round(uint32_t* c, uint32_t k0, uint32_t k1) {
+  uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ double philox_uniform(uint64_t seed, uint32_t env, unsigned long long& ctr) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), env, 0x6d79636fu};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; i++) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  ctr++;
+  uint64_t bits = ((uint64_t)c[0] << 21) | (uint64_t)(c[1] >> 11);
+  return (double)bits * (1.0 / 9007199254740992.0);
+}
+// _sample_goal (mycobot.py:238-243, utils.py:14-21): same draw structure, device streams
+__device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& cfg, uint64_t seed, uint32_t env, unsigned long long& ctr, double* g) {
+  g[0] = -0.12 + (0.12 - (-0.12)) * philox_uniform(seed, env, ctr);
+  g[1] = -0.06 + (0.06 - (-0.06)) * philox_uniform(seed, env, ctr);
+  g[2] = m->d.height_offset;
+  if (cfg.target_in_the_air) {
+    if (philox_uniform(seed, env, ctr) < 0.5) g[2] += 0.0 + (0.1 - 0.0) * philox_uniform(seed, env, ctr);
+  }
+}
+
+// observation (mycobot.py:342-388): written from the frames currently in shared memory (stale by one
+// substep after a step, fresh after forward), qpos / qvel current.
+template <class S>
+__device__ void write_obs(S& s, const DevModel* __restrict__ m, const mcb_task_cfg& cfg, int lane, int env, double* obs, double* ag, double* dg, double* ag_out3) {
+  const double dt = cfg.frame_skip * m->d.timestep;
+  int eb = m->d.eef_body;
+  const double* R = s.xmat + eb * 9;
+  const double* ep = m->d.eef_pos;
+  double grip[3], gvel[3] = {0, 0, 0};
+  for (int r = 0; r < 3; r++) grip[r] = s.xpos[eb * 3 + r] + R[3 * r] * ep[0] + R[3 * r + 1] * ep[1] + R[3 * r + 2] * ep[2];
+  {
+    unsigned mask = m->d.ancmask[eb];
+    double off[3] = {grip[0] - m->d.ref_robot[0], grip[1] - m->d.ref_robot[1], grip[2] - m->d.ref_robot[2]};
+    while (mask) {
+      int j = __ffs(mask) - 1; mask &= mask - 1;
+      const double* cd = s.cdof + j * 6;
+      double t[3];
+      cross3(t, cd, off);
+      for (int r = 0; r < 3; r++) gvel[r] += (cd[3 + r] + t[r]) * s.qvel[j];
+    }
+  }
+  double o[MCB_OBS_OBJECT];
+  double achieved[3];
+  int nobs;
+  if (cfg.has_object) {
+    const double* Ro = s.xmat + CUBE * 9;
+    double op[3] = {s.xpos[CUBE * 3], s.xpos[CUBE * 3 + 1], s.xpos[CUBE * 3 + 2]};
+    double velp[3], velr[3];
+    // site at the body origin; jacp cols: e_k for the linear dofs, (Rcol_k x (site - refcube)) for rotational
+    double off[3] = {op[0] - s.refcube[0], op[1] - s.refcube[1], op[2] - s.refcube[2]};
+    for (int r = 0; r < 3; r++) { velp[r] = 0; velr[r] = 0; }
+    for (int j = 12; j < 18; j++) {
+      const double* cd = s.cdof + j * 6;
+      double t[3];
+      cross3(t, cd, off);
+      for (int r = 0; r < 3; r++) { velp[r] += (cd[3 + r] + t[r]) * s.qvel[j]; velr[r] += cd[r] * s.qvel[j]; }
+    }
+    double cy = sqrt(Ro[8] * Ro[8] + Ro[5] * Ro[5]);
+    double e0, e1, e2;
+    if (cy > 2.220446049250313e-16 * 4.0) { e2 = -atan2(Ro[1], Ro[0]); e1 = -atan2(-Ro[2], cy); e0 = -atan2(Ro[5], Ro[8]); }
+    else { e2 = -atan2(-Ro[3], Ro[4]); e1 = -atan2(-Ro[2], cy); e0 = 0.0; }
+    o[0] = grip[0]; o[1] = grip[1]; o[2] = grip[2];
+    o[3] = op[0]; o[4] = op[1]; o[5] = op[2];
+    o[6] = op[0] - grip[0]; o[7] = op[1] - grip[1]; o[8] = op[2] - grip[2];
+    o[9] = s.qpos[6]; o[10] = s.qpos[8];
+    o[11] = e0; o[12] = e1; o[13] = e2;
+    o[14] = velp[0] * dt - gvel[0] * dt; o[15] = velp[1] * dt - gvel[1] * dt; o[16] = velp[2] * dt - gvel[2] * dt;
+    o[17] = velr[0] * dt; o[18] = velr[1] * dt; o[19] = velr[2] * dt;
+    o[20] = gvel[0] * dt; o[21] = gvel[1] * dt; o[22] = gvel[2] * dt;
+    o[23] = s.qvel[6] * dt; o[24] = s.qvel[8] * dt;
+    achieved[0] = op[0]; achieved[1] = op[1]; achieved[2] = op[2];
+    nobs = MCB_OBS_OBJECT;
+  } else {
+    o[0] = grip[0]; o[1] = grip[1]; o[2] = grip[2];
+    o[3] = s.qpos[6]; o[4] = s.qpos[8];
+    o[5] = gvel[0] * dt; o[6] = gvel[1] * dt; o[7] = gvel[2] * dt;
+    o[8] = s.qvel[6] * dt; o[9] = s.qvel[8] * dt;
+    achieved[0] = grip[0]; achieved[1] = grip[1]; achieved[2] = grip[2];
+    nobs = MCB_OBS_REACH;
+  }
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < MCB_OBS_OBJECT; k++) if (lane == k && k < nobs) obs[(size_t)env * nobs + k] = o[k];
+  }
+  if (lane < 3) {
+    if (ag) ag[(size_t)env * 3 + lane] = achieved[lane];
+    if (dg) dg[(size_t)env * 3 + lane] = s.goal[lane];
+  }
+  ag_out3[0] = achieved[0]; ag_out3[1] = achieved[1]; ag_out3[2] = achieved[2];
+}
+
+template <class S>
+__device__ void load_state(S& s, const double* __restrict__ st, int lane) {
+  for (int w = lane; w < MCB_STATE_STRIDE; w += 32) {
+    double v = st[w];
+    if (w < 19) s.qpos[w] = v;
+    else if (w < 37) s.qvel[w - 19] = v;
+    else if (w < 44) s.ctrl[w - 37] = v;
+    else if (w < 62) s.warm[w - 44] = v;
+    else if (w < 65) s.goal[w - 62] = v;
+  }
+  __syncwarp();
+}
+template <class S>
+__device__ void store_state(const S& s, double* __restrict__ st, int lane) {
+  for (int w = lane; w < MCB_STATE_STRIDE; w += 32) {
+    double v = 0;
+    if (w < 19) v = s.qpos[w];
+    else if (w < 37) v = s.qvel[w - 19];
+    else if (w < 44) v = s.ctrl[w - 37];
+    else if (w < 62) v = s.warm[w - 44];
+    else if (w < 65) v = s.goal[w - 62];
+    st[w] = v;
+  }
+}
+
+// reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.
+template <int NEFC, class S>
+__device__ void reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
+  for (int w = lane; w < NQ; w += 32) s.qpos[w] = m->d.init_qpos[w];
+  if (lane < NV) s.qvel[lane] = 0;
+  if (lane < NU) s.ctrl[lane] = m->d.init_ctrl[lane];
+  __syncwarp();
+  forward<NEFC>(s, m, lane, nba, nva);
+  double oxy[2] = {m->d.initial_gripper_xpos[0], m->d.initial_gripper_xpos[1]};
+  double g[3];
+  if (lane == 0) {
+    if (a.cfg.has_object) {
+      if (a.inj_xy) { oxy[0] = a.inj_xy[(size_t)env * 2]; oxy[1] = a.inj_xy[(size_t)env * 2 + 1]; }
+      else {
+        int guard = 0;
+        while (sqrt((oxy[0] - m->d.initial_gripper_xpos[0]) * (oxy[0] - m->d.initial_gripper_xpos[0]) +
+                    (oxy[1] - m->d.initial_gripper_xpos[1]) * (oxy[1] - m->d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
+          sample_goal(m, a.cfg, a.seed, env, ctr, g);
+          oxy[0] = g[0]; oxy[1] = g[1];
+        }
+      }
+      s.qpos[12] = oxy[0]; s.qpos[13] = oxy[1];
+    }
+    if (a.inj_goal) { g[0] = a.inj_goal[(size_t)env * 3]; g[1] = a.inj_goal[(size_t)env * 3 + 1]; g[2] = a.inj_goal[(size_t)env * 3 + 2]; }
+    else {
+      int guard = 0;
+      sample_goal(m, a.cfg, a.seed, env, ctr, g);
+      while (sqrt((g[0] - oxy[0]) * (g[0] - oxy[0]) + (g[1] - oxy[1]) * (g[1] - oxy[1])) < 0.1 && guard++ < 10000) sample_goal(m, a.cfg, a.seed, env, ctr, g);
+    }
+    s.goal[0] = g[0]; s.goal[1] = g[1]; s.goal[2] = g[2];
+  }
+  __syncwarp();
+  forward<NEFC>(s, m, lane, nba, nva);
+}
+
+template <class S>
+__device__ void debug_dump(const S& s, const StepArgs& a, int lane, int nva) {
+  // layout (doubles): [0] nefc [1] ncon [2..] M(18*18) bias smooth qacc_smooth qacc xpos(39) xmat(117) J(nefc*18) aref D contact(7*ncon)
+  double* o = a.debug;
+  if (lane == 0) { o[0] = s.nefc; o[1] = s.ncon; o[2] = s.iters; o[3] = s.overflow; }
+  o += 4;
+  for (int w = lane; w < NV * NV; w += 32) o[w] = s.M[(w / NV) * LD + (w % NV)];
+  o += NV * NV;
+  if (lane < NV) { o[lane] = s.qfrc_bias[lane]; o[NV + lane] = s.qfrc_smooth[lane]; o[2 * NV + lane] = s.qacc_smooth[lane]; o[3 * NV + lane] = s.qacc[lane]; o[4 * NV + lane] = s.qfrc_con[lane]; }
+  o += 5 * NV;
+  for (int w = lane; w < NB * 3; w += 32) o[w] = s.xpos[w];
+  o += NB * 3;
+  for (int w = lane; w < NB * 9; w += 32) o[w] = s.xmat[w];
+  o += NB * 9;
+  for (int w = lane; w < s.nefc * NV; w += 32) o[w] = s.J[(w / NV) * LD + (w % NV)];
+  o += s.nefc * NV;
+  for (int w = lane; w < s.nefc; w += 32) { o[w] = s.earef[w]; o[s.nefc + w] = s.eD[w]; }
+  o += 2 * s.nefc;
+  for (int w = lane; w < s.ncon; w += 32) {
+    o[w * 7] = s.cdist[w];
+    for (int k = 0; k < 3; k++) { o[w * 7 + 1 + k] = s.cpos[w * 3 + k]; o[w * 7 + 4 + k] = s.cframe[w * 9 + k]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NEFC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) mcb_env_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef EnvS<NEFC> S;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS + wid;
+  if (env >= a.n_envs) return;
+  S& s = *reinterpret_cast<S*>(smem_raw + (size_t)wid * sizeof(S));
+  const DevModel* __restrict__ m = a.m;
+  const mcb_task_cfg& cfg = a.cfg;
+  const int nba = cfg.has_object ? NB : NB - 1;
+  const int nva = cfg.has_object ? NV : NH;
+
+  if (a.mode == MODE_RESET && a.mask && !a.mask[env]) return;
+
+  // zero the matrices whose sparsity pattern is static, and the bookkeeping
+  for (int w = lane; w < NV * LD; w += 32) { s.M[w] = 0; s.H[w] = 0; s.L[w] = 0; }
+  for (int w = lane; w < NB * 10; w += 32) { s.cinert[w] = 0; s.crb[w] = 0; }
+  for (int w = lane; w < NB * 9; w += 32) s.xmat[w] = 0;
+  for (int w = lane; w < NB * 3; w += 32) s.xpos[w] = 0;
+  for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
+  if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; }
+  if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
+  load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
+  unsigned long long ctr = a.rng_ctr[env];
+  double achieved[3];
+  int substeps = 0;
+
+  if (a.mode == MODE_RESET) {
+    reset_env<NEFC>(s, a, m, lane, env, nba, nva, ctr);
+    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+    if (lane == 0) { a.elapsed[env] = 0; a.ep_return[env] = 0; }
+    substeps = 2;
+  } else if (a.mode == MODE_FORWARD) {
+    forward<NEFC>(s, m, lane, nba, nva);
+    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+    if (a.debug && env == a.debug_env) debug_dump(s, a, lane, nva);
+    substeps = 1;
+  } else {
+    // MyCobotEnv.step, joint controller: ctrl = clip(action, -1, 1) widened to double (mycobot.py:133,192-193)
+    if (lane < NU) {
+      float act = a.actions[(size_t)env * NU + lane];
+      act = fminf(1.0f, fmaxf(-1.0f, act));
+      s.ctrl[lane] = (double)act;
+    }
+    __syncwarp();
+    for (int it = 0; it < cfg.frame_skip; it++) {
+      forward<NEFC>(s, m, lane, nba, nva);
+      euler(s, m, lane, nva);
+    }
+    substeps = cfg.frame_skip;
+    if (cfg.block_gripper) {  // _step_callback (mycobot.py:300-306)
+      if (lane == 0) { s.qpos[7] = 0; s.qpos[9] = 0; }
+      __syncwarp();
+      forward<NEFC>(s, m, lane, nba, nva);
+      substeps++;
+    }
+    int el = a.elapsed[env] + 1;
+    // observation goes to final_obs first if this env is about to auto-reset; decide after success
+    double ob_ag[3];
+    // compute success / reward from achieved goal (needs obs math) -- write into the regular outputs first
+    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, ob_ag);
+    double dx = ob_ag[0] - s.goal[0], dy = ob_ag[1] - s.goal[1], dz = ob_ag[2] - s.goal[2];
+    double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    bool succ = dist < cfg.distance_threshold;
+    bool term = succ, trunc = succ || (el >= cfg.max_episode_steps);
+    double rew = cfg.reward_type == 0 ? -(double)(dist > cfg.distance_threshold) : -dist;
+    double epret = a.ep_return[env] + rew;
+    if (lane == 0) {
+      if (cfg.reward_type == 0) ((float*)a.reward)[env] = -(float)(dist > cfg.distance_threshold);
+      else ((double*)a.reward)[env] = -dist;
+      a.terminated[env] = term; a.truncated[env] = trunc; a.success[env] = succ;
+    }
+    bool done = term || trunc;
+    if (done && lane == 0) {
+      atomicAdd(a.stats + 0, 1.0); atomicAdd(a.stats + 1, succ ? 1.0 : 0.0);
+      atomicAdd(a.stats + 2, epret); atomicAdd(a.stats + 3, (double)el);
+    }
+    if (done && cfg.auto_reset) {
+      if (a.final_obs) {
+        double dummy[3];
+        write_obs(s, m, cfg, lane, env, a.final_obs, nullptr, nullptr, dummy);
+      }
+      reset_env<NEFC>(s, a, m, lane, env, nba, nva, ctr);
+      write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+      el = 0; epret = 0; substeps += 2;
+    }
+    if (lane == 0) { a.elapsed[env] = el; a.ep_return[env] = epret; }
+  }
+  __syncwarp();
+  store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
+  if (lane == 0) {
+    a.rng_ctr[env] = ctr;
+    if (a.mode == MODE_STEP) atomicAdd(a.stats + 4, 1.0);
+    if (s.overflow) atomicAdd(a.stats + 5, (double)s.overflow);
+    atomicAdd(a.stats + 6, (double)s.iters);
+    atomicAdd(a.stats + 7, (double)substeps);
+  }
+}
+
+__global__ void reward_kernel(const double* __restrict__ ag, const double* __restrict__ g, int64_t n, double thr, int type, void* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double dx = ag[3 * i] - g[3 * i], dy = ag[3 * i + 1] - g[3 * i + 1], dz = ag[3 * i + 2] - g[3 * i + 2];
+  double d = sqrt(dx * dx + dy * dy + dz * dz);
+  if (type == 0) ((float*)out)[i] = -(float)(d > thr);
+  else ((double*)out)[i] = -d;
+}
+
+__global__ void init_state_kernel(double* state, int* elapsed, double* ep_return, unsigned long long* ctr, const DevModel* m, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* st = state + (size_t)i * MCB_STATE_STRIDE;
+  for (int k = 0; k < MCB_STATE_STRIDE; k++) st[k] = 0;
+  for (int k = 0; k < NQ; k++) st[k] = m->d.init_qpos[k];
+  for (int k = 0; k < NU; k++) st[37 + k] = m->d.init_ctrl[k];
+  elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
+}
+
+// gather / scatter between the resident state record and caller arrays
+__global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int* el, int write) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* st = state + (size_t)i * MCB_STATE_STRIDE;
+  if (write) {
+    if (qpos) for (int k = 0; k < NQ; k++) st[k] = qpos[(size_t)i * NQ + k];
+    if (qvel) for (int k = 0; k < NV; k++) st[19 + k] = qvel[(size_t)i * NV + k];
+    if (ctrl) for (int k = 0; k < NU; k++) st[37 + k] = ctrl[(size_t)i * NU + k];
+    if (warm) for (int k = 0; k < NV; k++) st[44 + k] = warm[(size_t)i * NV + k];
+    if (goal) for (int k = 0; k < 3; k++) st[62 + k] = goal[(size_t)i * 3 + k];
+    if (el) elapsed[i] = el[i];
+  } else {
+    if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = st[k];
+    if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = st[19 + k];
+    if (ctrl) for (int k = 0; k < NU; k++) ctrl[(size_t)i * NU + k] = st[37 + k];
+    if (warm) for (int k = 0; k < NV; k++) warm[(size_t)i * NV + k] = st[44 + k];
+    if (goal) for (int k = 0; k < 3; k++) goal[(size_t)i * 3 + k] = st[62 + k];
+    if (el) el[i] = elapsed[i];
+  }
+}
+
+// DFMA throughput probe: 8 independent chains per thread
+__global__ void dfma_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  double sum = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (sum == 123.456) out[0] = sum;
+}
+
+}  // namespace
+
+// ================================================================================================
+struct mcb_model {
+  int device;
+  DevModel* dev;
+  DevModel host;
+};
+
+struct mcb_batch {
+  mcb_model* model;
+  int n_envs, nefc, warps, obs_dim;
+  size_t smem;
+  mcb_task_cfg cfg;
+  uint64_t seed;
+  double* state; int* elapsed; double* ep_return; unsigned long long* rng_ctr; double* stats;
+  double* debug;
+  int last_launches;
+  // staging for the host-buffer entry point
+  float* d_actions; double *d_obs, *d_ag, *d_dg; void* d_reward; uint8_t* d_flags;
+  float* h_actions; double *h_obs, *h_ag, *h_dg; void* h_reward; uint8_t* h_flags;
+};
+
+static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
+  int blocks = (b->n_envs + b->warps - 1) / b->warps;
+  a.m = b->model->dev; a.n_envs = b->n_envs; a.cfg = b->cfg; a.seed = b->seed;
+  a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
+  switch (b->nefc) {
+    case 32: mcb_env_kernel<32, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
+    case 64: mcb_env_kernel<64, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
+    default: mcb_env_kernel<96, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+const char* mcb_version(void) { return "mycobot_b200 0.1 (sm_100a)"; }
+const char* mcb_last_error(void) { return g_err.c_str(); }
+int32_t mcb_model_desc_size(void) { return (int32_t)sizeof(mcb_model_desc); }
+int32_t mcb_task_cfg_size(void) { return (int32_t)sizeof(mcb_task_cfg); }
+
+int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** out) {
+  if (!d || !out) return fail("mcb_model_create: null argument");
+  CK(cudaSetDevice(device));
+  mcb_model* m = new mcb_model();
+  m->device = device;
+  DevModel& h = m->host;
+  memset(&h, 0, sizeof h);
+  h.d = *d;
+  // level tables
+  int maxl = 0;
+  for (int b = 0; b < NB; b++) if (d->level[b] > maxl) maxl = d->level[b];
+  h.nlevel = maxl + 1;
+  int pos = 0;
+  for (int L = 0; L <= maxl; L++) {
+    h.level_start[L] = pos;
+    for (int b = 0; b < NB; b++) if (d->level[b] == L) h.level_body[pos++] = b;
+  }
+  h.level_start[maxl + 1] = pos;
+  // non-zeros of M: (i, j) with j an ancestor dof of i (or i itself)
+  int n = 0;
+  for (int i = 0; i < NV; i++) {
+    uint32_t mask = d->ancmask[d->dof_body[i]];
+    for (int j = 0; j <= i; j++)
+      if ((mask >> j) & 1u) { if (n >= NMNZ_MAX) { delete m; return fail("mcb_model_create: too many M non-zeros"); } h.mnz_i[n] = (unsigned char)i; h.mnz_j[n] = (unsigned char)j; n++; }
+  }
+  h.nmnz = n;
+  // contact parameter mixing per candidate pair (mj_collideGeoms / mj_contactParam)
+  if (d->npair > MCB_MAXPAIR) { delete m; return fail("mcb_model_create: too many pairs"); }
+  for (int p = 0; p < d->npair; p++) {
+    int g1 = d->pair_g1[p], g2 = d->pair_g2[p];
+    PairParam& pp = h.pair[p];
+    pp.g1 = g1; pp.g2 = g2;
+    pp.dim = d->geom_condim[g1] > d->geom_condim[g2] ? d->geom_condim[g1] : d->geom_condim[g2];
+    if (pp.dim != 3 && pp.dim != 4) { delete m; return fail("mcb_model_create: only condim 3 and 4 are supported"); }
+    double fr[3];
+    for (int k = 0; k < 3; k++) fr[k] = fmax(d->geom_friction[g1][k], d->geom_friction[g2][k]);
+    pp.friction[0] = fr[0]; pp.friction[1] = fr[1]; pp.friction[2] = fr[2];
+    double sa = d->geom_solmix[g1], sb = d->geom_solmix[g2], mix;
+    if (sa >= MINVAL && sb >= MINVAL) mix = sa / (sa + sb);
+    else if (sa < MINVAL && sb < MINVAL) mix = 0.5;
+    else if (sa < MINVAL) mix = 0.0; else mix = 1.0;
+    const double *ra = d->geom_solref[g1], *rb = d->geom_solref[g2];
+    if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) pp.solref[k] = mix * ra[k] + (1 - mix) * rb[k];
+    else for (int k = 0; k < 2; k++) pp.solref[k] = fmin(ra[k], rb[k]);
+    for (int k = 0; k < 5; k++) pp.solimp[k] = mix * d->geom_solimp[g1][k] + (1 - mix) * d->geom_solimp[g2][k];
+    pp.tran = d->geom_invweight[g1][0] + d->geom_invweight[g2][0];
+    pp.rot = d->geom_invweight[g1][1] + d->geom_invweight[g2][1];
+  }
+  CK(cudaMalloc(&m->dev, sizeof(DevModel)));
+  CK(cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  *out = m;
+  return 0;
+}
+
+int32_t mcb_model_destroy(mcb_model* m) {
+  if (!m) return 0;
+  cudaFree(m->dev);
+  delete m;
+  return 0;
+}
+
+
+int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out) {
+  if (!m || !cfg || !out || n_envs <= 0) return fail("mcb_batch_create: bad argument");
+  CK(cudaSetDevice(m->device));
+  mcb_batch* b = new mcb_batch();
+  memset(b, 0, sizeof *b);
+  b->model = m; b->n_envs = n_envs; b->cfg = *cfg; b->seed = seed;
+  b->obs_dim = cfg->has_object ? MCB_OBS_OBJECT : MCB_OBS_REACH;
+  int nefc = cfg->nefc_max ? cfg->nefc_max : (cfg->has_object ? 96 : 32);
+  if (nefc != 32 && nefc != 64 && nefc != 96) { delete b; return fail("mcb_batch_create: nefc_max must be 32, 64 or 96"); }
+  b->nefc = nefc; b->warps = WPB;
+  size_t per = nefc == 32 ? sizeof(EnvS<32>) : nefc == 64 ? sizeof(EnvS<64>) : sizeof(EnvS<96>);
+  b->smem = per * b->warps;
+  cudaError_t e;
+  if (nefc == 32) e = cudaFuncSetAttribute(mcb_env_kernel<32, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
+  else if (nefc == 64) e = cudaFuncSetAttribute(mcb_env_kernel<64, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
+  else e = cudaFuncSetAttribute(mcb_env_kernel<96, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
+  if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(max dynamic smem)", e); }
+  size_t N = (size_t)n_envs;
+  CK(cudaMalloc(&b->state, N * MCB_STATE_STRIDE * sizeof(double)));
+  CK(cudaMalloc(&b->elapsed, N * sizeof(int)));
+  CK(cudaMalloc(&b->ep_return, N * sizeof(double)));
+  CK(cudaMalloc(&b->rng_ctr, N * sizeof(unsigned long long)));
+  CK(cudaMalloc(&b->stats, 8 * sizeof(double)));
+  CK(cudaMalloc(&b->debug, (4 + NV * NV + 5 * NV + NB * 12 + 96 * NV + 2 * 96 + 7 * MAXCON) * sizeof(double)));
+  CK(cudaMemset(b->stats, 0, 8 * sizeof(double)));
+  init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = b;
+  return 0;
+}
+
+int32_t mcb_batch_destroy(mcb_batch* b) {
+  if (!b) return 0;
+  cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->stats); cudaFree(b->debug);
+  if (b->d_actions) { cudaFree(b->d_actions); cudaFree(b->d_obs); cudaFree(b->d_ag); cudaFree(b->d_dg); cudaFree(b->d_reward); cudaFree(b->d_flags); }
+  if (b->h_actions) { cudaFreeHost(b->h_actions); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_ag); cudaFreeHost(b->h_dg); cudaFreeHost(b->h_reward); cudaFreeHost(b->h_flags); }
+  delete b;
+  return 0;
+}
+int32_t mcb_batch_num_envs(const mcb_batch* b) { return b ? b->n_envs : -1; }
+int32_t mcb_batch_obs_dim(const mcb_batch* b) { return b ? b->obs_dim : -1; }
+
+int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals, double* obs, double* ag, double* dg, void* stream) {
+  if (!b) return fail("mcb_reset: null batch");
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.mode = MODE_RESET; a.mask = mask; a.inj_xy = obj_xy; a.inj_goal = goals; a.obs = obs; a.ag = ag; a.dg = dg;
+  return launch(b, a, (cudaStream_t)stream);
+}
+
+int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, double* dg, void* reward, uint8_t* terminated,
+                 uint8_t* truncated, uint8_t* success, double* final_obs, void* stream) {
+  if (!b || !actions || !reward || !terminated || !truncated || !success) return fail("mcb_step: null argument");
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.mode = MODE_STEP; a.actions = actions; a.obs = obs; a.ag = ag; a.dg = dg; a.reward = reward;
+  a.terminated = terminated; a.truncated = truncated; a.success = success; a.final_obs = final_obs;
+  b->last_launches = 1;
+  return launch(b, a, (cudaStream_t)stream);
+}
+
+int32_t mcb_forward(mcb_batch* b, double* obs, double* ag, double* dg, void* stream) {
+  if (!b) return fail("mcb_forward: null batch");
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.mode = MODE_FORWARD; a.obs = obs; a.ag = ag; a.dg = dg;
+  return launch(b, a, (cudaStream_t)stream);
+}
+
+int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out, int32_t cap, void* stream) {
+  if (!b || env < 0 || env >= b->n_envs) return fail("mcb_debug_forward: bad argument");
+  (void)what;
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.mode = MODE_FORWARD; a.debug = b->debug; a.debug_env = env;
+  if (launch(b, a, (cudaStream_t)stream)) return -1;
+  int total = 4 + NV * NV + 5 * NV + NB * 12 + 96 * NV + 2 * 96 + 7 * MAXCON;
+  if (cap < total) return fail("mcb_debug_forward: buffer too small");
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  CK(cudaMemcpy(h_out, b->debug, total * sizeof(double), cudaMemcpyDeviceToHost));
+  return total;
+}
+
+int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int32_t* elapsed, void* stream) {
+  if (!b) return fail("mcb_get_state: null batch");
+  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, 0);
+  CK(cudaGetLastError());
+  return 0;
+}
+int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const double* goal,
+                      const int32_t* elapsed, void* stream) {
+  if (!b) return fail("mcb_set_state: null batch");
+  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, (double*)qpos, (double*)qvel, (double*)ctrl,
+                                                                             (double*)warm, (double*)goal, (int*)elapsed, 1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int32_t mcb_compute_reward(const double* ag, const double* g, int64_t n, double thr, int32_t type, void* out, void* stream) {
+  if (!ag || !g || !out || n < 0) return fail("mcb_compute_reward: bad argument");
+  if (n == 0) return 0;
+  reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, g, n, thr, type, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream) {
+  if (!b || !out) return fail("mcb_stats: null argument");
+  CK(cudaMemcpyAsync(out, b->stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (reset_after) CK(cudaMemsetAsync(b->stats, 0, 8 * sizeof(double), (cudaStream_t)stream));
+  return 0;
+}
+
+int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, double* h_ag, double* h_dg, void* h_reward, uint8_t* h_term,
+                      uint8_t* h_trunc, uint8_t* h_succ, void* stream) {
+  if (!b || !h_actions) return fail("mcb_step_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t N = (size_t)b->n_envs, od = (size_t)b->obs_dim;
+  size_t rbytes = b->cfg.reward_type == 0 ? sizeof(float) : sizeof(double);
+  if (!b->d_actions) {
+    CK(cudaMalloc(&b->d_actions, N * NU * sizeof(float)));
+    CK(cudaMalloc(&b->d_obs, N * od * sizeof(double)));
+    CK(cudaMalloc(&b->d_ag, N * 3 * sizeof(double)));
+    CK(cudaMalloc(&b->d_dg, N * 3 * sizeof(double)));
+    CK(cudaMalloc(&b->d_reward, N * sizeof(double)));
+    CK(cudaMalloc(&b->d_flags, N * 3));
+    CK(cudaMallocHost(&b->h_actions, N * NU * sizeof(float)));
+    CK(cudaMallocHost(&b->h_obs, N * od * sizeof(double)));
+    CK(cudaMallocHost(&b->h_ag, N * 3 * sizeof(double)));
+    CK(cudaMallocHost(&b->h_dg, N * 3 * sizeof(double)));
+    CK(cudaMallocHost(&b->h_reward, N * sizeof(double)));
+    CK(cudaMallocHost(&b->h_flags, N * 3));
+  }
+  memcpy(b->h_actions, h_actions, N * NU * sizeof(float));
+  CK(cudaMemcpyAsync(b->d_actions, b->h_actions, N * NU * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (mcb_step(b, b->d_actions, b->d_obs, b->d_ag, b->d_dg, b->d_reward, b->d_flags, b->d_flags + N, b->d_flags + 2 * N, nullptr, stream)) return -1;
+  CK(cudaMemcpyAsync(b->h_obs, b->d_obs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_ag, b->d_ag, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_dg, b->d_dg, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_reward, b->d_reward, N * rbytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_flags, b->d_flags, N * 3, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h_obs) memcpy(h_obs, b->h_obs, N * od * sizeof(double));
+  if (h_ag) memcpy(h_ag, b->h_ag, N * 3 * sizeof(double));
+  if (h_dg) memcpy(h_dg, b->h_dg, N * 3 * sizeof(double));
+  if (h_reward) memcpy(h_reward, b->h_reward, N * rbytes);
+  if (h_term) memcpy(h_term, b->h_flags, N);
+  if (h_trunc) memcpy(h_trunc, b->h_flags + N, N);
+  if (h_succ) memcpy(h_succ, b->h_flags + 2 * N, N);
+  return 0;
+}
+
+int32_t mcb_last_step_launches(const mcb_batch* b) { return b ? b->last_launches : -1; }
+
+int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out) {
+  if (!tflops_out || iters <= 0) return fail("mcb_fp64_peak_probe: bad argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* out;
+  CK(cudaMalloc(&out, sizeof(double)));
+  int blocks = prop.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    CK(cudaEventRecord(e0));
+    dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, float* ms_out, void* stream) {
+  (void)b; (void)actions; (void)reps; (void)ms_out; (void)stream;
+  return fail("mcb_time_step_kernel: not implemented; time mcb_step with CUDA events on the caller's stream");
+}
+
+}  // extern "C"

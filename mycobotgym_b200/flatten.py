@@ -1,0 +1,261 @@
+"""FlatModel (mjModel-like table) -> `mcb_model_desc` (include/mycobot_b200.h).
+
+Second half of north-star subsystem (1): the compiled model is reduced to its 13 jointed
+bodies -- bodies without joints (flange, camera frames, gripper_base, gripper_tcp, finger
+layers; mycobot280_main.xml:157-175,194-200,221-226) are merged into their jointed ancestor
+(composite mass / centre of mass / inertia, composed fixed transforms) -- and laid out as the
+fixed-size structure-of-arrays the CUDA kernels read.  The merge is exact rigid-body algebra;
+the oracle works on the unmerged 25-body table, so GPU-vs-oracle parity also checks the merge.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import mjcf
+from .mjcf import quat2mat, quat_mul
+
+NB, NV, NQ, NU, NHINGE, NGEOM, MAXPAIR = 13, 18, 19, 7, 12, 5, 12
+
+_d = C.c_double
+_i = C.c_int32
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("parent", _i * NB), ("level", _i * NB), ("subtree_size", _i * NB), ("dof_body", _i * NV),
+        ("ancmask", C.c_uint32 * NB),
+        ("Tpos", _d * 3 * NB), ("Tmat", _d * 9 * NB), ("axis", _d * 3 * NB),
+        ("mass", _d * NB), ("ipos", _d * 3 * NB), ("inertia", _d * 6 * NB),
+        ("armature", _d * NV), ("damping", _d * NV), ("dof_invweight0", _d * NV),
+        ("ref_robot", _d * 3), ("qpos0", _d * NQ),
+        ("jnt_limited", _i * NHINGE), ("jnt_range", _d * 2 * NHINGE), ("jnt_solref", _d * 2 * NHINGE),
+        ("jnt_solimp", _d * 5 * NHINGE),
+        ("con_body1", _i * 2), ("con_body2", _i * 2), ("con_anchor1", _d * 3 * 2), ("con_anchor2", _d * 3 * 2),
+        ("con_diag", _d * 2), ("con_solref", _d * 2 * 2), ("con_solimp", _d * 5 * 2),
+        ("jeq_dof1", _i), ("jeq_dof2", _i), ("jeq_polycoef", _d * 5), ("jeq_diag", _d), ("jeq_solref", _d * 2),
+        ("jeq_solimp", _d * 5),
+        ("geom_type", _i * NGEOM), ("geom_body", _i * NGEOM), ("geom_condim", _i * NGEOM),
+        ("geom_pos", _d * 3 * NGEOM), ("geom_mat", _d * 9 * NGEOM), ("geom_size", _d * 3 * NGEOM),
+        ("geom_rbound", _d * NGEOM), ("geom_friction", _d * 3 * NGEOM), ("geom_solref", _d * 2 * NGEOM),
+        ("geom_solimp", _d * 5 * NGEOM), ("geom_solmix", _d * NGEOM), ("geom_invweight", _d * 2 * NGEOM),
+        ("npair", _i), ("pair_g1", _i * MAXPAIR), ("pair_g2", _i * MAXPAIR),
+        ("eef_body", _i), ("eef_pos", _d * 3), ("obj_body", _i),
+        ("act_moment", _d * NV * NU), ("act_gain", _d * NU), ("act_bias", _d * 3 * NU),
+        ("act_ctrlrange", _d * 2 * NU), ("act_forcerange", _d * 2 * NU), ("act_ctrllimited", _i * NU),
+        ("act_forcelimited", _i * NU),
+        ("timestep", _d), ("gravity", _d * 3), ("tolerance", _d), ("ls_tolerance", _d), ("meaninertia", _d),
+        ("impratio", _d), ("iterations", _i), ("ls_iterations", _i),
+        ("initial_gripper_xpos", _d * 3), ("height_offset", _d), ("init_qpos", _d * NQ), ("init_ctrl", _d * NU),
+    ]
+
+
+class TaskCfg(C.Structure):
+    _fields_ = [
+        ("has_object", _i), ("block_gripper", _i), ("target_in_the_air", _i), ("reward_type", _i),
+        ("max_episode_steps", _i), ("frame_skip", _i), ("auto_reset", _i), ("nefc_max", _i),
+        ("distance_threshold", _d),
+    ]
+
+
+def _set(arr, value):
+    a = np.ascontiguousarray(value)
+    flat = np.ctypeslib.as_array(arr).reshape(-1)
+    flat[:] = a.reshape(-1)
+
+
+def _rel_pose(m, body, anc):
+    """Pose of `body`'s frame in the frame of ancestor body `anc` (anc == 0: world), at q = 0 of the
+    joints strictly between them (there are none by construction: only fixed bodies are crossed)."""
+    pos = np.zeros(3)
+    quat = np.array([1.0, 0, 0, 0])
+    b = body
+    while b != anc:
+        pos = m["body_pos"][b] + quat2mat(m["body_quat"][b]) @ pos
+        quat = quat_mul(m["body_quat"][b], quat)
+        b = int(m["body_parentid"][b])
+    return pos, quat
+
+
+def reduce_model(m) -> ModelDesc:
+    nbody = int(m["nbody"])
+    assert int(m["nv"]) == NV and int(m["nq"]) == NQ and int(m["nu"]) == NU and int(m["njnt"]) == NB
+    jointed = [b for b in range(nbody) if m["body_jntnum"][b] > 0]
+    assert len(jointed) == NB
+    jidx = {b: k for k, b in enumerate(jointed)}
+    assert np.all(m["jnt_pos"] == 0), "reduced FK assumes joint anchors at the body origin"
+    d = ModelDesc()
+
+    def weld_jointed(b):
+        w = int(m["body_weldid"][b])
+        return jidx[w] if w != 0 else -1
+
+    parent, level = [], []
+    for k, b in enumerate(jointed):
+        p = int(m["body_parentid"][b])
+        pw = int(m["body_weldid"][p])
+        pk = jidx[pw] if pw != 0 else -1
+        parent.append(pk)
+        level.append(0 if pk < 0 else level[pk] + 1)
+        anc = pw if pw != 0 else 0
+        pos, quat = _rel_pose(m, b, anc)
+        if m["jnt_type"][m["body_jntadr"][b]] == mjcf.JNT_FREE:
+            pos, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
+        _set(d.Tpos[k], pos)
+        _set(d.Tmat[k], quat2mat(quat))
+        _set(d.axis[k], m["jnt_axis"][m["body_jntadr"][b]])
+    _set(d.parent, parent)
+    _set(d.level, level)
+    sub = [1] * NB
+    for k in range(NB - 1, -1, -1):
+        if parent[k] >= 0:
+            sub[parent[k]] += sub[k]
+    for k in range(NB):  # DFS pre-order => subtree is the contiguous range [k, k+sub[k])
+        for c in range(k + 1, k + sub[k]):
+            a = c
+            while a != k and a >= 0:
+                a = parent[a]
+            assert a == k
+    _set(d.subtree_size, sub)
+    _set(d.dof_body, [jidx[int(b)] for b in m["dof_bodyid"]])
+    for k, b in enumerate(jointed):
+        mask = 0
+        dof = int(m["body_dofadr"][b] + m["body_dofnum"][b] - 1)
+        while dof >= 0:
+            mask |= 1 << dof
+            dof = int(m["dof_parentid"][dof])
+        d.ancmask[k] = mask
+
+    # composite inertia of each jointed body with its merged fixed descendants
+    for k, b in enumerate(jointed):
+        parts = []
+        for f in range(nbody):
+            if int(m["body_weldid"][f]) != b or m["body_mass"][f] <= 0:
+                continue
+            pos, quat = _rel_pose(m, f, b)
+            R = quat2mat(quat)
+            Ri = R @ quat2mat(m["body_iquat"][f])
+            parts.append((float(m["body_mass"][f]), pos + R @ m["body_ipos"][f], Ri @ np.diag(m["body_inertia"][f]) @ Ri.T))
+        mt = sum(p[0] for p in parts)
+        com = sum(p[0] * p[1] for p in parts) / mt
+        I = np.zeros((3, 3))
+        for ms, p, Ig in parts:
+            dd = p - com
+            I += Ig + ms * (dd @ dd * np.eye(3) - np.outer(dd, dd))
+        d.mass[k] = mt
+        _set(d.ipos[k], com)
+        _set(d.inertia[k], [I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
+    _set(d.armature, m["dof_armature"])
+    _set(d.damping, m["dof_damping"])
+    _set(d.dof_invweight0, m["dof_invweight0"])
+    _set(d.qpos0, m["qpos0"])
+
+    fk = mjcf.fk_numpy(m, m["qpos0"])
+    xpos, xquat, xmat, xipos = fk[0], fk[1], fk[2], fk[3]
+    root = int(m["body_rootid"][jointed[0]])
+    sel = [b for b in range(nbody) if m["body_rootid"][b] == root and m["body_mass"][b] > 0]
+    mtot = sum(m["body_mass"][b] for b in sel)
+    _set(d.ref_robot, sum(m["body_mass"][b] * xipos[b] for b in sel) / mtot)
+
+    nh = 0
+    for j in range(NB):
+        if m["jnt_type"][j] != mjcf.JNT_HINGE:
+            continue
+        assert m["jnt_dofadr"][j] == nh and m["jnt_margin"][j] == 0
+        d.jnt_limited[nh] = int(m["jnt_limited"][j])
+        _set(d.jnt_range[nh], m["jnt_range"][j])
+        _set(d.jnt_solref[nh], m["jnt_solref"][j])
+        _set(d.jnt_solimp[nh], m["jnt_solimp"][j])
+        nh += 1
+    assert nh == NHINGE
+
+    ci = 0
+    for e in range(int(m["neq"])):
+        if m["eq_type"][e] == mjcf.EQ_CONNECT:
+            b1, b2 = int(m["eq_obj1id"][e]), int(m["eq_obj2id"][e])
+            assert b1 in jidx and b2 in jidx
+            d.con_body1[ci], d.con_body2[ci] = jidx[b1], jidx[b2]
+            _set(d.con_anchor1[ci], m["eq_data"][e, 0:3])
+            _set(d.con_anchor2[ci], m["eq_data"][e, 3:6])
+            d.con_diag[ci] = m["body_invweight0"][b1, 0] + m["body_invweight0"][b2, 0]
+            _set(d.con_solref[ci], m["eq_solref"][e])
+            _set(d.con_solimp[ci], m["eq_solimp"][e])
+            ci += 1
+        else:
+            d1, d2 = int(m["jnt_dofadr"][m["eq_obj1id"][e]]), int(m["jnt_dofadr"][m["eq_obj2id"][e]])
+            d.jeq_dof1, d.jeq_dof2 = d1, d2
+            _set(d.jeq_polycoef, m["eq_data"][e, 0:5])
+            d.jeq_diag = m["dof_invweight0"][d1] + m["dof_invweight0"][d2]
+            _set(d.jeq_solref, m["eq_solref"][e])
+            _set(d.jeq_solimp, m["eq_solimp"][e])
+    assert ci == 2 and list(m["eq_type"]) == [mjcf.EQ_CONNECT, mjcf.EQ_CONNECT, mjcf.EQ_JOINT]
+
+    assert int(m["ngeom"]) == NGEOM
+    for g in range(NGEOM):
+        gb = int(m["geom_bodyid"][g])
+        w = int(m["body_weldid"][gb])
+        pos, quat = _rel_pose(m, gb, w if w != 0 else 0)
+        R = quat2mat(quat)
+        d.geom_type[g] = int(m["geom_type"][g])
+        d.geom_body[g] = weld_jointed(gb)
+        d.geom_condim[g] = int(m["geom_condim"][g])
+        _set(d.geom_pos[g], pos + R @ m["geom_pos"][g])
+        _set(d.geom_mat[g], R @ quat2mat(m["geom_quat"][g]))
+        _set(d.geom_size[g], m["geom_size"][g])
+        d.geom_rbound[g] = m["geom_rbound"][g]
+        _set(d.geom_friction[g], m["geom_friction"][g])
+        _set(d.geom_solref[g], m["geom_solref"][g])
+        _set(d.geom_solimp[g], m["geom_solimp"][g])
+        d.geom_solmix[g] = m["geom_solmix"][g]
+        _set(d.geom_invweight[g], m["body_invweight0"][gb])
+        assert m["geom_margin"][g] == 0 and m["geom_gap"][g] == 0
+    pairs = []
+    excl = {tuple(e) for e in m["exclude"].tolist()}
+    for g1 in range(NGEOM):
+        for g2 in range(g1 + 1, NGEOM):
+            a, b = (g1, g2) if m["geom_type"][g1] <= m["geom_type"][g2] else (g2, g1)
+            b1, b2 = int(m["geom_bodyid"][a]), int(m["geom_bodyid"][b])
+            w1, w2 = int(m["body_weldid"][b1]), int(m["body_weldid"][b2])
+            if w1 == w2 or (min(b1, b2), max(b1, b2)) in excl:
+                continue
+            if w1 and w2 and (m["body_weldid"][m["body_parentid"][w1]] == w2 or m["body_weldid"][m["body_parentid"][w2]] == w1):
+                continue
+            if not ((m["geom_contype"][a] & m["geom_conaffinity"][b]) or (m["geom_contype"][b] & m["geom_conaffinity"][a])):
+                continue
+            pairs.append((a, b))
+    assert len(pairs) <= MAXPAIR
+    d.npair = len(pairs)
+    for i, (a, b) in enumerate(pairs):
+        d.pair_g1[i], d.pair_g2[i] = a, b
+
+    s_eef = m["site_names"].index("EEF")
+    s_obj = m["site_names"].index("object0")
+    sb = int(m["site_bodyid"][s_eef])
+    w = int(m["body_weldid"][sb])
+    pos, quat = _rel_pose(m, sb, w)
+    d.eef_body = jidx[w]
+    _set(d.eef_pos, pos + quat2mat(quat) @ m["site_pos"][s_eef])
+    ob = int(m["site_bodyid"][s_obj])
+    assert ob in jidx and np.all(m["site_pos"][s_obj] == 0)
+    d.obj_body = jidx[ob]
+
+    _set(d.act_moment, m["actuator_moment"])
+    _set(d.act_gain, m["actuator_gain"])
+    _set(d.act_bias, m["actuator_biasprm"])
+    _set(d.act_ctrlrange, m["actuator_ctrlrange"])
+    _set(d.act_forcerange, m["actuator_forcerange"])
+    _set(d.act_ctrllimited, m["actuator_ctrllimited"])
+    _set(d.act_forcelimited, m["actuator_forcelimited"])
+    d.timestep, d.tolerance, d.ls_tolerance = float(m["timestep"]), float(m["tolerance"]), float(m["ls_tolerance"])
+    _set(d.gravity, m["gravity"])
+    d.meaninertia, d.impratio = float(m["stat_meaninertia"]), float(m["impratio"])
+    d.iterations, d.ls_iterations = int(m["iterations"]), int(m["ls_iterations"])
+
+    # _env_setup constants (mycobot.py:450-481), non-fetch: sites at qpos0
+    seb = int(m["site_bodyid"][s_eef])
+    _set(d.initial_gripper_xpos, xpos[seb] + xmat[seb] @ m["site_pos"][s_eef])
+    d.height_offset = float((xpos[ob] + xmat[ob] @ m["site_pos"][s_obj])[2])
+    _set(d.init_qpos, m["qpos0"])
+    _set(d.init_ctrl, np.zeros(NU))
+    return d

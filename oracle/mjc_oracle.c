@@ -450,13 +450,13 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
     double t = dot3(d, A[i]);
     double s = fabs(t) - (s1[i] + s2[0] * Q[i][0] + s2[1] * Q[i][1] + s2[2] * Q[i][2]);
     if (s > margin) return 0;
-    if (s > best) { best = s; code = i; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -A[i][k] : A[i][k]); }
+    if (s > best + (code >= 0 ? 1e-10 : 0.0)) { best = s; code = i; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -A[i][k] : A[i][k]); }
   }
   for (int j = 0; j < 3; j++) {
     double t = dot3(d, B[j]);
     double s = fabs(t) - (s2[j] + s1[0] * Q[0][j] + s1[1] * Q[1][j] + s1[2] * Q[2][j]);
     if (s > margin) return 0;
-    if (s > best) { best = s; code = 3 + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -B[j][k] : B[j][k]); }
+    if (s > best + 1e-10) { best = s; code = 3 + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -B[j][k] : B[j][k]); }
   }
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
@@ -470,7 +470,7 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
       for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(A[k], L)); rb += s2[k] * fabs(dot3(B[k], L)); }
       double s = fabs(t) - (ra + rb);
       if (s > margin) return 0;
-      if (s * 1.05 > best + 1e-12 && s > best) { best = s; code = 6 + 3 * i + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -L[k] : L[k]); }
+      if (s * 1.05 > best + 1e-10 && s > best) { best = s; code = 6 + 3 * i + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -L[k] : L[k]); }
     }
   if (code < 0) return 0;
   if (code >= 6) {
