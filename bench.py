@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched myCobot step on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pick|reach|push] [--impl ours|reference]
+
+One "step" = one `step()` of every env of the workload = 20 physics substeps (joint controller) +
+observation / reward / success / auto-reset, i.e. one launch of the fused env kernel.  Default workload
+= BASELINE.json configs[3]: pick-and-place, 16384 envs per GPU, random actions, auto-reset with goal
+resampling (weak scaling: per-GPU work fixed).  For N>1 the driver launches this under torchrun, one
+rank per GPU; envs are sharded with no data-path collective, NCCL only reduces the 8-double statistics
+vector once at the end of the timed region.
+
+`--impl reference`: the reference's CPU path.  MuJoCo 2.3.2 is not installable here, so this arm times the
+repo's CPU restatement (oracle/, kind "port") on all host cores, same metric and workload, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (env kwargs, envs per GPU, algorithmic FLOP per env-step [DESIGN.md "Algorithmic work"])
+    "reach": (dict(has_object=False, reward_type="dense"), 4096, 0.60e6),
+    "push": (dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse"), 16384, 1.27e6),
+    "pick": (dict(has_object=True, reward_type="sparse"), 16384, 1.25e6),
+}
+METRIC = "env-steps/sec (pick-and-place, 16K envs/GPU) at 1/2/4/8 B200 vs CPU MuJoCo"
+UNIT = "env-steps/s"
+
+
+def _cpu_worker(job):
+    workload, tid, envs_per_worker, steps = job
+    from mycobotgym_b200 import mjcf
+    from oracle.oracle import OracleEnv
+
+    flat = mjcf.load_compiled()
+    kw, _, _ = WORKLOADS[workload]
+    okw = dict(has_object=kw.get("has_object", True), block_gripper=kw.get("block_gripper", False),
+               target_in_the_air=kw.get("target_in_the_air", True), reward_type=kw.get("reward_type", "sparse"))
+    envs = [OracleEnv(flat, **okw) for _ in range(envs_per_worker)]
+    rng = np.random.default_rng(tid)
+    for e in envs:
+        e.reset(seed=tid)
+    envs[0].step(np.zeros(7, dtype=np.float32))
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        for e in envs:
+            a = rng.uniform(-1, 1, 7).astype(np.float32)
+            o, r, te, tr, info = e.step(a)
+            if te or tr:
+                e.reset()
+            n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_port_throughput(workload, budget_env_steps, workers=None):
+    """Times the CPU restatement (oracle/) on the host cores: one process per core (the reference's own
+    parallelism is one env per subprocess, scripts/train.py:80-85), each stepping its envs serially with the
+    same random-action protocol (50-step TimeLimit, reset on done).  Throughput = sum of env-steps / slowest worker."""
+    import multiprocessing as mp
+
+    workers = workers or os.cpu_count() or 1
+    steps = 25
+    envs_per_worker = max(1, budget_env_steps // (workers * steps))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(workload, t, envs_per_worker, steps) for t in range(workers)])
+    total = sum(r[0] for r in res)
+    dt = max(r[1] for r in res)
+    return total / dt, workers, f"{workers} processes x {envs_per_worker} envs x {steps} steps = {total} env-steps in {dt:.1f}s ({workload})"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kw, per_gpu, _ = WORKLOADS[args.workload]
+    # each "step" of this arm = a bounded sample of the workload; K steps + W warm-up must end within minutes
+    per_step_budget = 2000
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_port_throughput(args.workload, per_step_budget)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * per_step_budget / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: CPU restatement of the reference step (MuJoCo 2.3.2 not installable), "
+                                                    f"random actions, auto-reset, bounded sample of {per_step_budget} env-steps per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mycobotgym_b200 import _lib
+    from mycobotgym_b200.vector_env import MyCobotVectorEnv, all_reduce_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (workers are forked)
+    cpu_val, cores, sample = cpu_port_throughput(args.workload, 20000) if (world == 1 and not args.no_cpu_baseline) else (None, None, None)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kw, per_gpu, flop_per_step = WORKLOADS[args.workload]
+    n = args.envs_per_gpu or per_gpu
+    env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, **kw)
+    env.reset()
+    K, W = args.steps, args.warmup
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    acts = torch.rand(K + W, n, 7, device=dev, generator=gen) * 2 - 1
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    for t in range(W):
+        env.step(acts[t])
+    env.stats(reset=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for t in range(K):
+        flush.zero_()                      # L2 flush between timed iterations (outside the per-step events)
+        ev[t][0].record()
+        env.step(acts[W + t])
+        ev[t][1].record()
+    stats = env.stats(reset=False).clone()
+    all_reduce_stats(stats)                # the path's only collective: 8 doubles, once per rollout
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    value = world * n * K / (total_ms * 1e-3)
+
+    # e2e: the same step through host buffers (pinned staging inside the C ABI), H2D + D2H inside the timed region
+    a_host = acts[W:].cpu().numpy()
+    out = env.step_host(a_host[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(K):
+        out = env.step_host(a_host[t], out)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * K / float(e2e_s.item())
+    rbytes = 4 if kw["reward_type"] == "sparse" else 8
+    h2d, d2h = n * 7 * 4, n * ((env.obs_dim + 6) * 8 + rbytes + 3)
+
+    if rank == 0:
+        L = _lib.load()
+        import ctypes as C
+
+        peak = C.c_double(0)
+        _lib.check(L.mcb_fp64_peak_probe(local, 20000, C.byref(peak)))
+        per_gpu_rate = value / world
+        achieved = per_gpu_rate * flop_per_step / 1e12
+        st = stats.cpu().numpy()
+        state_bytes = 2 * 72 * 8 + 28 + (env.obs_dim + 6) * 8 + rbytes + 3
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, joint controller, 20 substeps/step, uniform random actions "
+                                   f"U[-1,1]^7 float32, 50-step TimeLimit, auto-reset with on-device goal resampling",
+                       "envs_per_gpu": n, "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
+                       "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": K * env.last_step_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+                         "traffic": None,
+                         "note": "dominant kernel = mcb_env_kernel (the whole step); algorithmic FLOP/env-step from DESIGN.md; "
+                                 "peak = DFMA micro-kernel measured in this run (FP64 peak is not in MEASURED_PEAKS.json)",
+                         "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
+            "cpu_baseline": None if cpu_val is None else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "episode_stats": {"episodes": st[0], "successes": st[1], "return_sum": st[2], "length_sum": st[3], "env_steps": st[4],
+                              "row_overflows": st[5], "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="pick", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-port timing leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

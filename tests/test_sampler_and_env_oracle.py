@@ -1,0 +1,117 @@
+"""Goal / cube-xy sampler golden vectors and the env-level oracle (mycobot.py:132-400)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from mycobotgym_b200 import mjcf
+from oracle.oracle import OracleEnv
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def flat():
+    return mjcf.load_compiled()
+
+
+def test_sampler_golden_has_object_seed0(flat):
+    env = OracleEnv(flat, has_object=True)
+    random.seed(0)
+    env.reset(seed=0)
+    assert env.sim.qpos[12].hex() == "-0x1.ea6585257338ep-4" and env.sim.qpos[13].hex() == "-0x1.940bb35ca5400p-11"
+    assert [v.hex() for v in env.goal] == ["0x1.695e447adb0b8p-4", "-0x1.f77de0424967cp-6", "0x1.ae147ae147ae1p-3"]
+    env.reset()
+    np.testing.assert_allclose(env.sim.qpos[12:14], [-0.100693, -0.02159345], atol=5e-9)
+    np.testing.assert_allclose(env.goal, [0.00190575, 0.05194006, 0.21], atol=5e-9)
+    env.reset()
+    np.testing.assert_allclose(env.sim.qpos[12:14], [-0.09382612, 0.00615207], atol=5e-9)
+    assert env.goal[2].hex() == "0x1.11908d354f20ep-2"
+
+
+def test_sampler_golden_seed4_and_reach(flat):
+    env = OracleEnv(flat, has_object=True)
+    random.seed(4)
+    env.reset(seed=4)  # the seed used by scripts/test_human_gym.py:24
+    np.testing.assert_allclose(env.sim.qpos[12:14], [-0.06334846, -0.04762008], atol=5e-9)
+    assert env.goal[2].hex() == "0x1.153bb56ed247ep-2"
+    env = OracleEnv(flat, has_object=False)
+    random.seed(0)
+    env.reset(seed=0)
+    np.testing.assert_allclose(env.goal, [-0.11972572, -0.00077066, 0.21], atol=5e-9)
+    env.reset()
+    np.testing.assert_allclose(env.goal, [-0.100693, -0.02159345, 0.25858354], atol=5e-9)
+
+
+def test_product_sampler_matches_oracle_protocol(flat):
+    from mycobotgym_b200.vector_env import ReferenceGoalSampler
+
+    env = OracleEnv(flat, has_object=True)
+    random.seed(0)
+    env.reset(seed=0)
+    s = ReferenceGoalSampler(1, env.height_offset, env.initial_gripper_xpos[:2], True, True)
+    random.seed(0)
+    s.seed(0)
+    xy, g = s.sample([0])
+    assert np.array_equal(xy[0], env.sim.qpos[12:14]) and np.array_equal(g[0], env.goal)
+
+
+def test_env_semantics(flat):
+    env = OracleEnv(flat, has_object=True, reward_type="sparse")
+    random.seed(1)
+    obs, info = env.reset(seed=1)
+    assert obs["observation"].shape == (25,) and obs["achieved_goal"].shape == (3,) and info == {}
+    # fresh observation after reset: object_pos == cube qpos, velocities zero
+    np.testing.assert_array_equal(obs["observation"][3:6], env.sim.qpos[12:15])
+    np.testing.assert_array_equal(obs["observation"][14:25], 0)
+    o, r, te, tr, inf = env.step(np.zeros(7, dtype=np.float32))
+    assert r.dtype == np.float32 and float(r) == -1.0 and not te and not tr and inf["is_success"] is False
+    for _ in range(49):
+        o, r, te, tr, inf = env.step(np.zeros(7, dtype=np.float32))
+    assert tr and not te                                                     # TimeLimit(50), __init__.py:34
+    # success => terminated and truncated (mycobot.py:390-400); sparse reward -0.0 (mycobot.py:293)
+    env.goal = o["achieved_goal"].copy()
+    assert float(env.compute_reward(o["achieved_goal"], env.goal)) == 0.0
+    assert np.signbit(env.compute_reward(o["achieved_goal"], env.goal))
+    # batched compute_reward for HER (train.py:93-97)
+    ag = np.zeros((5, 3)); g = np.zeros((5, 3)); g[2:, 0] = 0.02
+    np.testing.assert_array_equal(env.compute_reward(ag, g), np.array([-0.0, -0.0, -1, -1, -1], dtype=np.float32))
+    # at d == threshold: not success, reward -0.0
+    g1 = np.array([0.01, 0, 0.0])
+    assert float(env.compute_reward(np.zeros(3), g1)) == 0.0
+
+
+def test_observation_is_one_substep_stale(flat):
+    # site poses in the obs come from the last substep's pre-advance kinematics
+    env = OracleEnv(flat, has_object=False, reward_type="dense")
+    random.seed(0)
+    env.reset(seed=0)
+    o, *_ = env.step(np.full(7, 0.5, dtype=np.float32))
+    stale = o["observation"][:3].copy()
+    env.sim.forward()
+    fresh = env.sim.site_xpos[1].copy()
+    assert 1e-7 < np.abs(stale - fresh).max() < 1e-2
+    # block_gripper re-runs forward => fresh (mycobot.py:300-306)
+    envb = OracleEnv(flat, has_object=True, block_gripper=True)
+    random.seed(0)
+    envb.reset(seed=0)
+    o, *_ = envb.step(np.full(7, 0.5, dtype=np.float32))
+    np.testing.assert_array_equal(o["observation"][:3], envb.sim.site_xpos[1])
+    assert envb.sim.qpos[7] == 0 and envb.sim.qpos[9] == 0
+
+
+@pytest.mark.parametrize("name", ["reach_dense_seed0", "reach_dense_seed1_perturbed", "pick_sparse_seed0",
+                                  "pick_sparse_seed4_perturbed", "push_sparse_seed2", "grasp_pick_sparse"])
+def test_oracle_reproduces_committed_golden(flat, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    env = OracleEnv(flat, has_object=bool(g["has_object"]), block_gripper=bool(g["block_gripper"]), reward_type=str(g["reward_type"]))
+    env.sim.set_state(g["qpos0"], g["qvel0"], g["ctrl0"], g["warm0"])
+    env.goal = g["goal"].copy()
+    for t in range(len(g["actions"])):
+        o, r, te, tr, info = env.step(g["actions"][t])
+        np.testing.assert_allclose(env.sim.qpos, g["qpos"][t], atol=1e-12)
+        np.testing.assert_allclose(env.sim.qvel, g["qvel"][t], atol=1e-10)
+        np.testing.assert_allclose(o["observation"], g["obs"][t], atol=1e-12)
+        assert float(r) == pytest.approx(float(g["reward"][t]), abs=1e-12)
+        assert te == bool(g["terminated"][t]) and tr == bool(g["truncated"][t])
