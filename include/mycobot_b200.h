@@ -118,7 +118,7 @@ typedef struct mcb_task_cfg {
   int32_t max_episode_steps;   /* 50 */
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
-  int32_t nefc_max;            /* constraint-row capacity per env: 32, 64 or 96 (0 = default for the task) */
+  int32_t nefc_max;            /* 0 (default): two-tier layout (48-row common case + 128-row fallback launch); 128: fallback layout only */
   double distance_threshold;   /* 0.01 */
 } mcb_task_cfg;
 
@@ -179,10 +179,11 @@ int32_t mcb_compute_reward(const double* achieved_goal, const double* goal, int6
  * [6]=solver iterations, [7]=substeps.  `out` is a device pointer to 8 doubles. */
 int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream);
 
-/* debug taps for stage-level parity tests: copies the given quantity of env `env` after the most recent
- * mcb_forward() into host memory.  what: 0 M[18*18], 1 qfrc_bias[18], 2 qacc_smooth[18], 3 qacc[18],
- * 4 nefc/ncon (2 doubles), 5 efc_J[nefc*18], 6 efc_aref, 7 efc_D, 8 contact (dist,pos3,normal3)*ncon,
- * 9 xpos[13*3], 10 xmat[13*9], 11 qfrc_smooth[18], 12 efc_pos. Returns number of doubles written. */
+/* debug tap for stage-level parity tests: runs mcb_forward() and copies intermediate quantities of env `env`
+ * to host memory (`what` is reserved, pass 0).  Layout in doubles: nefc, ncon, solver iterations, overflow |
+ * M[18*18] | qfrc_bias, qfrc_smooth, qacc_smooth, qacc, qfrc_constraint [18 each] | xpos[13*3] | xmat[13*9] |
+ * efc_J[nefc*18] in MuJoCo row order (equality, limits, contacts) | efc_aref[nefc] | efc_D[nefc] |
+ * (dist, pos3, normal3) * ncon.  cap must be >= 3170.  Returns the number of doubles written. */
 int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out, int32_t cap, void* stream);
 
 /* measurement helpers used by bench.py */

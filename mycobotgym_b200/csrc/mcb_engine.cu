@@ -1,23 +1,32 @@
 // mcb_engine.cu -- B200 (sm_100a) batched myCobot physics-and-task engine, C ABI in include/mycobot_b200.h.
 //
-// One environment per warp; the whole env-step (frame_skip substeps of the MuJoCo-equivalent
-// forward dynamics + semi-implicit Euler, then observation / reward / success / auto-reset) is one
-// kernel launch.  An env's working set (state, body frames, spatial inertias, M / H and their
-// Cholesky factors, the constraint Jacobian) lives in the warp's slice of shared memory; HBM sees one
-// 576-byte state record read and written per env-step plus the action and the outputs.
-// All arithmetic is fp64 on the CUDA cores (DFMA); tensor cores are deliberately unused: the per-env
-// matrices are 18x18 and smaller and the work is a sequence of tree recursions, not a dense contraction.
+// One environment per warp; the whole env-step (frame_skip substeps of the MuJoCo-equivalent forward
+// dynamics + semi-implicit Euler, then observation / reward / success / auto-reset) is one kernel launch.
+// An env's working set lives in the warp's slice of shared memory; HBM sees one 576-byte state record read
+// and written per env-step plus the action and the outputs.  All arithmetic is fp64 on the CUDA cores
+// (DFMA); tensor cores are deliberately unused: the per-env matrices are 18x18 and smaller and the work is a
+// sequence of tree recursions and tiny factorizations, not a dense contraction.
+//
+// Layout decisions that set the speed (profiles/r01_*):
+//   * the kernel is latency-bound, so resident envs per SM is the first lever: shared memory per env is
+//     ~14 KB (16 envs/SM) in the common case.  Dead dynamics temporaries and the constraint rows share one
+//     union; matrices are packed lower triangles; the constraint Jacobian is stored BLOCKED by row type
+//     (robot rows: 12 columns, cube rows: 6, coupled rows: 18, joint-limit rows: none);
+//   * capacity is two-tier: the launch uses the small layout (48 rows); an env that needs more (a grasp)
+//     aborts untouched, is queued on a device list and is redone by a second launch with the big layout;
+//   * the block structure robot(12) + cube(6) is used everywhere: M's cube block never couples, H couples
+//     only through finger-cube contact rows, so the usual factorizations are 12x12 and 6x6, fully unrolled.
 //
 // Stage map (what each device function restates; the reference reaches all of it through
 // mujoco.mj_step, mycobotgym/envs/mycobot.py:193 -> gymnasium MujocoEnv.do_simulation):
 //   fk()              mj_kinematics              cinert_cdof()  mj_comPos
-//   crb_mass()        mj_crb                     chol()         mj_factorM (dense LL' instead of sparse L'DL)
+//   crb_mass()        mj_crb                     chol_blk()     mj_factorM (dense LL' per block, not sparse L'DL)
+//   velocity_rne()    mj_comVel, mj_rne          actuation_smooth() mj_passive, mj_fwdActuation
 //   collide()         mj_collision (plane-box, box-box)
-//   make_rows()       mj_makeConstraint + mj_makeImpedance
-//   velocity_rne()    mj_comVel, mj_passive, mj_referenceConstraint, mj_rne
-//   actuation()       mj_fwdActuation            newton()       mj_solNewton (pyramidal cones)
+//   make_rows()       mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint
+//   Newton            mj_solNewton (pyramidal cones, exact line search)
 //   euler()           mj_Euler + mj_integratePos
-//   epilogue()        MyCobotEnv._get_obs / compute_reward / _is_success / reset_model (mycobot.py:207-298,342-400)
+//   write_obs() etc.  MyCobotEnv._get_obs / compute_reward / _is_success / reset_model (mycobot.py:207-298,342-400)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -32,15 +41,18 @@
 #define NQ MCB_NQ
 #define NU MCB_NU
 #define NH MCB_NHINGE
-#define LD 19           // row stride of the dense 18-wide matrices (odd => conflict-free column and row access)
-#define MAXCON 13
+#define NTRI 171        // packed lower triangle of an 18 x 18 matrix
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+#define SR 13           // padded strides of the blocked Jacobian rows (odd => conflict-free lane-per-row reads)
+#define SC 7
+#define SF 19
 #define FULLMASK 0xffffffffu
 #define MINVAL 1e-15
 #define MINIMP 0.0001
 #define MAXIMP 0.9999
 #define CUBE 12
 #define NMNZ_MAX 96
-#define WPB 1            // warps (= envs) per CTA; 1 keeps the per-SM env count limited only by shared memory
+#define RM_INEQ 0x10000  // rmeta bit: inequality row (limit / contact)
 
 namespace {
 
@@ -53,7 +65,7 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
 
 struct PairParam {
-  int g1, g2, dim;
+  int g1, g2, dim, ptype;  // ptype: 0 rows touch robot dofs only, 1 cube dofs only, 2 both
   double friction[3], solref[2], solimp[5], tran, rot;
 };
 
@@ -79,6 +91,8 @@ struct StepArgs {
   double* ep_return;         // [N]
   unsigned long long* rng_ctr;  // [N]
   double* stats;             // [8]
+  int* redo_count;           // envs that overflowed the small layout in this launch
+  int* redo_list;            // [N]
   const float* actions;      // [N, 7]
   const uint8_t* mask;       // reset
   const double* inj_xy;      // reset
@@ -91,23 +105,25 @@ struct StepArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-env shared-memory working set
-template <int NEFC>
+// per-env shared-memory working set.  BIG = false: the common case; BIG = true: the fallback for envs whose
+// contact set does not fit (grasps, pile-ups).
+template <bool BIG>
 struct EnvS {
+  enum { NROW = BIG ? 128 : 48, POOL = BIG ? 2432 : 460, MAXC = BIG ? 16 : 8, IS_BIG = BIG };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
-  double lR[NB * 9], xpos[NB * 3], xmat[NB * 9];
-  double cdof[NV * 6], cdof_dot[NV * 6], cinert[NB * 10], crb[NB * 10];
-  double cvel[NB * 6], cacc[NB * 6], buf[NV * 6];
-  double M[NV * LD], L[NV * LD], H[NV * LD], Linv[NV], Hinv[NV];
-  double qfrc_bias[NV], qfrc_act[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV];
-  double Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV], qfrc_con[NV];
-  double refcube[4];
-  double J[NEFC * LD];
-  double ekp[NEFC], eB[NEFC], eD[NEFC], earef[NEFC], eJaref[NEFC], eJv[NEFC];
-  double cdist[MAXCON], cpos[MAXCON * 3], cframe[MAXCON * 9];
-  int etype[NEFC];   // 0 equality, 1 limit / contact (inequality)
-  int cpair[MAXCON], cefc[MAXCON];
-  int nefc, ncon, ne, nl, overflow, iters, pad0, pad1;
+  double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
+  double M[NTRI], H[NTRI], invd[NV];
+  double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
+  double anchors[12];
+  union {
+    struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
+    struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
+  };
+  double cdist[MAXC], cpos[MAXC * 3], cframe[MAXC * 9];
+  int cpair[MAXC], crow[MAXC];
+  int rmeta[NROW];   // bits 0-7 index (eq / contact / dof), 8 sign, 9-11 sub-row, 12-13 kind (0 connect 1 joint-eq 2 limit 3 contact), 16 inequality
+  int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
+  int nR, nC, nF, nU, nefc, ncon, overflow, iters;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,6 +167,7 @@ __device__ __forceinline__ void quat2mat(double* m, const double* q) {
   m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
   m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // fk(): body frames of the 13 jointed bodies.  Lane b builds the local transform of body b
@@ -205,6 +222,7 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
     __syncwarp();
   }
 }
+
 
 // cinert_cdof(): spatial inertia of every (composite) body and motion axis of every dof, both expressed
 // about a per-tree reference point (robot: fixed world point; cube: its own centre of mass).
@@ -271,7 +289,9 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
   __syncwarp();
 }
 
-// crb_mass(): composite rigid-body inertias (subtree = contiguous DFS range) and the joint-space inertia M.
+
+// crb_mass(): composite rigid-body inertias (subtree = contiguous DFS range) and the joint-space inertia M
+// (packed lower triangle; the robot-cube block is structurally zero and never written).
 template <class S>
 __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   for (int w = lane; w < nba * 10; w += 32) {
@@ -292,47 +312,88 @@ __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba
     const double* b = s.buf + i * 6;
     double v = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
     if (i == j) v += m->d.armature[i];
-    s.M[i * LD + j] = v;
-    s.M[j * LD + i] = v;
+    s.M[TRI(i, j)] = v;
   }
   __syncwarp();
 }
 
-// chol(): dense Cholesky A = L L' of the leading n x n block, in place (lower triangle), lane i owns row i.
-// invd[k] = 1 / L[k][k].
-__device__ void chol(double* A, double* invd, int n, int lane) {
-  for (int j = 0; j < n; j++) {
-    double sv = 0;
-    if (lane >= j && lane < n) {
-      const double* ri = A + lane * LD;
-      const double* rj = A + j * LD;
-      double s0 = ri[j], s1 = 0;
-      int k = 0;
-      for (; k + 1 < j; k += 2) { s0 -= ri[k] * rj[k]; s1 -= ri[k + 1] * rj[k + 1]; }
-      if (k < j) s0 -= ri[k] * rj[k];
-      sv = s0 + s1;
-    }
-    double sjj = __shfl_sync(FULLMASK, sv, j);
+// chol_blk<N0, N>(): Cholesky of the diagonal block rows/cols [N0, N0+N) of a packed symmetric matrix,
+// src -> dst (may alias).  Lane i owns row i in registers; finished rows are broadcast through dst.
+// `dadd` is added to the lane's diagonal entry first (Euler: h * damping).  invd[k] = 1 / L[k][k].
+// Fully unrolled: every shared-memory offset is an immediate, no index arithmetic in the inner loops.
+template <int N0, int N>
+__device__ __noinline__ void chol_blk(const double* src, double* dst, double* invd, double dadd, int lane) {
+  const int i = lane;
+  const bool mine = (i >= N0 && i < N0 + N);
+  const int ro = i * (i + 1) / 2 + N0;
+  double row[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) row[k] = (mine && N0 + k <= i) ? src[ro + k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < N; k++) if (N0 + k == i) row[k] += dadd;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    const double* rj = dst + TRI(N0 + j, N0);
+    double s0 = row[j], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < j; k++) { if (k & 1) s1 -= row[k] * rj[k]; else s0 -= row[k] * rj[k]; }
+    double sv = s0 + s1;
+    double sjj = __shfl_sync(FULLMASK, sv, N0 + j);
     if (sjj < MINVAL) sjj = MINVAL;
     double inv = rsqrt(sjj);
-    if (lane == j) { A[j * LD + j] = sjj * inv; invd[j] = inv; }
-    else if (lane > j && lane < n) A[lane * LD + j] = sv * inv;
+    double l = (i == N0 + j) ? sjj * inv : sv * inv;
+    row[j] = l;
+    if (mine && i >= N0 + j) dst[ro + j] = l;
+    if (i == N0 + j) invd[N0 + j] = inv;
     __syncwarp();
   }
 }
-// chol_solve(): x = (L L')^-1 b ; every lane passes its b (lane >= n: ignored) and gets x for its row.
-__device__ double chol_solve(const double* L, const double* invd, int n, int lane, double b) {
-  for (int k = 0; k < n; k++) {
+// solve_blk<N0, N>(): x = (L L')^-1 b on the same block; lane i passes b_i and receives x_i (other lanes: unchanged).
+template <int N0, int N>
+__device__ __noinline__ double solve_blk(const double* L, const double* invd, int lane, double b) {
+  const int i = lane;
+  const int ro = i * (i + 1) / 2;
+#pragma unroll
+  for (int k = N0; k < N0 + N; k++) {
     double yk = __shfl_sync(FULLMASK, b, k) * invd[k];
-    if (lane == k) b = yk;
-    else if (lane > k && lane < n) b -= L[lane * LD + k] * yk;
+    if (i == k) b = yk;
+    else if (i > k && i < N0 + N) b -= L[ro + k] * yk;
   }
-  for (int k = n - 1; k >= 0; k--) {
+#pragma unroll
+  for (int k = N0 + N - 1; k >= N0; k--) {
     double xk = __shfl_sync(FULLMASK, b, k) * invd[k];
-    if (lane == k) b = xk;
-    else if (lane < k) b -= L[k * LD + lane] * xk;
+    if (i == k) b = xk;
+    else if (i < k && i >= N0) b -= L[TRI(k, 0) + i] * xk;
   }
   return b;
+}
+// factor / solve with the block structure: coupled => one 18 x 18 block, else robot 12 x 12 and cube 6 x 6
+__device__ __forceinline__ void chol_sys(const double* src, double* dst, double* invd, double dadd, int lane, int nva, bool coupled) {
+  if (coupled) chol_blk<0, 18>(src, dst, invd, dadd, lane);
+  else {
+    chol_blk<0, 12>(src, dst, invd, dadd, lane);
+    if (nva > NH) chol_blk<12, 6>(src, dst, invd, dadd, lane);
+  }
+}
+__device__ __forceinline__ double solve_sys(const double* L, const double* invd, int lane, int nva, bool coupled, double b) {
+  if (coupled) return solve_blk<0, 18>(L, invd, lane, b);
+  b = solve_blk<0, 12>(L, invd, lane, b);
+  if (nva > NH) b = solve_blk<12, 6>(L, invd, lane, b);
+  return b;
+}
+// y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
+template <class S>
+__device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const double* v) {
+  double acc = 0;
+  const int ro = lane * (lane + 1) / 2;
+  if (lane < NH) {
+#pragma unroll
+    for (int j = 0; j < NH; j++) acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+  } else if (lane < nva) {
+#pragma unroll
+    for (int j = NH; j < NV; j++) acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+  }
+  return acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,6 +553,7 @@ __device__ int box_box(RawCon* out, const double* p1, const double* R1, const do
   return cnt;
 }
 
+
 __device__ void geom_pose(const double* xpos, const double* xmat, const DevModel* __restrict__ m, int g, double* pos, double* mat) {
   int b = m->d.geom_body[g];
   const double* gp = m->d.geom_pos[g];
@@ -507,6 +569,7 @@ __device__ void geom_pose(const double* xpos, const double* xmat, const DevModel
     }
   }
 }
+
 
 template <class S>
 __device__ void collide(S& s, const DevModel* __restrict__ m, int lane, int nba) {
@@ -538,7 +601,7 @@ __device__ void collide(S& s, const DevModel* __restrict__ m, int lane, int nba)
   int total = __shfl_sync(FULLMASK, incl, 31);
   for (int c = 0; c < n; c++) {
     int idx = base + c;
-    if (idx >= MAXCON) break;
+    if (idx >= S::MAXC) break;
     s.cdist[idx] = rc[c].dist;
     s.cpair[idx] = lane;
     double f[9];
@@ -557,7 +620,7 @@ __device__ void collide(S& s, const DevModel* __restrict__ m, int lane, int nba)
     for (int k = 0; k < 3; k++) s.cpos[idx * 3 + k] = rc[c].pos[k];
   }
   if (lane == 0) {
-    if (total > MAXCON) { s.overflow += total - MAXCON; total = MAXCON; }
+    if (total > S::MAXC) { s.overflow += total - S::MAXC; total = S::MAXC; }
     s.ncon = total;
   }
   __syncwarp();
@@ -577,24 +640,6 @@ __device__ double impedance(const double* solimp_in, double pos) {
   return s0 + y * (s1 - s0);
 }
 
-// row_params(): R, D and the reference-acceleration coefficients of one row.  For the rows of a pyramidal
-// contact `diag` is the first row's diagApprox and `pyr_mu` > 0 (R = 2 mu^2 R_first); otherwise pyr_mu = 0.
-template <class S>
-__device__ __forceinline__ void row_params(S& s, int r, double timestep, const double* solref_in, const double* solimp, double pos, double diag, double pyr_mu, int type) {
-  double sr0 = solref_in[0], sr1 = solref_in[1];
-  if (sr0 > 0) sr0 = fmax(sr0, 2 * timestep);
-  double imp = impedance(solimp, pos);
-  double R = fmax(MINVAL, (1 - imp) * diag / imp);
-  if (pyr_mu > 0) R = 2 * pyr_mu * pyr_mu * R;
-  double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
-  double K, B;
-  if (sr0 > 0) { K = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmax(MINVAL, dmax * sr0); }
-  else { K = -sr0 / fmax(MINVAL, dmax * dmax); B = -sr1 / fmax(MINVAL, dmax); }
-  s.eD[r] = 1 / R;
-  s.ekp[r] = K * imp * pos;
-  s.eB[r] = B;
-  s.etype[r] = type;
-}
 
 // point Jacobian column of dof j for a world point attached to body b (0 if j does not move b)
 template <class S>
@@ -613,28 +658,112 @@ __device__ __forceinline__ void jac_col(const S& s, const DevModel* __restrict__
   }
 }
 
-// make_rows(): equality (7 rows), joint limits, pyramidal contact rows; J dense [nefc][LD].
-template <int NEFC, class S>
-__device__ void make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
+
+// row storage of the blocked Jacobian: robot rows [0, nR) x 12, cube rows [nR, nR+nC) x 6, coupled rows x 18,
+// then nU joint-limit rows (a signed unit vector each, no storage)
+template <class S> __device__ __forceinline__ double* row_r(S& s, int r) { return s.pool + r * SR; }
+template <class S> __device__ __forceinline__ double* row_c(S& s, int r) { return s.pool + s.nR * SR + (r - s.nR) * SC; }
+template <class S> __device__ __forceinline__ double* row_f(S& s, int r) { return s.pool + s.nR * SR + s.nC * SC + (r - s.nR - s.nC) * SF; }
+
+// dot product of constraint row r with an 18-vector
+template <class S>
+__device__ __forceinline__ double row_dot(S& s, int r, const double* v) {
+  double acc = 0;
+  if (r < s.nR) {
+    const double* p = row_r(s, r);
+#pragma unroll
+    for (int k = 0; k < NH; k++) acc += p[k] * v[k];
+  } else if (r < s.nR + s.nC) {
+    const double* p = row_c(s, r);
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc += p[k] * v[NH + k];
+  } else if (r < s.nR + s.nC + s.nF) {
+    const double* p = row_f(s, r);
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc += p[k] * v[k];
+  } else {
+    int meta = s.rmeta[r];
+    double x = v[meta & 0xff];
+    acc = (meta & 0x100) ? -x : x;
+  }
+  return acc;
+}
+
+// make_rows(): equality (7 robot rows), pyramidal contact rows by block type, joint-limit unit rows; then R, D
+// and the reference acceleration of every row.  Returns false if the layout's capacity is exceeded.
+template <class S>
+__device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   const double h = m->d.timestep;
-  // --- connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1) -> stash in buf
+  // connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1)
   if (lane < 4) {
     int e = lane >> 1, side = lane & 1;
     int b = side ? m->d.con_body2[e] : m->d.con_body1[e];
     const double* a = side ? m->d.con_anchor2[e] : m->d.con_anchor1[e];
     const double* R = s.xmat + b * 9;
-    for (int r = 0; r < 3; r++) s.buf[lane * 3 + r] = s.xpos[b * 3 + r] + R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
+    for (int r = 0; r < 3; r++) s.anchors[lane * 3 + r] = s.xpos[b * 3 + r] + R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
+  }
+  // limits: lane j < 12, lower then upper (both can not be active for a positive-width range)
+  int lim = 0, neg = 0;
+  if (lane < NH && m->d.jnt_limited[lane]) {
+    double v = s.qpos[lane];
+    if (v - m->d.jnt_range[lane][0] < 0) lim = 1;
+    else if (m->d.jnt_range[lane][1] - v < 0) { lim = 1; neg = 1; }
+  }
+  unsigned bal = __ballot_sync(FULLMASK, lim);
+  const int nU = __popc(bal);
+  // row bookkeeping (lane 0): contacts -> groups
+  if (lane == 0) {
+    int nRc = 0, nC = 0, nF = 0, nc = s.ncon;
+    for (int c = 0; c < nc; c++) {
+      const PairParam& pp = m->pair[s.cpair[c]];
+      int rows = 2 * (pp.dim - 1);
+      if (pp.ptype == 0) nRc += rows; else if (pp.ptype == 1) nC += rows; else nF += rows;
+    }
+    int nR = 7 + nRc;
+    bool fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
+    if (!fits) {
+      // drop contacts from the end until it fits (the small layout aborts the env instead, see the kernel)
+      s.overflow += 1;
+      while (nc > 0 && !fits) {
+        nc--;
+        const PairParam& pp = m->pair[s.cpair[nc]];
+        int rows = 2 * (pp.dim - 1);
+        if (pp.ptype == 0) { nRc -= rows; nR -= rows; } else if (pp.ptype == 1) nC -= rows; else nF -= rows;
+        fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
+      }
+      s.ncon = nc;
+    }
+    int r0 = 7, r1 = nR, r2 = nR + nC, orow = 7 + nU;
+    for (int c = 0; c < nc; c++) {
+      const PairParam& pp = m->pair[s.cpair[c]];
+      int rows = 2 * (pp.dim - 1), base;
+      if (pp.ptype == 0) { base = r0; r0 += rows; } else if (pp.ptype == 1) { base = r1; r1 += rows; } else { base = r2; r2 += rows; }
+      s.crow[c] = base;
+      for (int k = 0; k < rows; k++) { s.rmeta[base + k] = c | (k << 9) | (3 << 12) | RM_INEQ; s.omap[base + k] = orow + k; }
+      orow += rows;
+    }
+    for (int k = 0; k < 6; k++) { s.rmeta[k] = (k / 3) | ((k % 3) << 9); s.omap[k] = k; }
+    s.rmeta[6] = (1 << 12); s.omap[6] = 6;
+    s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU;
   }
   __syncwarp();
-  for (int w = lane; w < 6 * NV; w += 32) {
-    int row = w / NV, j = w % NV;
+  if (lim) {
+    int u = __popc(bal & ((1u << lane) - 1));
+    int r = s.nR + s.nC + s.nF + u;
+    s.rmeta[r] = lane | (neg << 8) | (2 << 12) | RM_INEQ;
+    s.omap[r] = 7 + u;
+  }
+  // equality Jacobian rows (robot block)
+  for (int w = lane; w < 6 * NH; w += 32) {
+    int row = w / NH, j = w % NH;
     int e = row / 3, r = row % 3;
     double l1[3], l2[3], rt[3];
-    jac_col(s, m, m->d.con_body1[e], j, s.buf + (2 * e) * 3, l1, rt);
-    jac_col(s, m, m->d.con_body2[e], j, s.buf + (2 * e + 1) * 3, l2, rt);
-    s.J[row * LD + j] = l1[r] - l2[r];
+    jac_col(s, m, m->d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
+    jac_col(s, m, m->d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
+    s.pool[row * SR + j] = l1[r] - l2[r];
   }
-  for (int j = lane; j < NV; j += 32) {
+  if (lane < NH) {
+    int j = lane;
     double v = 0;
     if (j == m->d.jeq_dof1) v = 1;
     if (j == m->d.jeq_dof2) {
@@ -642,50 +771,15 @@ __device__ void make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       const double* pc = m->d.jeq_polycoef;
       v = -(pc[1] + 2 * pc[2] * dif + 3 * pc[3] * dif * dif + 4 * pc[4] * dif * dif * dif);
     }
-    s.J[6 * LD + j] = v;
+    s.pool[6 * SR + j] = v;
   }
-  if (lane < 6) {
-    int e = lane / 3, r = lane % 3;
-    double pos = s.buf[(2 * e) * 3 + r] - s.buf[(2 * e + 1) * 3 + r];
-    row_params(s, lane, h, m->d.con_solref[e], m->d.con_solimp[e], pos, m->d.con_diag[e], 0.0, 0);
-  } else if (lane == 6) {
-    int d1 = m->d.jeq_dof1, d2 = m->d.jeq_dof2;
-    double p1 = s.qpos[d1] - m->d.qpos0[d1], dif = s.qpos[d2] - m->d.qpos0[d2];
-    const double* pc = m->d.jeq_polycoef;
-    double pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
-    row_params(s, 6, h, m->d.jeq_solref, m->d.jeq_solimp, pos, m->d.jeq_diag, 0.0, 0);
-  }
-  // --- limits: lane j < 12, lower then upper (both can not be active for a positive-width range)
-  int lim = 0; double dist = 0; double sgn = 0;
-  if (lane < NH && m->d.jnt_limited[lane]) {
-    double v = s.qpos[lane];
-    double dl = v - m->d.jnt_range[lane][0], du = m->d.jnt_range[lane][1] - v;
-    if (dl < 0) { lim = 1; dist = dl; sgn = 1; }
-    else if (du < 0) { lim = 1; dist = du; sgn = -1; }
-  }
-  unsigned bal = __ballot_sync(FULLMASK, lim);
-  int nl = __popc(bal);
-  int ne = 7;
-  if (lim) {
-    int r = ne + __popc(bal & ((1u << lane) - 1));
-    for (int j = 0; j < NV; j++) s.J[r * LD + j] = (j == lane ? sgn : 0.0);
-    row_params(s, r, h, m->d.jnt_solref[lane], m->d.jnt_solimp[lane], dist, m->d.dof_invweight0[lane], 0.0, 1);
-  }
-  // --- contacts: row offsets (lane 0), then (contact, dof) items
-  if (lane == 0) {
-    int r = ne + nl, nc = 0;
-    for (int c = 0; c < s.ncon; c++) {
-      int rows = 2 * (m->pair[s.cpair[c]].dim - 1);
-      if (r + rows > NEFC) { s.overflow += s.ncon - c; break; }
-      s.cefc[c] = r; r += rows; nc++;
-    }
-    s.ncon = nc; s.nefc = r; s.ne = ne; s.nl = nl;
-  }
-  __syncwarp();
-  int ncon = s.ncon;
+  // contact Jacobian rows: items (contact, dof)
+  const int ncon = s.ncon;
   for (int w = lane; w < ncon * NV; w += 32) {
     int c = w / NV, j = w % NV;
     const PairParam& pp = m->pair[s.cpair[c]];
+    if (pp.ptype == 0 && j >= NH) continue;
+    if (pp.ptype == 1 && j < NH) continue;
     int b1 = m->d.geom_body[pp.g1], b2 = m->d.geom_body[pp.g2];
     const double* pt = s.cpos + c * 3;
     const double* f = s.cframe + c * 9;
@@ -694,33 +788,70 @@ __device__ void make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     jac_col(s, m, b2, j, pt, l2, r2);
     double dl[3] = {l2[0] - l1[0], l2[1] - l1[1], l2[2] - l1[2]}, dr[3] = {r2[0] - r1[0], r2[1] - r1[1], r2[2] - r1[2]};
     double Jn = dot3(f, dl), Jt1 = dot3(f + 3, dl), Jt2 = dot3(f + 6, dl), Jr = dot3(f, dr);
-    int r0 = s.cefc[c];
+    int r0 = s.crow[c];
+    double* p; int st;
+    if (pp.ptype == 0) { p = row_r(s, r0) + j; st = SR; }
+    else if (pp.ptype == 1) { p = row_c(s, r0) + (j - NH); st = SC; }
+    else { p = row_f(s, r0) + j; st = SF; }
     double mu = pp.friction[0];
-    s.J[(r0 + 0) * LD + j] = Jn + mu * Jt1;
-    s.J[(r0 + 1) * LD + j] = Jn + (-mu) * Jt1;
-    s.J[(r0 + 2) * LD + j] = Jn + mu * Jt2;
-    s.J[(r0 + 3) * LD + j] = Jn + (-mu) * Jt2;
+    p[0] = Jn + mu * Jt1;
+    p[st] = Jn + (-mu) * Jt1;
+    p[2 * st] = Jn + mu * Jt2;
+    p[3 * st] = Jn + (-mu) * Jt2;
     if (pp.dim == 4) {
       double mt = pp.friction[1];
-      s.J[(r0 + 4) * LD + j] = Jn + mt * Jr;
-      s.J[(r0 + 5) * LD + j] = Jn + (-mt) * Jr;
+      p[4 * st] = Jn + mt * Jr;
+      p[5 * st] = Jn + (-mt) * Jr;
     }
   }
-  for (int w = lane; w < ncon * 6; w += 32) {
-    int c = w / 6, k = w % 6;
-    const PairParam& pp = m->pair[s.cpair[c]];
-    if (k >= 2 * (pp.dim - 1)) continue;
-    double mu = pp.friction[0];
-    double diag_first = pp.tran + mu * mu * pp.tran;
-    row_params(s, s.cefc[c] + k, h, pp.solref, pp.solimp, s.cdist[c], diag_first, mu / sqrt(m->d.impratio), 1);
+  __syncwarp();
+  // per-row regularisation and reference acceleration (mj_makeImpedance, mj_referenceConstraint)
+  const int nefc = s.nefc;
+  for (int r = lane; r < nefc; r += 32) {
+    int meta = s.rmeta[r], kind = (meta >> 12) & 3, idx = meta & 0xff, sub = (meta >> 9) & 7;
+    const double *solref, *solimp;
+    double pos, diag, pyr = 0;
+    if (kind == 0) {
+      pos = s.anchors[(2 * idx) * 3 + sub] - s.anchors[(2 * idx + 1) * 3 + sub];
+      solref = m->d.con_solref[idx]; solimp = m->d.con_solimp[idx]; diag = m->d.con_diag[idx];
+    } else if (kind == 1) {
+      int d1 = m->d.jeq_dof1, d2 = m->d.jeq_dof2;
+      double p1 = s.qpos[d1] - m->d.qpos0[d1], dif = s.qpos[d2] - m->d.qpos0[d2];
+      const double* pc = m->d.jeq_polycoef;
+      pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
+      solref = m->d.jeq_solref; solimp = m->d.jeq_solimp; diag = m->d.jeq_diag;
+    } else if (kind == 2) {
+      double v = s.qpos[idx];
+      pos = (meta & 0x100) ? m->d.jnt_range[idx][1] - v : v - m->d.jnt_range[idx][0];
+      solref = m->d.jnt_solref[idx]; solimp = m->d.jnt_solimp[idx]; diag = m->d.dof_invweight0[idx];
+    } else {
+      const PairParam& pp = m->pair[s.cpair[idx]];
+      double mu = pp.friction[0];
+      pos = s.cdist[idx];
+      solref = pp.solref; solimp = pp.solimp;
+      diag = pp.tran + mu * mu * pp.tran;     // the pyramid's first-row diagApprox; all rows share R = 2 mu^2 R_first
+      pyr = mu / sqrt(m->d.impratio);
+    }
+    double sr0 = solref[0], sr1 = solref[1];
+    if (sr0 > 0) sr0 = fmax(sr0, 2 * h);
+    double imp = impedance(solimp, pos);
+    double R = fmax(MINVAL, (1 - imp) * diag / imp);
+    if (pyr > 0) R = 2 * pyr * pyr * R;
+    double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
+    double K, B;
+    if (sr0 > 0) { K = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmax(MINVAL, dmax * sr0); }
+    else { K = -sr0 / fmax(MINVAL, dmax * dmax); B = -sr1 / fmax(MINVAL, dmax); }
+    double vel = row_dot(s, r, s.qvel);
+    s.eD[r] = 1 / R;
+    s.earef[r] = -B * vel - K * imp * pos;
   }
   __syncwarp();
+  return s.overflow == 0;
 }
 
-// velocity_rne(): cvel, cdof_dot, bias forces (RNE with zero qacc), efc reference accelerations.
+// velocity_rne(): cvel, cdof_dot, bias forces (RNE with zero qacc).
 template <class S>
 __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
-  // cvel[b] = sum over ancestor dofs (ascending) of cdof_j * qvel_j
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
     unsigned mask = m->d.ancmask[b];
@@ -778,17 +909,10 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
     const double* b = s.cvel + m->d.dof_body[lane] * 6;
     s.qfrc_bias[lane] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
   }
-  // efc_vel and aref
-  for (int r = lane; r < s.nefc; r += 32) {
-    const double* Jr = s.J + r * LD;
-    double v = 0;
-    for (int k = 0; k < nva; k++) v += Jr[k] * s.qvel[k];
-    s.earef[r] = -s.eB[r] * v - s.ekp[r];
-  }
   __syncwarp();
 }
 
-// actuation(): affine PD "general" actuators with ctrl and force clamps; then qfrc_smooth.
+// actuation_smooth(): affine PD "general" actuators with ctrl and force clamps, passive damping; qfrc_smooth.
 template <class S>
 __device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   double force = 0;
@@ -808,51 +932,40 @@ __device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane,
     double fa = __shfl_sync(FULLMASK, force, a);
     if (lane < NV) qa += m->d.act_moment[a][lane] * fa;
   }
-  if (lane < nva) {
-    s.qfrc_act[lane] = qa;
-    s.qfrc_smooth[lane] = -m->d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
-  }
+  if (lane < nva) s.qfrc_smooth[lane] = -m->d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
   __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// newton(): primal Newton solver with exact line search over the piecewise-quadratic cost (pyramidal cones).
-template <int NEFC, class S>
+// Newton: primal solver with exact line search over the piecewise-quadratic cost (pyramidal cones).
+template <class S>
 struct Newton {
   S& s; const DevModel* __restrict__ m; int lane, nva, nefc;
+  bool coupled;
   double gauss, cost, qg0, qg1, qg2;
-  double qa[3], qb[3], qc[3];  // per-lane quadratic coefficients of rows lane, lane+32, lane+64
-  int lsn;
+  double qa[S::NROW / 32 + 1], qb[S::NROW / 32 + 1], qc[S::NROW / 32 + 1];  // per-lane quadratic coefficients of rows lane + 32 t
 
-  __device__ double mulM_row(const double* v) const {
-    double acc = 0;
-    if (lane < nva) { const double* r = s.M + lane * LD; for (int k = 0; k < nva; k++) acc += r[k] * v[k]; }
-    return acc;
-  }
-  __device__ double jdot(int r, const double* v) const {
-    const double* Jr = s.J + r * LD;
-    double acc = 0;
-    for (int k = 0; k < nva; k++) acc += Jr[k] * v[k];
-    return acc;
-  }
-  // constraint cost at jar = J*x - aref for a trial vector x (no side effects)
-  __device__ double cost_of(const double* x) const {
-    double c = 0;
+  __device__ __forceinline__ bool active(int r, double jar) const { return !(s.rmeta[r] & RM_INEQ) || jar < 0; }
+
+  // out[r] = J_r . v (- aref_r if sub)
+  __device__ void rows_times(const double* v, double* out, bool sub_aref) {
     for (int r = lane; r < nefc; r += 32) {
-      double jar = jdot(r, x) - s.earef[r];
-      if (s.etype[r] == 0 || jar < 0) c += 0.5 * s.eD[r] * jar * jar;
+      double d = row_dot(s, r, v);
+      out[r] = sub_aref ? d - s.earef[r] : d;
     }
+  }
+  __device__ double cost_rows(const double* jar) const {
+    double c = 0;
+    for (int r = lane; r < nefc; r += 32) { double j = jar[r]; if (active(r, j)) c += 0.5 * s.eD[r] * j * j; }
     return warp_sum(c);
   }
-  // cost, gradient; optionally Hessian factor + Newton direction
-  __device__ void update(bool hessian) {
-    // constraint forces, cost
+  // cost and gradient at the current point (Jaref, Ma valid); eJv is used as the efc_force scratch
+  __device__ void update_cost_grad() {
     double c = 0;
     for (int r = lane; r < nefc; r += 32) {
       double jar = s.eJaref[r];
-      bool act = (s.etype[r] == 0 || jar < 0);
-      double f = act ? -s.eD[r] * jar : 0.0;
-      s.eJv[r] = f;  // eJv temporarily holds efc_force
+      bool act = active(r, jar);
+      s.eJv[r] = act ? -s.eD[r] * jar : 0.0;
       if (act) c += 0.5 * s.eD[r] * jar * jar;
     }
     double g = 0;
@@ -860,70 +973,99 @@ struct Newton {
     __syncwarp();
     gauss = warp_sum(g);
     cost = gauss + warp_sum(c);
+    // qfrc_constraint = J' f, by row group
     if (lane < nva) {
       double q = 0;
-      for (int r = 0; r < nefc; r++) q += s.J[r * LD + lane] * s.eJv[r];
+      const int nR = s.nR, nC = s.nC, nF = s.nF, nU = s.nU;
+      if (lane < NH) { for (int r = 0; r < nR; r++) q += s.pool[r * SR + lane] * s.eJv[r]; }
+      else { const double* p = s.pool + nR * SR + (lane - NH); for (int r = 0; r < nC; r++) q += p[r * SC] * s.eJv[nR + r]; }
+      { const double* p = s.pool + nR * SR + nC * SC + lane; for (int r = 0; r < nF; r++) q += p[r * SF] * s.eJv[nR + nC + r]; }
+      for (int u = 0; u < nU; u++) {
+        int r = nR + nC + nF + u, meta = s.rmeta[r];
+        if ((meta & 0xff) == lane) q += (meta & 0x100) ? -s.eJv[r] : s.eJv[r];
+      }
       s.qfrc_con[lane] = q;
       s.grad[lane] = s.Ma[lane] - s.qfrc_smooth[lane] - q;
     }
     __syncwarp();
-    if (!hessian) return;
-    build_H();
-    chol(s.H, s.Hinv, nva, lane);
-    double mg = chol_solve(s.H, s.Hinv, nva, lane, lane < nva ? s.grad[lane] : 0.0);
-    if (lane < nva) { s.Mgrad[lane] = mg; s.search[lane] = -mg; }
+  }
+  // H = M + J' diag(D * active) J (packed lower triangle), accumulated per block in registers
+  __device__ void build_H() {
+    const int nR = s.nR, nC = s.nC, nF = s.nF, nU = s.nU;
+    int ri[3], rj[3];      // robot-robot entries e = lane + 32 p < 78
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      int e = lane + 32 * p, i = 0;
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      ri[p] = i; rj[p] = e - i * (i + 1) / 2;
+    }
+    int ci = 0, cj = 0;    // cube-cube entry t = lane < 21
+    { int i = 0; while ((i + 1) * (i + 2) / 2 <= lane) i++; ci = i; cj = lane - i * (i + 1) / 2; }
+    double arr[3], acc_cc = 0, arc[3] = {0, 0, 0};
+#pragma unroll
+    for (int p = 0; p < 3; p++) arr[p] = (lane + 32 * p < 78) ? s.M[lane + 32 * p] : 0.0;
+    if (lane < 21 && nva > NH) acc_cc = s.M[TRI(NH + ci, NH + cj)];
+    for (int r = 0; r < nR; r++) {
+      if (!active(r, s.eJaref[r])) continue;
+      const double* p = s.pool + r * SR;
+      double D = s.eD[r];
+#pragma unroll
+      for (int q = 0; q < 3; q++) if (lane + 32 * q < 78) arr[q] += D * p[ri[q]] * p[rj[q]];
+    }
+    if (nva > NH) {
+      for (int r = 0; r < nC; r++) {
+        if (!active(nR + r, s.eJaref[nR + r])) continue;
+        const double* p = s.pool + nR * SR + r * SC;
+        if (lane < 21) acc_cc += s.eD[nR + r] * p[ci] * p[cj];
+      }
+      for (int r = 0; r < nF; r++) {
+        int g = nR + nC + r;
+        if (!active(g, s.eJaref[g])) continue;
+        const double* p = s.pool + nR * SR + nC * SC + r * SF;
+        double D = s.eD[g];
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < 78) arr[q] += D * p[ri[q]] * p[rj[q]];
+        if (lane < 21) acc_cc += D * p[NH + ci] * p[NH + cj];
+#pragma unroll
+        for (int q = 0; q < 3; q++) { int t = lane + 32 * q; if (t < 72) arc[q] += D * p[NH + t / NH] * p[t % NH]; }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) if (lane + 32 * p < 78) s.H[lane + 32 * p] = arr[p];
+    if (nva > NH) {
+      if (lane < 21) s.H[TRI(NH + ci, NH + cj)] = acc_cc;
+#pragma unroll
+      for (int q = 0; q < 3; q++) { int t = lane + 32 * q; if (t < 72) s.H[TRI(NH + t / NH, t % NH)] = arc[q]; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      for (int u = 0; u < nU; u++) {
+        int r = nR + nC + nF + u;
+        if (active(r, s.eJaref[r])) { int d = s.rmeta[r] & 0xff; s.H[TRI(d, d)] += s.eD[r]; }
+      }
+    }
     __syncwarp();
   }
-  // H = M + J' diag(D * active) J, lower triangle, 3x3 register tiles (21 lanes busy for 18 dofs)
-  __device__ void build_H() {
-    int nt = nva / 3;
-    int ti = -1, tj = -1;
-    {
-      int t = lane, i = 0;
-      while (i < nt && t > i) { t -= i + 1; i++; }
-      if (i < nt) { ti = i; tj = t; }
-    }
-    if (ti >= 0) {
-      double acc[9];
-      const double* Mi = s.M + (3 * ti) * LD + 3 * tj;
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) acc[3 * a + b] = Mi[a * LD + b];
-      for (int r = 0; r < nefc; r++) {
-        if (!(s.etype[r] == 0 || s.eJaref[r] < 0)) continue;
-        const double* Jr = s.J + r * LD;
-        double D = s.eD[r];
-        double ji0 = D * Jr[3 * ti], ji1 = D * Jr[3 * ti + 1], ji2 = D * Jr[3 * ti + 2];
-        double jj0 = Jr[3 * tj], jj1 = Jr[3 * tj + 1], jj2 = Jr[3 * tj + 2];
-        acc[0] += ji0 * jj0; acc[1] += ji0 * jj1; acc[2] += ji0 * jj2;
-        acc[3] += ji1 * jj0; acc[4] += ji1 * jj1; acc[5] += ji1 * jj2;
-        acc[6] += ji2 * jj0; acc[7] += ji2 * jj1; acc[8] += ji2 * jj2;
-      }
-      double* Hi = s.H + (3 * ti) * LD + 3 * tj;
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) Hi[a * LD + b] = acc[3 * a + b];
-    }
+  __device__ void newton_direction() {
+    build_H();
+    chol_sys(s.H, s.H, s.invd, 0.0, lane, nva, coupled);
+    double mg = solve_sys(s.H, s.invd, lane, nva, coupled, lane < nva ? s.grad[lane] : 0.0);
+    if (lane < nva) s.search[lane] = -mg;
     __syncwarp();
   }
   struct Pt { double alpha, cost, d0, d1; };
   __device__ void ls_eval(Pt& p) {
     double a = p.alpha, q0 = 0, q1 = 0, q2 = 0;
 #pragma unroll
-    for (int t = 0; t < (NEFC + 31) / 32; t++) {
+    for (int t = 0; t < S::NROW / 32 + 1; t++) {
       int r = lane + 32 * t;
-      if (r < nefc) {
-        if (s.etype[r] == 0 || s.eJaref[r] + a * s.eJv[r] < 0) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
-      }
+      if (r < nefc && active(r, s.eJaref[r] + a * s.eJv[r])) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
     }
     q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
     p.cost = a * a * q2 + a * q1 + q0;
     p.d0 = 2 * a * q2 + q1;
     p.d1 = 2 * q2;
     if (p.d1 <= 0) p.d1 = MINVAL;
-    lsn++;
   }
   __device__ double line_search(double scale) {
     double sn = 0;
@@ -931,15 +1073,15 @@ struct Newton {
     double snorm = sqrt(warp_sum(sn));
     if (snorm < MINVAL) return 0;
     double gtol = m->d.tolerance * m->d.ls_tolerance * snorm / scale;
-    double mv = mulM_row(s.search);
+    double mv = mulM_row(s, lane, nva, s.search);
     if (lane < nva) s.Mv[lane] = mv;
-    for (int r = lane; r < nefc; r += 32) s.eJv[r] = jdot(r, s.search);
+    rows_times(s.search, s.eJv, false);
     double g1 = 0, g2 = 0;
     if (lane < nva) { g1 = s.search[lane] * (s.Ma[lane] - s.qfrc_smooth[lane]); g2 = s.search[lane] * mv; }
     qg0 = gauss; qg1 = warp_sum(g1); qg2 = 0.5 * warp_sum(g2);
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < (NEFC + 31) / 32; t++) {
+    for (int t = 0; t < S::NROW / 32 + 1; t++) {
       int r = lane + 32 * t;
       if (r < nefc) {
         double D = s.eD[r], ja = s.eJaref[r], jv = s.eJv[r];
@@ -983,27 +1125,27 @@ struct Newton {
   }
 
   __device__ void solve() {
-    lsn = 0;
     const double scale = 1.0 / (m->d.meaninertia * (double)NV);
-    // warmstart(): better of qacc_warmstart and qacc_smooth
-    {
-      double cw = cost_of(s.warm);
-      double ma = mulM_row(s.warm), g = 0;
-      if (lane < nva) g = 0.5 * (ma - s.qfrc_smooth[lane]) * (s.warm[lane] - s.qacc_smooth[lane]);
-      cw += warp_sum(g);
-      double cs = cost_of(s.qacc_smooth);
-      bool use_smooth = cw > cs;
-      if (lane < nva) {
-        s.qacc[lane] = use_smooth ? s.qacc_smooth[lane] : s.warm[lane];
-        s.Ma[lane] = use_smooth ? s.qfrc_smooth[lane] : ma;  // M*qacc_smooth == qfrc_smooth up to rounding; recomputed below
-      }
-      __syncwarp();
-      double ma2 = mulM_row(s.qacc);
-      if (lane < nva) s.Ma[lane] = ma2;
-    }
-    for (int r = lane; r < nefc; r += 32) s.eJaref[r] = jdot(r, s.qacc) - s.earef[r];
+    coupled = s.nF > 0;
+    // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
+    rows_times(s.warm, s.eJaref, true);
+    rows_times(s.qacc_smooth, s.eJv, true);
+    double ma = mulM_row(s, lane, nva, s.warm), g = 0;
+    if (lane < nva) g = 0.5 * (ma - s.qfrc_smooth[lane]) * (s.warm[lane] - s.qacc_smooth[lane]);
     __syncwarp();
-    update(true);
+    double cw = cost_rows(s.eJaref) + warp_sum(g);
+    double cs = cost_rows(s.eJv);
+    bool use_smooth = cw > cs;
+    if (use_smooth) {
+      for (int r = lane; r < nefc; r += 32) s.eJaref[r] = s.eJv[r];
+      if (lane < nva) s.qacc[lane] = s.qacc_smooth[lane];
+      __syncwarp();
+      double ma2 = mulM_row(s, lane, nva, s.qacc);
+      if (lane < nva) s.Ma[lane] = ma2;
+    } else if (lane < nva) { s.qacc[lane] = s.warm[lane]; s.Ma[lane] = ma; }
+    __syncwarp();
+    update_cost_grad();
+    newton_direction();
     int iter = 0;
     const int maxiter = m->d.iterations;
     while (iter < maxiter) {
@@ -1013,18 +1155,13 @@ struct Newton {
       for (int r = lane; r < nefc; r += 32) s.eJaref[r] += alpha * s.eJv[r];
       __syncwarp();
       double oldcost = cost;
-      update(false);
+      update_cost_grad();
       iter++;
       double gn = 0;
       if (lane < nva) gn = s.grad[lane] * s.grad[lane];
       double improvement = scale * (oldcost - cost), gradient = scale * sqrt(warp_sum(gn));
       if (improvement < m->d.tolerance || gradient < m->d.tolerance) break;
-      // continue: Hessian at the new point
-      build_H();
-      chol(s.H, s.Hinv, nva, lane);
-      double mg = chol_solve(s.H, s.Hinv, nva, lane, lane < nva ? s.grad[lane] : 0.0);
-      if (lane < nva) { s.Mgrad[lane] = mg; s.search[lane] = -mg; }
-      __syncwarp();
+      newton_direction();
     }
     if (lane == 0) s.iters += iter;
     if (lane < nva) s.warm[lane] = s.qacc[lane];
@@ -1032,36 +1169,32 @@ struct Newton {
   }
 };
 
-// forward(): everything mj_forward does for this model.
-template <int NEFC, class S>
-__device__ void forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+// forward(): everything mj_forward does for this model.  Returns false if the layout overflowed.
+template <class S>
+__device__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   fk(s, m, lane, nba);
   cinert_cdof(s, m, lane, nba, nva);
   crb_mass(s, m, lane, nba, nva);
-  for (int w = lane; w < nva * LD; w += 32) s.L[w] = s.M[w];
-  __syncwarp();
-  chol(s.L, s.Linv, nva, lane);
-  collide(s, m, lane, nba);
-  make_rows<NEFC>(s, m, lane, nva);
   velocity_rne(s, m, lane, nba, nva);
   actuation_smooth(s, m, lane, nva);
-  double qs = chol_solve(s.L, s.Linv, nva, lane, lane < nva ? s.qfrc_smooth[lane] : 0.0);
+  chol_sys(s.M, s.H, s.invd, 0.0, lane, nva, false);
+  double qs = solve_sys(s.H, s.invd, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] : 0.0);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
-  Newton<NEFC, S> nw{s, m, lane, nva, s.nefc};
+  collide(s, m, lane, nba);
+  bool ok = make_rows(s, m, lane, nva);
+  if (!ok && !S::IS_BIG) return false;
+  Newton<S> nw{s, m, lane, nva, s.nefc};
   nw.solve();
+  return true;
 }
 
 // euler(): (M + h*diag(damping))^-1 (qfrc_smooth + qfrc_constraint), semi-implicit advance.
 template <class S>
 __device__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   const double h = m->d.timestep;
-  for (int w = lane; w < nva * LD; w += 32) s.L[w] = s.M[w];
-  __syncwarp();
-  if (lane < nva) s.L[lane * LD + lane] += h * m->d.damping[lane];
-  __syncwarp();
-  chol(s.L, s.Linv, nva, lane);
-  double qacc = chol_solve(s.L, s.Linv, nva, lane, lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
+  chol_sys(s.M, s.H, s.invd, lane < nva ? h * m->d.damping[lane] : 0.0, lane, nva, false);
+  double qacc = solve_sys(s.H, s.invd, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
   if (lane < nva) s.qvel[lane] += h * qacc;
   __syncwarp();
   if (lane < NH) s.qpos[lane] += h * s.qvel[lane];
@@ -1086,7 +1219,6 @@ __device__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG: one stream per env, key = seed, counter = (env, draw index)
 __device__ __forceinline__ void philox_round(uint32_t* c, uint32_t k0, uint32_t k1) {
   uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
@@ -1208,14 +1340,15 @@ __device__ void store_state(const S& s, double* __restrict__ st, int lane) {
   }
 }
 
-// reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.
-template <int NEFC, class S>
-__device__ void reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
+
+// reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.  false: layout overflow.
+template <class S>
+__device__ bool reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
   for (int w = lane; w < NQ; w += 32) s.qpos[w] = m->d.init_qpos[w];
   if (lane < NV) s.qvel[lane] = 0;
   if (lane < NU) s.ctrl[lane] = m->d.init_ctrl[lane];
   __syncwarp();
-  forward<NEFC>(s, m, lane, nba, nva);
+  if (!forward(s, m, lane, nba, nva)) return false;
   double oxy[2] = {m->d.initial_gripper_xpos[0], m->d.initial_gripper_xpos[1]};
   double g[3];
   if (lane == 0) {
@@ -1240,16 +1373,20 @@ __device__ void reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ 
     s.goal[0] = g[0]; s.goal[1] = g[1]; s.goal[2] = g[2];
   }
   __syncwarp();
-  forward<NEFC>(s, m, lane, nba, nva);
+  return forward(s, m, lane, nba, nva);
 }
 
 template <class S>
-__device__ void debug_dump(const S& s, const StepArgs& a, int lane, int nva) {
-  // layout (doubles): [0] nefc [1] ncon [2..] M(18*18) bias smooth qacc_smooth qacc xpos(39) xmat(117) J(nefc*18) aref D contact(7*ncon)
+__device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
+  // layout (doubles): [0] nefc [1] ncon [2] iters [3] overflow | M(18*18) | bias smooth qacc_smooth qacc qfrc_con | xpos(39) xmat(117)
+  //                   | J(nefc*18, MuJoCo row order) aref D | contact(7*ncon)
   double* o = a.debug;
   if (lane == 0) { o[0] = s.nefc; o[1] = s.ncon; o[2] = s.iters; o[3] = s.overflow; }
   o += 4;
-  for (int w = lane; w < NV * NV; w += 32) o[w] = s.M[(w / NV) * LD + (w % NV)];
+  for (int w = lane; w < NV * NV; w += 32) {
+    int i = w / NV, j = w % NV;
+    o[w] = (i >= j) ? s.M[TRI(i, j)] : s.M[TRI(j, i)];
+  }
   o += NV * NV;
   if (lane < NV) { o[lane] = s.qfrc_bias[lane]; o[NV + lane] = s.qfrc_smooth[lane]; o[2 * NV + lane] = s.qacc_smooth[lane]; o[3 * NV + lane] = s.qacc[lane]; o[4 * NV + lane] = s.qfrc_con[lane]; }
   o += 5 * NV;
@@ -1257,10 +1394,19 @@ __device__ void debug_dump(const S& s, const StepArgs& a, int lane, int nva) {
   o += NB * 3;
   for (int w = lane; w < NB * 9; w += 32) o[w] = s.xmat[w];
   o += NB * 9;
-  for (int w = lane; w < s.nefc * NV; w += 32) o[w] = s.J[(w / NV) * LD + (w % NV)];
-  o += s.nefc * NV;
-  for (int w = lane; w < s.nefc; w += 32) { o[w] = s.earef[w]; o[s.nefc + w] = s.eD[w]; }
-  o += 2 * s.nefc;
+  const int nefc = s.nefc;
+  for (int w = lane; w < nefc * NV; w += 32) {
+    int r = w / NV, j = w % NV;
+    double v = 0;
+    if (r < s.nR) v = j < NH ? row_r(s, r)[j] : 0.0;
+    else if (r < s.nR + s.nC) v = j >= NH ? row_c(s, r)[j - NH] : 0.0;
+    else if (r < s.nR + s.nC + s.nF) v = row_f(s, r)[j];
+    else { int meta = s.rmeta[r]; v = ((meta & 0xff) == j) ? ((meta & 0x100) ? -1.0 : 1.0) : 0.0; }
+    o[s.omap[r] * NV + j] = v;
+  }
+  o += nefc * NV;
+  for (int w = lane; w < nefc; w += 32) { o[s.omap[w]] = s.earef[w]; o[nefc + s.omap[w]] = s.eD[w]; }
+  o += 2 * nefc;
   for (int w = lane; w < s.ncon; w += 32) {
     o[w * 7] = s.cdist[w];
     for (int k = 0; k < 3; k++) { o[w * 7 + 1 + k] = s.cpos[w * 3 + k]; o[w * 7 + 4 + k] = s.cframe[w * 9 + k]; }
@@ -1268,103 +1414,119 @@ __device__ void debug_dump(const S& s, const StepArgs& a, int lane, int nva) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NEFC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) mcb_env_kernel(const StepArgs a) {
+// The env kernel: one warp (= one CTA) per env.  BIG = false is the first launch over all envs; envs whose
+// constraint set overflows the small layout leave every output untouched and enqueue themselves on redo_list,
+// which the BIG = true launch then serves (grid-stride over the list).
+template <bool BIG>
+__global__ void __launch_bounds__(32, BIG ? 4 : 16) mcb_env_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef EnvS<NEFC> S;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS + wid;
-  if (env >= a.n_envs) return;
-  S& s = *reinterpret_cast<S*>(smem_raw + (size_t)wid * sizeof(S));
+  typedef EnvS<BIG> S;
+  const int lane = threadIdx.x & 31;
+  S& s = *reinterpret_cast<S*>(smem_raw);
   const DevModel* __restrict__ m = a.m;
   const mcb_task_cfg& cfg = a.cfg;
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
+  const int nwork = BIG ? *a.redo_count : a.n_envs;
 
-  if (a.mode == MODE_RESET && a.mask && !a.mask[env]) return;
+  for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+    const int env = BIG ? a.redo_list[item] : item;
+    if (a.mode == MODE_RESET && a.mask && !a.mask[env]) continue;
 
-  // zero the matrices whose sparsity pattern is static, and the bookkeeping
-  for (int w = lane; w < NV * LD; w += 32) { s.M[w] = 0; s.H[w] = 0; s.L[w] = 0; }
-  for (int w = lane; w < NB * 10; w += 32) { s.cinert[w] = 0; s.crb[w] = 0; }
-  for (int w = lane; w < NB * 9; w += 32) s.xmat[w] = 0;
-  for (int w = lane; w < NB * 3; w += 32) s.xpos[w] = 0;
-  for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
-  if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; }
-  if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
-  load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
-  unsigned long long ctr = a.rng_ctr[env];
-  double achieved[3];
-  int substeps = 0;
+    // zero what has a static sparsity pattern or is read before it is first written
+    for (int w = lane; w < NTRI; w += 32) { s.M[w] = 0; s.H[w] = 0; }
+    for (int w = lane; w < NB * 10; w += 32) { s.cinert[w] = 0; s.crb[w] = 0; }
+    for (int w = lane; w < NB * 9; w += 32) s.xmat[w] = 0;
+    for (int w = lane; w < NB * 3; w += 32) s.xpos[w] = 0;
+    for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
+    if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; s.search[lane] = 0; s.Mv[lane] = 0; }
+    if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
+    __syncwarp();
+    load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
+    unsigned long long ctr = a.rng_ctr[env];
+    double achieved[3];
+    int substeps = 0;
+    bool ok = true;
 
-  if (a.mode == MODE_RESET) {
-    reset_env<NEFC>(s, a, m, lane, env, nba, nva, ctr);
-    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
-    if (lane == 0) { a.elapsed[env] = 0; a.ep_return[env] = 0; }
-    substeps = 2;
-  } else if (a.mode == MODE_FORWARD) {
-    forward<NEFC>(s, m, lane, nba, nva);
-    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
-    if (a.debug && env == a.debug_env) debug_dump(s, a, lane, nva);
-    substeps = 1;
-  } else {
-    // MyCobotEnv.step, joint controller: ctrl = clip(action, -1, 1) widened to double (mycobot.py:133,192-193)
-    if (lane < NU) {
-      float act = a.actions[(size_t)env * NU + lane];
-      act = fminf(1.0f, fmaxf(-1.0f, act));
-      s.ctrl[lane] = (double)act;
+    if (a.mode == MODE_RESET) {
+      ok = reset_env(s, a, m, lane, env, nba, nva, ctr);
+      if (ok) {
+        write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+        if (lane == 0) { a.elapsed[env] = 0; a.ep_return[env] = 0; }
+      }
+      substeps = 2;
+    } else if (a.mode == MODE_FORWARD) {
+      ok = forward(s, m, lane, nba, nva);
+      if (ok) {
+        write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+        if (a.debug && env == a.debug_env) debug_dump(s, a, lane, nva);
+      }
+      substeps = 1;
+    } else {
+      // MyCobotEnv.step, joint controller: ctrl = clip(action, -1, 1) widened to double (mycobot.py:133,192-193)
+      if (lane < NU) {
+        float act = a.actions[(size_t)env * NU + lane];
+        act = fminf(1.0f, fmaxf(-1.0f, act));
+        s.ctrl[lane] = (double)act;
+      }
+      __syncwarp();
+      for (int it = 0; it < cfg.frame_skip && ok; it++) {
+        ok = forward(s, m, lane, nba, nva);
+        if (ok) euler(s, m, lane, nva);
+      }
+      substeps = cfg.frame_skip;
+      if (ok && cfg.block_gripper) {  // _step_callback (mycobot.py:300-306)
+        if (lane == 0) { s.qpos[7] = 0; s.qpos[9] = 0; }
+        __syncwarp();
+        ok = forward(s, m, lane, nba, nva);
+        substeps++;
+      }
+      if (ok) {
+        int el = a.elapsed[env] + 1;
+        double ob_ag[3];
+        write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, ob_ag);
+        double dx = ob_ag[0] - s.goal[0], dy = ob_ag[1] - s.goal[1], dz = ob_ag[2] - s.goal[2];
+        double dist = sqrt(dx * dx + dy * dy + dz * dz);
+        bool succ = dist < cfg.distance_threshold;
+        bool term = succ, trunc = succ || (el >= cfg.max_episode_steps);
+        double rew = cfg.reward_type == 0 ? -(double)(dist > cfg.distance_threshold) : -dist;
+        double epret = a.ep_return[env] + rew;
+        bool done = term || trunc;
+        double final_stats[4] = {1.0, succ ? 1.0 : 0.0, epret, (double)el};
+        if (done && cfg.auto_reset) {
+          if (a.final_obs) {
+            double dummy[3];
+            write_obs(s, m, cfg, lane, env, a.final_obs, nullptr, nullptr, dummy);
+          }
+          ok = reset_env(s, a, m, lane, env, nba, nva, ctr);
+          if (ok) write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
+          el = 0; epret = 0; substeps += 2;
+        }
+        if (ok && lane == 0) {
+          if (cfg.reward_type == 0) ((float*)a.reward)[env] = -(float)(dist > cfg.distance_threshold);
+          else ((double*)a.reward)[env] = -dist;
+          a.terminated[env] = term; a.truncated[env] = trunc; a.success[env] = succ;
+          if (done) { for (int k = 0; k < 4; k++) atomicAdd(a.stats + k, final_stats[k]); }
+          a.elapsed[env] = el; a.ep_return[env] = epret;
+        }
+      }
     }
     __syncwarp();
-    for (int it = 0; it < cfg.frame_skip; it++) {
-      forward<NEFC>(s, m, lane, nba, nva);
-      euler(s, m, lane, nva);
+    if (!ok) {
+      // small layout overflowed: leave the env untouched for the big-layout launch
+      // (observation rows written above are rewritten by it; state, counters and statistics are not yet committed)
+      if (lane == 0) { int k = atomicAdd(a.redo_count, 1); a.redo_list[k] = env; }
+      continue;
     }
-    substeps = cfg.frame_skip;
-    if (cfg.block_gripper) {  // _step_callback (mycobot.py:300-306)
-      if (lane == 0) { s.qpos[7] = 0; s.qpos[9] = 0; }
-      __syncwarp();
-      forward<NEFC>(s, m, lane, nba, nva);
-      substeps++;
-    }
-    int el = a.elapsed[env] + 1;
-    // observation goes to final_obs first if this env is about to auto-reset; decide after success
-    double ob_ag[3];
-    // compute success / reward from achieved goal (needs obs math) -- write into the regular outputs first
-    write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, ob_ag);
-    double dx = ob_ag[0] - s.goal[0], dy = ob_ag[1] - s.goal[1], dz = ob_ag[2] - s.goal[2];
-    double dist = sqrt(dx * dx + dy * dy + dz * dz);
-    bool succ = dist < cfg.distance_threshold;
-    bool term = succ, trunc = succ || (el >= cfg.max_episode_steps);
-    double rew = cfg.reward_type == 0 ? -(double)(dist > cfg.distance_threshold) : -dist;
-    double epret = a.ep_return[env] + rew;
+    store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
     if (lane == 0) {
-      if (cfg.reward_type == 0) ((float*)a.reward)[env] = -(float)(dist > cfg.distance_threshold);
-      else ((double*)a.reward)[env] = -dist;
-      a.terminated[env] = term; a.truncated[env] = trunc; a.success[env] = succ;
+      a.rng_ctr[env] = ctr;
+      if (a.mode == MODE_STEP) atomicAdd(a.stats + 4, 1.0);
+      if (BIG && s.overflow) atomicAdd(a.stats + 5, (double)s.overflow);
+      atomicAdd(a.stats + 6, (double)s.iters);
+      atomicAdd(a.stats + 7, (double)substeps);
     }
-    bool done = term || trunc;
-    if (done && lane == 0) {
-      atomicAdd(a.stats + 0, 1.0); atomicAdd(a.stats + 1, succ ? 1.0 : 0.0);
-      atomicAdd(a.stats + 2, epret); atomicAdd(a.stats + 3, (double)el);
-    }
-    if (done && cfg.auto_reset) {
-      if (a.final_obs) {
-        double dummy[3];
-        write_obs(s, m, cfg, lane, env, a.final_obs, nullptr, nullptr, dummy);
-      }
-      reset_env<NEFC>(s, a, m, lane, env, nba, nva, ctr);
-      write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
-      el = 0; epret = 0; substeps += 2;
-    }
-    if (lane == 0) { a.elapsed[env] = el; a.ep_return[env] = epret; }
-  }
-  __syncwarp();
-  store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
-  if (lane == 0) {
-    a.rng_ctr[env] = ctr;
-    if (a.mode == MODE_STEP) atomicAdd(a.stats + 4, 1.0);
-    if (s.overflow) atomicAdd(a.stats + 5, (double)s.overflow);
-    atomicAdd(a.stats + 6, (double)s.iters);
-    atomicAdd(a.stats + 7, (double)substeps);
+    __syncwarp();
   }
 }
 
@@ -1421,6 +1583,15 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
   if (sum == 123.456) out[0] = sum;
 }
 
+
+__global__ void iota_kernel(int* list, int* count, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] = i;
+  if (i == 0) *count = n;
+}
+
+#define DEBUG_DOUBLES (4 + NV * NV + 5 * NV + NB * 12 + 128 * NV + 2 * 128 + 7 * 16)
+
 }  // namespace
 
 // ================================================================================================
@@ -1432,8 +1603,9 @@ struct mcb_model {
 
 struct mcb_batch {
   mcb_model* model;
-  int n_envs, nefc, warps, obs_dim;
-  size_t smem;
+  int n_envs, obs_dim, big_only, big_grid;
+  size_t smem_small, smem_big;
+  int* redo_count; int* redo_list;
   mcb_task_cfg cfg;
   uint64_t seed;
   double* state; int* elapsed; double* ep_return; unsigned long long* rng_ctr; double* stats;
@@ -1445,21 +1617,30 @@ struct mcb_batch {
 };
 
 static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
-  int blocks = (b->n_envs + b->warps - 1) / b->warps;
   a.m = b->model->dev; a.n_envs = b->n_envs; a.cfg = b->cfg; a.seed = b->seed;
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
-  switch (b->nefc) {
-    case 32: mcb_env_kernel<32, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
-    case 64: mcb_env_kernel<64, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
-    default: mcb_env_kernel<96, WPB><<<blocks, b->warps * 32, b->smem, st>>>(a); break;
+  a.redo_count = b->redo_count; a.redo_list = b->redo_list;
+  if (b->big_only) {
+    iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
+  } else {
+    CK(cudaMemsetAsync(b->redo_count, 0, sizeof(int), st));
+    mcb_env_kernel<false><<<b->n_envs, 32, b->smem_small, st>>>(a);
   }
+  CK(cudaGetLastError());
+  // fallback launch for envs that overflowed the small layout (grid-stride over the device list; usually empty)
+  mcb_env_kernel<true><<<b->big_only ? b->n_envs : b->big_grid, 32, b->smem_big, st>>>(a);
   CK(cudaGetLastError());
   return 0;
 }
 
 extern "C" {
 
-const char* mcb_version(void) { return "mycobot_b200 0.1 (sm_100a)"; }
+const char* mcb_version(void) {
+  static char buf[160];
+  snprintf(buf, sizeof buf, "mycobot_b200 0.2 (sm_100a; shared memory per env: %zu B common layout, %zu B fallback layout)",
+           sizeof(EnvS<false>), sizeof(EnvS<true>));
+  return buf;
+}
 const char* mcb_last_error(void) { return g_err.c_str(); }
 int32_t mcb_model_desc_size(void) { return (int32_t)sizeof(mcb_model_desc); }
 int32_t mcb_task_cfg_size(void) { return (int32_t)sizeof(mcb_task_cfg); }
@@ -1509,6 +1690,8 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
     if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) pp.solref[k] = mix * ra[k] + (1 - mix) * rb[k];
     else for (int k = 0; k < 2; k++) pp.solref[k] = fmin(ra[k], rb[k]);
     for (int k = 0; k < 5; k++) pp.solimp[k] = mix * d->geom_solimp[g1][k] + (1 - mix) * d->geom_solimp[g2][k];
+    { int b1 = d->geom_body[g1], b2 = d->geom_body[g2]; bool c1 = b1 == CUBE, c2 = b2 == CUBE, r1 = b1 >= 0 && !c1, r2 = b2 >= 0 && !c2;
+      pp.ptype = ((c1 || c2) && (r1 || r2)) ? 2 : ((c1 || c2) ? 1 : 0); }
     pp.tran = d->geom_invweight[g1][0] + d->geom_invweight[g2][0];
     pp.rot = d->geom_invweight[g1][1] + d->geom_invweight[g2][1];
   }
@@ -1533,23 +1716,27 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   memset(b, 0, sizeof *b);
   b->model = m; b->n_envs = n_envs; b->cfg = *cfg; b->seed = seed;
   b->obs_dim = cfg->has_object ? MCB_OBS_OBJECT : MCB_OBS_REACH;
-  int nefc = cfg->nefc_max ? cfg->nefc_max : (cfg->has_object ? 96 : 32);
-  if (nefc != 32 && nefc != 64 && nefc != 96) { delete b; return fail("mcb_batch_create: nefc_max must be 32, 64 or 96"); }
-  b->nefc = nefc; b->warps = WPB;
-  size_t per = nefc == 32 ? sizeof(EnvS<32>) : nefc == 64 ? sizeof(EnvS<64>) : sizeof(EnvS<96>);
-  b->smem = per * b->warps;
-  cudaError_t e;
-  if (nefc == 32) e = cudaFuncSetAttribute(mcb_env_kernel<32, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
-  else if (nefc == 64) e = cudaFuncSetAttribute(mcb_env_kernel<64, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
-  else e = cudaFuncSetAttribute(mcb_env_kernel<96, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem);
-  if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(max dynamic smem)", e); }
+  if (cfg->nefc_max != 0 && cfg->nefc_max != 48 && cfg->nefc_max != 128) { delete b; return fail("mcb_batch_create: nefc_max must be 0 (two-tier), 48 or 128"); }
+  b->big_only = cfg->nefc_max == 128;
+  b->smem_small = sizeof(EnvS<false>);
+  b->smem_big = sizeof(EnvS<true>);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, m->device));
+  b->big_grid = prop.multiProcessorCount * 4;
+  cudaError_t e = cudaFuncSetAttribute(mcb_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_small);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(shared memory)", e); }
   size_t N = (size_t)n_envs;
   CK(cudaMalloc(&b->state, N * MCB_STATE_STRIDE * sizeof(double)));
   CK(cudaMalloc(&b->elapsed, N * sizeof(int)));
   CK(cudaMalloc(&b->ep_return, N * sizeof(double)));
   CK(cudaMalloc(&b->rng_ctr, N * sizeof(unsigned long long)));
   CK(cudaMalloc(&b->stats, 8 * sizeof(double)));
-  CK(cudaMalloc(&b->debug, (4 + NV * NV + 5 * NV + NB * 12 + 96 * NV + 2 * 96 + 7 * MAXCON) * sizeof(double)));
+  CK(cudaMalloc(&b->redo_count, sizeof(int)));
+  CK(cudaMalloc(&b->redo_list, N * sizeof(int)));
+  CK(cudaMemset(b->redo_count, 0, sizeof(int)));
+  CK(cudaMalloc(&b->debug, DEBUG_DOUBLES * sizeof(double)));
   CK(cudaMemset(b->stats, 0, 8 * sizeof(double)));
   init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs);
   CK(cudaGetLastError());
@@ -1560,7 +1747,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
 
 int32_t mcb_batch_destroy(mcb_batch* b) {
   if (!b) return 0;
-  cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->stats); cudaFree(b->debug);
+  cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->stats); cudaFree(b->debug); cudaFree(b->redo_count); cudaFree(b->redo_list);
   if (b->d_actions) { cudaFree(b->d_actions); cudaFree(b->d_obs); cudaFree(b->d_ag); cudaFree(b->d_dg); cudaFree(b->d_reward); cudaFree(b->d_flags); }
   if (b->h_actions) { cudaFreeHost(b->h_actions); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_ag); cudaFreeHost(b->h_dg); cudaFreeHost(b->h_reward); cudaFreeHost(b->h_flags); }
   delete b;
@@ -1582,7 +1769,7 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, do
   StepArgs a; memset(&a, 0, sizeof a);
   a.mode = MODE_STEP; a.actions = actions; a.obs = obs; a.ag = ag; a.dg = dg; a.reward = reward;
   a.terminated = terminated; a.truncated = truncated; a.success = success; a.final_obs = final_obs;
-  b->last_launches = 1;
+  b->last_launches = 2;  // small-layout kernel + big-layout fallback kernel
   return launch(b, a, (cudaStream_t)stream);
 }
 
@@ -1599,7 +1786,7 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
   StepArgs a; memset(&a, 0, sizeof a);
   a.mode = MODE_FORWARD; a.debug = b->debug; a.debug_env = env;
   if (launch(b, a, (cudaStream_t)stream)) return -1;
-  int total = 4 + NV * NV + 5 * NV + NB * 12 + 96 * NV + 2 * 96 + 7 * MAXCON;
+  int total = DEBUG_DOUBLES;
   if (cap < total) return fail("mcb_debug_forward: buffer too small");
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   CK(cudaMemcpy(h_out, b->debug, total * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1622,8 +1809,8 @@ int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, cons
 }
 
 int32_t mcb_compute_reward(const double* ag, const double* g, int64_t n, double thr, int32_t type, void* out, void* stream) {
-  if (!ag || !g || !out || n < 0) return fail("mcb_compute_reward: bad argument");
   if (n == 0) return 0;
+  if (!ag || !g || !out || n < 0) return fail("mcb_compute_reward: bad argument");
   reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, g, n, thr, type, out);
   CK(cudaGetLastError());
   return 0;

@@ -163,6 +163,6 @@ if __name__ == "__main__":
     timing(False, 4096)
     timing(True, 16384)
     if not quick:
-        timing(True, 16384, nefc_max=64)
+        timing(True, 16384, nefc_max=128)
         timing(False, 16384)
     print("ALL", "PASS" if ok else "FAIL")
