@@ -79,6 +79,9 @@ struct DevModel {
   PairParam pair[MCB_MAXPAIR];
 };
 
+// the flattened model lives in constant memory: one model per process and device (a few KB, broadcast reads)
+__constant__ DevModel c_m;
+
 enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_RESET = 2 };
 
 struct StepArgs {
@@ -112,12 +115,13 @@ struct EnvS {
   enum { NROW = BIG ? 128 : 48, POOL = BIG ? 2432 : 460, MAXC = BIG ? 16 : 8, IS_BIG = BIG };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
   double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
-  double M[NTRI], H[NTRI], invd[NV];
+  double M[NTRI], H[NTRI];
   double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
   double anchors[12];
   union {
     struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
     struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
+    double cscr[136];                                                                                                           // collision scratch (between the two)
   };
   double cdist[MAXC], cpos[MAXC * 3], cframe[MAXC * 9];
   int cpair[MAXC], crow[MAXC];
@@ -176,16 +180,16 @@ __device__ __forceinline__ void quat2mat(double* m, const double* q) {
 template <class S>
 __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
   if (lane < NH) {
-    double ang = s.qpos[lane] - m->d.qpos0[lane];
+    double ang = s.qpos[lane] - c_m.d.qpos0[lane];
     double sn, cs;
     sincos(ang, &sn, &cs);
-    const double* ax = m->d.axis[lane];
+    const double* ax = c_m.d.axis[lane];
     double oc = 1.0 - cs;
     double R[9];
     R[0] = cs + oc * ax[0] * ax[0];         R[1] = oc * ax[0] * ax[1] - sn * ax[2]; R[2] = oc * ax[0] * ax[2] + sn * ax[1];
     R[3] = oc * ax[0] * ax[1] + sn * ax[2]; R[4] = cs + oc * ax[1] * ax[1];         R[5] = oc * ax[1] * ax[2] - sn * ax[0];
     R[6] = oc * ax[0] * ax[2] - sn * ax[1]; R[7] = oc * ax[1] * ax[2] + sn * ax[0]; R[8] = cs + oc * ax[2] * ax[2];
-    const double* T = m->d.Tmat[lane];
+    const double* T = c_m.d.Tmat[lane];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -198,12 +202,12 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
     s.xpos[CUBE * 3] = s.qpos[12]; s.xpos[CUBE * 3 + 1] = s.qpos[13]; s.xpos[CUBE * 3 + 2] = s.qpos[14];
   }
   __syncwarp();
-  for (int L = 0; L < m->nlevel; L++) {
-    int s0 = m->level_start[L], n = (m->level_start[L + 1] - s0) * 12;
+  for (int L = 0; L < c_m.nlevel; L++) {
+    int s0 = c_m.level_start[L], n = (c_m.level_start[L + 1] - s0) * 12;
     for (int w = lane; w < n; w += 32) {
-      int b = m->level_body[s0 + w / 12], e = w % 12;
+      int b = c_m.level_body[s0 + w / 12], e = w % 12;
       if (b == CUBE) continue;
-      int p = m->d.parent[b];
+      int p = c_m.d.parent[b];
       if (e < 9) {
         int r = e / 3, c = e % 3;
         double v;
@@ -212,7 +216,7 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
         s.xmat[b * 9 + e] = v;
       } else {
         int r = e - 9;
-        const double* t = m->d.Tpos[b];
+        const double* t = c_m.d.Tpos[b];
         double v;
         if (p < 0) v = t[r];
         else v = s.xpos[p * 3 + r] + s.xmat[p * 9 + 3 * r] * t[0] + s.xmat[p * 9 + 3 * r + 1] * t[1] + s.xmat[p * 9 + 3 * r + 2] * t[2];
@@ -231,7 +235,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
   if (lane < nba) {
     int b = lane;
     const double* R = s.xmat + b * 9;
-    const double* ip = m->d.ipos[b];
+    const double* ip = c_m.d.ipos[b];
     double com[3], off[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) com[r] = s.xpos[b * 3 + r] + R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];
@@ -240,9 +244,9 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
       for (int r = 0; r < 3; r++) { s.refcube[r] = com[r]; off[r] = 0; }
     } else {
 #pragma unroll
-      for (int r = 0; r < 3; r++) off[r] = com[r] - m->d.ref_robot[r];
+      for (int r = 0; r < 3; r++) off[r] = com[r] - c_m.d.ref_robot[r];
     }
-    const double* I = m->d.inertia[b];  // xx yy zz xy xz yz
+    const double* I = c_m.d.inertia[b];  // xx yy zz xy xz yz
     double A[9];                         // A = R * Ib
 #pragma unroll
     for (int r = 0; r < 3; r++) {
@@ -250,7 +254,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
       A[3 * r + 1] = R[3 * r] * I[3] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[5];
       A[3 * r + 2] = R[3 * r] * I[4] + R[3 * r + 1] * I[5] + R[3 * r + 2] * I[2];
     }
-    double mass = m->d.mass[b];
+    double mass = c_m.d.mass[b];
     double* ci = s.cinert + b * 10;
     ci[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2] + mass * (off[1] * off[1] + off[2] * off[2]);
     ci[1] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5] + mass * (off[0] * off[0] + off[2] * off[2]);
@@ -265,10 +269,10 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
     double* cd = s.cdof + j * 6;
     if (j < NH) {
       const double* R = s.xmat + j * 9;  // hinge j belongs to body j
-      const double* a = m->d.axis[j];
+      const double* a = c_m.d.axis[j];
       double ax[3], off[3];
 #pragma unroll
-      for (int r = 0; r < 3; r++) { ax[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; off[r] = m->d.ref_robot[r] - s.xpos[j * 3 + r]; }
+      for (int r = 0; r < 3; r++) { ax[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; off[r] = c_m.d.ref_robot[r] - s.xpos[j * 3 + r]; }
       cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
       cross3(cd + 3, ax, off);
     } else {
@@ -277,7 +281,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
         cd[0] = cd[1] = cd[2] = 0; cd[3] = (k == 0); cd[4] = (k == 1); cd[5] = (k == 2);
       } else {
         const double* R = s.xmat + CUBE * 9;
-        const double* ip = m->d.ipos[CUBE];
+        const double* ip = c_m.d.ipos[CUBE];
         double ax[3] = {R[k - 3], R[k], R[k + 3]}, off[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) off[r] = R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];  // refcube - xpos
@@ -296,41 +300,49 @@ template <class S>
 __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   for (int w = lane; w < nba * 10; w += 32) {
     int b = w / 10, k = w % 10;
-    int e = b + m->d.subtree_size[b];
+    int e = b + c_m.d.subtree_size[b];
     if (e > nba) e = nba;
     double acc = s.cinert[w];
     for (int c = b + 1; c < e; c++) acc += s.cinert[c * 10 + k];
     s.crb[w] = acc;
   }
   __syncwarp();
-  if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + m->d.dof_body[lane] * 10, s.cdof + lane * 6);
+  if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + c_m.d.dof_body[lane] * 10, s.cdof + lane * 6);
   __syncwarp();
-  for (int e = lane; e < m->nmnz; e += 32) {
-    int i = m->mnz_i[e], j = m->mnz_j[e];
+  for (int e = lane; e < c_m.nmnz; e += 32) {
+    int i = c_m.mnz_i[e], j = c_m.mnz_j[e];
     if (i >= nva) continue;
     const double* a = s.cdof + j * 6;
     const double* b = s.buf + i * 6;
     double v = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
-    if (i == j) v += m->d.armature[i];
+    if (i == j) v += c_m.d.armature[i];
     s.M[TRI(i, j)] = v;
   }
   __syncwarp();
 }
 
-// chol_blk<N0, N>(): Cholesky of the diagonal block rows/cols [N0, N0+N) of a packed symmetric matrix,
-// src -> dst (may alias).  Lane i owns row i in registers; finished rows are broadcast through dst.
-// `dadd` is added to the lane's diagonal entry first (Euler: h * damping).  invd[k] = 1 / L[k][k].
+// chol_solve_blk<N0, N>(): Cholesky A = L L' of the diagonal block rows/cols [N0, N0+N) of a packed symmetric
+// matrix (src -> dst, may alias) AND the solution of A x = b, in one pass.  Lane i owns row i in registers;
+// finished rows are broadcast through dst.  Lane 31 carries the right-hand side as an extra row, so the forward
+// substitution costs nothing extra; the back substitution is a branch-free shuffle chain.  `dadd` is added to the
+// lane's diagonal entry first (Euler: h * damping).  Lanes outside the block get their b back.
 // Fully unrolled: every shared-memory offset is an immediate, no index arithmetic in the inner loops.
 template <int N0, int N>
-__device__ __noinline__ void chol_blk(const double* src, double* dst, double* invd, double dadd, int lane) {
+__device__ __noinline__ double chol_solve_blk(const double* src, double* dst, double dadd, int lane, double b) {
   const int i = lane;
   const bool mine = (i >= N0 && i < N0 + N);
+  const bool rhs = (i == 31);
   const int ro = i * (i + 1) / 2 + N0;
   double row[N];
 #pragma unroll
-  for (int k = 0; k < N; k++) row[k] = (mine && N0 + k <= i) ? src[ro + k] : 0.0;
+  for (int k = 0; k < N; k++) {
+    double bk = __shfl_sync(FULLMASK, b, N0 + k);
+    double v = (mine && N0 + k <= i) ? src[ro + k] : 0.0;
+    row[k] = rhs ? bk : v;
+  }
 #pragma unroll
   for (int k = 0; k < N; k++) if (N0 + k == i) row[k] += dadd;
+  double myinv = 0.0, x = 0.0;
 #pragma unroll
   for (int j = 0; j < N; j++) {
     const double* rj = dst + TRI(N0 + j, N0);
@@ -344,41 +356,23 @@ __device__ __noinline__ void chol_blk(const double* src, double* dst, double* in
     double l = (i == N0 + j) ? sjj * inv : sv * inv;
     row[j] = l;
     if (mine && i >= N0 + j) dst[ro + j] = l;
-    if (i == N0 + j) invd[N0 + j] = inv;
+    double yj = __shfl_sync(FULLMASK, l, 31);   // entry j of L^-1 b
+    if (i == N0 + j) { myinv = inv; x = yj; }
     __syncwarp();
-  }
-}
-// solve_blk<N0, N>(): x = (L L')^-1 b on the same block; lane i passes b_i and receives x_i (other lanes: unchanged).
-template <int N0, int N>
-__device__ __noinline__ double solve_blk(const double* L, const double* invd, int lane, double b) {
-  const int i = lane;
-  const int ro = i * (i + 1) / 2;
-#pragma unroll
-  for (int k = N0; k < N0 + N; k++) {
-    double yk = __shfl_sync(FULLMASK, b, k) * invd[k];
-    if (i == k) b = yk;
-    else if (i > k && i < N0 + N) b -= L[ro + k] * yk;
   }
 #pragma unroll
   for (int k = N0 + N - 1; k >= N0; k--) {
-    double xk = __shfl_sync(FULLMASK, b, k) * invd[k];
-    if (i == k) b = xk;
-    else if (i < k && i >= N0) b -= L[TRI(k, 0) + i] * xk;
+    double xk = __shfl_sync(FULLMASK, x * myinv, k);
+    double lk = (i < k && i >= N0) ? dst[TRI(k, 0) + i] : 0.0;
+    x = (i == k) ? xk : fma(-lk, xk, x);
   }
-  return b;
+  return mine ? x : b;
 }
-// factor / solve with the block structure: coupled => one 18 x 18 block, else robot 12 x 12 and cube 6 x 6
-__device__ __forceinline__ void chol_sys(const double* src, double* dst, double* invd, double dadd, int lane, int nva, bool coupled) {
-  if (coupled) chol_blk<0, 18>(src, dst, invd, dadd, lane);
-  else {
-    chol_blk<0, 12>(src, dst, invd, dadd, lane);
-    if (nva > NH) chol_blk<12, 6>(src, dst, invd, dadd, lane);
-  }
-}
-__device__ __forceinline__ double solve_sys(const double* L, const double* invd, int lane, int nva, bool coupled, double b) {
-  if (coupled) return solve_blk<0, 18>(L, invd, lane, b);
-  b = solve_blk<0, 12>(L, invd, lane, b);
-  if (nva > NH) b = solve_blk<12, 6>(L, invd, lane, b);
+// factor + solve with the block structure: coupled => one 18 x 18 block, else robot 12 x 12 and cube 6 x 6
+__device__ __forceinline__ double factor_solve(const double* src, double* dst, double dadd, int lane, int nva, bool coupled, double b) {
+  if (coupled) return chol_solve_blk<0, 18>(src, dst, dadd, lane, b);
+  b = chol_solve_blk<0, 12>(src, dst, dadd, lane, b);
+  if (nva > NH) b = chol_solve_blk<12, 6>(src, dst, dadd, lane, b);
   return b;
 }
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
@@ -398,230 +392,315 @@ __device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const 
 
 // ------------------------------------------------------------------------------------------------
 // collision: narrow phase for the statically filtered primitive pairs, one lane per pair
-struct RawCon { double dist, pos[3], normal[3]; };
+// Narrow phase, warp-cooperative: the candidate pairs that pass the bounding-sphere test are processed one
+// after the other by the whole warp, all scratch in shared memory (the dead dynamics union).  Contacts are
+// appended to s.cdist / cpos / cframe / cpair in pair order.
+//
+// scratch layout (doubles) inside s.cscr[]
+#define CS_P1 0
+#define CS_P2 3
+#define CS_S1 6
+#define CS_S2 9
+#define CS_A 12     // A[i][k]: axis i of box 1 (column i of its rotation), row-major 3x3
+#define CS_B 21
+#define CS_C 30     // C[i][j] = A_i . B_j
+#define CS_SP 39    // separation along the 15 candidate axes
+#define CS_T 54     // signed centre distance along the axis
+#define CS_PX 69
+#define CS_PY 85
+#define CS_QX 101
+#define CS_QY 117
+#define CS_N 133
 
-__device__ int plane_box(RawCon* out, const double* ppos, const double* pmat, const double* bpos, const double* bmat, const double* bsize) {
-  double norm[3] = {pmat[2], pmat[5], pmat[8]}, dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
-  double dist = dot3(dif, norm);
-  int cnt = 0;
-  for (int i = 0; i < 8; i++) {
-    double vec[3] = {(i & 1 ? bsize[0] : -bsize[0]), (i & 2 ? bsize[1] : -bsize[1]), (i & 4 ? bsize[2] : -bsize[2])};
-    double corner[3];
-    for (int r = 0; r < 3; r++) corner[r] = bmat[3 * r] * vec[0] + bmat[3 * r + 1] * vec[1] + bmat[3 * r + 2] * vec[2];
-    double ldist = dot3(norm, corner);
-    if (dist + ldist > 0 || ldist > 0) continue;
-    double cd = dist + ldist;
-    out[cnt].dist = cd;
-    for (int k = 0; k < 3; k++) { out[cnt].pos[k] = corner[k] + bpos[k] - norm[k] * cd * 0.5; out[cnt].normal[k] = norm[k]; }
-    if (++cnt >= 4) return 4;
-  }
-  return cnt;
+template <class S>
+__device__ __forceinline__ void emit_contact(S& s, int idx, int pair, double dist, const double* pos, const double* nrm) {
+  s.cdist[idx] = dist;
+  s.cpair[idx] = pair;
+  double f[9];
+  f[0] = nrm[0]; f[1] = nrm[1]; f[2] = nrm[2];
+  // mju_makeFrame
+  double nn = sqrt(dot3(f, f));
+  if (nn < MINVAL) { f[0] = 1; f[1] = f[2] = 0; } else { f[0] /= nn; f[1] /= nn; f[2] /= nn; }
+  f[3] = f[4] = f[5] = 0;
+  if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
+  double t = dot3(f, f + 3);
+  f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
+  nn = sqrt(dot3(f + 3, f + 3));
+  if (nn < MINVAL) { f[3] = 1; f[4] = f[5] = 0; } else { f[3] /= nn; f[4] /= nn; f[5] /= nn; }
+  cross3(f + 6, f, f + 3);
+#pragma unroll
+  for (int k = 0; k < 9; k++) s.cframe[idx * 9 + k] = f[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) s.cpos[idx * 3 + k] = pos[k];
 }
 
-__device__ int clip_poly(double* px, double* py, int n, double hx, double hy) {
-  double qx[16], qy[16];
-  for (int side = 0; side < 4; side++) {
-    int cnt = 0;
-    for (int i = 0; i < n; i++) {
-      int j = (i + 1) % n;
-      double ax = px[i], ay = py[i], bx = px[j], by = py[j];
-      double da, db;
-      if (side == 0) { da = hx - ax; db = hx - bx; }
-      else if (side == 1) { da = hx + ax; db = hx + bx; }
-      else if (side == 2) { da = hy - ay; db = hy - by; }
-      else { da = hy + ay; db = hy + by; }
-      if (da >= 0) { qx[cnt] = ax; qy[cnt] = ay; cnt++; }
-      if ((da >= 0) != (db >= 0)) {
-        double t = da / (da - db);
-        qx[cnt] = ax + t * (bx - ax); qy[cnt] = ay + t * (by - ay); cnt++;
-      }
-    }
-    n = cnt;
-    for (int i = 0; i < n; i++) { px[i] = qx[i]; py[i] = qy[i]; }
-    if (n == 0) return 0;
-  }
-  return n;
-}
-
-// box_box(): 15-axis separating-axis test, then a clipped face manifold (<= 8 points) or one edge-edge point.
-// Normal points from box 1 to box 2.  Degenerate ties: first face axis wins (a later axis must be better by
-// 1e-10), an edge axis must beat the faces by 5%.
-__device__ int box_box(RawCon* out, const double* p1, const double* R1, const double* s1, const double* p2, const double* R2, const double* s2) {
-  double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-  double A[3][3], B[3][3], Cm[3][3], Q[3][3];
-  for (int i = 0; i < 3; i++)
-    for (int k = 0; k < 3; k++) { A[i][k] = R1[3 * k + i]; B[i][k] = R2[3 * k + i]; }
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) { Cm[i][j] = dot3(A[i], B[j]); Q[i][j] = fabs(Cm[i][j]); }
-  double best = -1e300; int code = -1; double bn[3] = {0, 0, 0};
-  for (int i = 0; i < 3; i++) {
-    double t = dot3(d, A[i]);
-    double sp = fabs(t) - (s1[i] + s2[0] * Q[i][0] + s2[1] * Q[i][1] + s2[2] * Q[i][2]);
-    if (sp > 0) return 0;
-    if (sp > best + (code >= 0 ? 1e-10 : 0.0)) { best = sp; code = i; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -A[i][k] : A[i][k]); }
-  }
-  for (int j = 0; j < 3; j++) {
-    double t = dot3(d, B[j]);
-    double sp = fabs(t) - (s2[j] + s1[0] * Q[0][j] + s1[1] * Q[1][j] + s1[2] * Q[2][j]);
-    if (sp > 0) return 0;
-    if (sp > best + 1e-10) { best = sp; code = 3 + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -B[j][k] : B[j][k]); }
-  }
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      double Lx[3];
-      cross3(Lx, A[i], B[j]);
-      double l = sqrt(dot3(Lx, Lx));
-      if (l < 1e-6) continue;
-      for (int k = 0; k < 3; k++) Lx[k] /= l;
-      double t = dot3(d, Lx);
-      double ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(A[k], Lx)); rb += s2[k] * fabs(dot3(B[k], Lx)); }
-      double sp = fabs(t) - (ra + rb);
-      if (sp > 0) return 0;
-      if (sp * 1.05 > best + 1e-10 && sp > best) { best = sp; code = 6 + 3 * i + j; for (int k = 0; k < 3; k++) bn[k] = (t < 0 ? -Lx[k] : Lx[k]); }
-    }
-  if (code < 0) return 0;
-  if (code >= 6) {
-    int i = (code - 6) / 3, j = (code - 6) % 3;
-    double pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
-    for (int a = 0; a < 3; a++) {
-      if (a == i) continue;
-      double sg = dot3(A[a], bn) > 0 ? 1.0 : -1.0;
-      for (int k = 0; k < 3; k++) pa[k] += sg * s1[a] * A[a][k];
-    }
-    for (int b = 0; b < 3; b++) {
-      if (b == j) continue;
-      double sg = dot3(B[b], bn) > 0 ? -1.0 : 1.0;
-      for (int k = 0; k < 3; k++) pb[k] += sg * s2[b] * B[b][k];
-    }
-    double w[3] = {pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]};
-    double b_ = Cm[i][j], dd = dot3(A[i], w), e = dot3(B[j], w);
-    double den = 1 - b_ * b_;
-    double u = (b_ * e - dd) / den, v = (e - b_ * dd) / den;
-    for (int k = 0; k < 3; k++) {
-      double ca = pa[k] + u * A[i][k], cb = pb[k] + v * B[j][k];
-      out[0].pos[k] = 0.5 * (ca + cb);
-      out[0].normal[k] = bn[k];
-    }
-    out[0].dist = best;
-    return 1;
-  }
-  const double *pr, *pi_, *sr, *si; double (*Ar)[3], (*Ai)[3]; double nref[3]; int ax;
-  if (code < 3) { pr = p1; pi_ = p2; sr = s1; si = s2; Ar = A; Ai = B; ax = code; for (int k = 0; k < 3; k++) nref[k] = bn[k]; }
-  else { pr = p2; pi_ = p1; sr = s2; si = s1; Ar = B; Ai = A; ax = code - 3; for (int k = 0; k < 3; k++) nref[k] = -bn[k]; }
-  int ia = 0; double bestd = -1;
-  for (int a = 0; a < 3; a++) { double v = fabs(dot3(Ai[a], nref)); if (v > bestd) { bestd = v; ia = a; } }
-  double isg = dot3(Ai[ia], nref) > 0 ? -1.0 : 1.0;
-  int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3;
-  int r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
-  double fc[3];
-  for (int k = 0; k < 3; k++) fc[k] = pi_[k] + isg * si[ia] * Ai[ia][k] - pr[k];
-  double px[16], py[16];
-  const double sgn[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
-  for (int c = 0; c < 4; c++) {
-    double vz[3];
-    for (int k = 0; k < 3; k++) vz[k] = fc[k] + sgn[c][0] * si[i1] * Ai[i1][k] + sgn[c][1] * si[i2] * Ai[i2][k];
-    px[c] = dot3(vz, Ar[r1]); py[c] = dot3(vz, Ar[r2]);
-  }
-  double o_n = dot3(fc, nref);
-  double u1 = dot3(Ai[i1], nref), u2 = dot3(Ai[i2], nref);
-  double a11 = dot3(Ai[i1], Ar[r1]), a12 = dot3(Ai[i1], Ar[r2]), a21 = dot3(Ai[i2], Ar[r1]), a22 = dot3(Ai[i2], Ar[r2]);
-  double det = a11 * a22 - a12 * a21;
-  double fx = dot3(fc, Ar[r1]), fy = dot3(fc, Ar[r2]);
-  int n = clip_poly(px, py, 4, sr[r1], sr[r2]);
-  int cnt = 0;
-  for (int c = 0; c < n && cnt < 8; c++) {
-    double dx = px[c] - fx, dy = py[c] - fy, h;
-    if (fabs(det) > 1e-12) {
-      double al = (dx * a22 - dy * a21) / det, be = (dy * a11 - dx * a12) / det;
-      h = o_n + al * u1 + be * u2;
-    } else h = o_n;
-    double depth = sr[ax] - h;
-    if (-depth >= 0) continue;
-    double pt[3];
-    for (int k = 0; k < 3; k++) pt[k] = pr[k] + px[c] * Ar[r1][k] + py[c] * Ar[r2][k] + (h + 0.5 * depth) * nref[k];
-    int dup = 0;
-    for (int e = 0; e < cnt; e++) {
-      double q[3] = {pt[0] - out[e].pos[0], pt[1] - out[e].pos[1], pt[2] - out[e].pos[2]};
-      if (dot3(q, q) < 1e-20) dup = 1;
-    }
-    if (dup) continue;
-    for (int k = 0; k < 3; k++) { out[cnt].pos[k] = pt[k]; out[cnt].normal[k] = bn[k]; }
-    out[cnt].dist = -depth;
-    cnt++;
-  }
-  return cnt;
-}
-
-
-__device__ void geom_pose(const double* xpos, const double* xmat, const DevModel* __restrict__ m, int g, double* pos, double* mat) {
-  int b = m->d.geom_body[g];
-  const double* gp = m->d.geom_pos[g];
-  const double* gm = m->d.geom_mat[g];
+// world pose of geom g into registers (uniform across the warp)
+template <class S>
+__device__ __forceinline__ void geom_pose(const S& s, int g, double* pos, double* mat) {
+  int b = c_m.d.geom_body[g];
+  const double* gp = c_m.d.geom_pos[g];
+  const double* gm = c_m.d.geom_mat[g];
   if (b < 0) {
+#pragma unroll
     for (int k = 0; k < 3; k++) pos[k] = gp[k];
+#pragma unroll
     for (int k = 0; k < 9; k++) mat[k] = gm[k];
   } else {
-    const double* R = xmat + b * 9;
+    const double* R = s.xmat + b * 9;
+#pragma unroll
     for (int r = 0; r < 3; r++) {
-      pos[r] = xpos[b * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
+      pos[r] = s.xpos[b * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
+#pragma unroll
       for (int c = 0; c < 3; c++) mat[3 * r + c] = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c];
     }
   }
 }
 
+// mjc_PlaneBox: corners below the plane, the first four in corner order.  Lanes 0..7 = corners.
+template <class S>
+__device__ int plane_box_coop(S& s, int lane, int pair, int ncon, const double* ppos, const double* pmat, const double* bpos, const double* bmat, const double* bsize) {
+  double norm[3] = {pmat[2], pmat[5], pmat[8]}, dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
+  double dist = dot3(dif, norm);
+  int i = lane & 7;
+  double vec[3] = {(i & 1 ? bsize[0] : -bsize[0]), (i & 2 ? bsize[1] : -bsize[1]), (i & 4 ? bsize[2] : -bsize[2])};
+  double corner[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) corner[r] = bmat[3 * r] * vec[0] + bmat[3 * r + 1] * vec[1] + bmat[3 * r + 2] * vec[2];
+  double ldist = dot3(norm, corner);
+  bool hit = lane < 8 && !(dist + ldist > 0 || ldist > 0);
+  unsigned bal = __ballot_sync(FULLMASK, hit);
+  int rank = __popc(bal & ((1u << lane) - 1));
+  int total = __popc(bal);
+  if (total > 4) total = 4;
+  if (hit && rank < 4 && ncon + rank < S::MAXC) {
+    double cd = dist + ldist, pos[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = corner[k] + bpos[k] - norm[k] * cd * 0.5;
+    emit_contact(s, ncon + rank, pair, cd, pos, norm);
+  }
+  return ncon + total;
+}
+
+// box_box_coop(): 15-axis separating-axis test (one lane per axis), then a clipped face manifold (<= 8 points,
+// Sutherland-Hodgman with one lane per polygon edge) or one edge-edge point.  Normal points from box 1 to box 2.
+// Degenerate ties: first face axis wins (a later axis must be better by 1e-10), an edge axis must beat the faces
+// by 5%.  Same arithmetic and the same discrete choices as the oracle's box_box().
+template <class S>
+__device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1, const double* R1, const double* s1, const double* p2, const double* R2, const double* s2) {
+  double* cs = s.cscr;
+  if (lane < 9) { int i = lane / 3, k = lane % 3; cs[CS_A + lane] = R1[3 * k + i]; cs[CS_B + lane] = R2[3 * k + i]; }
+  if (lane < 3) { cs[CS_P1 + lane] = p1[lane]; cs[CS_P2 + lane] = p2[lane]; cs[CS_S1 + lane] = s1[lane]; cs[CS_S2 + lane] = s2[lane]; }
+  __syncwarp();
+  if (lane < 9) { int i = lane / 3, j = lane % 3; cs[CS_C + lane] = dot3(cs + CS_A + 3 * i, cs + CS_B + 3 * j); }
+  __syncwarp();
+  const double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  // --- one candidate axis per lane
+  {
+    double sp = -1e300, t = 0;
+    if (lane < 3) {
+      int i = lane;
+      t = dot3(d, cs + CS_A + 3 * i);
+      sp = fabs(t) - (cs[CS_S1 + i] + s2[0] * fabs(cs[CS_C + 3 * i]) + s2[1] * fabs(cs[CS_C + 3 * i + 1]) + s2[2] * fabs(cs[CS_C + 3 * i + 2]));
+    } else if (lane < 6) {
+      int j = lane - 3;
+      t = dot3(d, cs + CS_B + 3 * j);
+      sp = fabs(t) - (cs[CS_S2 + j] + s1[0] * fabs(cs[CS_C + j]) + s1[1] * fabs(cs[CS_C + 3 + j]) + s1[2] * fabs(cs[CS_C + 6 + j]));
+    } else if (lane < 15) {
+      int i = (lane - 6) / 3, j = (lane - 6) % 3;
+      double Lx[3];
+      cross3(Lx, cs + CS_A + 3 * i, cs + CS_B + 3 * j);
+      double l = sqrt(dot3(Lx, Lx));
+      if (l >= 1e-6) {
+        for (int k = 0; k < 3; k++) Lx[k] /= l;
+        t = dot3(d, Lx);
+        double ra = 0, rb = 0;
+        for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(cs + CS_A + 3 * k, Lx)); rb += s2[k] * fabs(dot3(cs + CS_B + 3 * k, Lx)); }
+        sp = fabs(t) - (ra + rb);
+      }
+    }
+    if (lane < 15) { cs[CS_SP + lane] = sp; cs[CS_T + lane] = t; }
+    if (__any_sync(FULLMASK, lane < 15 && sp > 0)) return ncon;   // separated (a degenerate edge axis has sp = -1e300)
+  }
+  __syncwarp();
+  // --- sequential choice of the axis (uniform)
+  double best = -1e300; int code = -1;
+  for (int a = 0; a < 3; a++) { double sp = cs[CS_SP + a]; if (sp > best + (code >= 0 ? 1e-10 : 0.0)) { best = sp; code = a; } }
+  for (int a = 3; a < 6; a++) { double sp = cs[CS_SP + a]; if (sp > best + 1e-10) { best = sp; code = a; } }
+  for (int a = 6; a < 15; a++) { double sp = cs[CS_SP + a]; if (sp > -1e299 && sp * 1.05 > best + 1e-10 && sp > best) { best = sp; code = a; } }
+  if (code < 0) return ncon;
+  const double tsel = cs[CS_T + code];
+  double bn[3];
+  if (code >= 6) {
+    int i = (code - 6) / 3, j = (code - 6) % 3;
+    const double* Ai = cs + CS_A + 3 * i;
+    const double* Bj = cs + CS_B + 3 * j;
+    double Lx[3];
+    cross3(Lx, Ai, Bj);
+    double l = sqrt(dot3(Lx, Lx));
+    for (int k = 0; k < 3; k++) { Lx[k] /= l; bn[k] = (tsel < 0 ? -Lx[k] : Lx[k]); }
+    double pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
+    for (int a = 0; a < 3; a++) {
+      if (a == i) continue;
+      const double* Aa = cs + CS_A + 3 * a;
+      double sg = dot3(Aa, bn) > 0 ? 1.0 : -1.0;
+      for (int k = 0; k < 3; k++) pa[k] += sg * cs[CS_S1 + a] * Aa[k];
+    }
+    for (int b = 0; b < 3; b++) {
+      if (b == j) continue;
+      const double* Bb = cs + CS_B + 3 * b;
+      double sg = dot3(Bb, bn) > 0 ? -1.0 : 1.0;
+      for (int k = 0; k < 3; k++) pb[k] += sg * cs[CS_S2 + b] * Bb[k];
+    }
+    double w[3] = {pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]};
+    double b_ = cs[CS_C + 3 * i + j], dd = dot3(Ai, w), e = dot3(Bj, w);
+    double den = 1 - b_ * b_;
+    double u = (b_ * e - dd) / den, v = (e - b_ * dd) / den;
+    double pos[3];
+    for (int k = 0; k < 3; k++) { double ca = pa[k] + u * Ai[k], cb = pb[k] + v * Bj[k]; pos[k] = 0.5 * (ca + cb); }
+    if (lane == 0 && ncon < S::MAXC) emit_contact(s, ncon, pair, best, pos, bn);
+    return ncon + 1;
+  }
+  // --- face contact: reference box owns the axis
+  const bool ref1 = code < 3;
+  const int ax = ref1 ? code : code - 3;
+  const double* Ar = cs + (ref1 ? CS_A : CS_B);
+  const double* Ai = cs + (ref1 ? CS_B : CS_A);
+  const double* pr = cs + (ref1 ? CS_P1 : CS_P2);
+  const double* pi_ = cs + (ref1 ? CS_P2 : CS_P1);
+  const double* sr = cs + (ref1 ? CS_S1 : CS_S2);
+  const double* si = cs + (ref1 ? CS_S2 : CS_S1);
+  {
+    const double* axv = Ar + 3 * ax;
+    for (int k = 0; k < 3; k++) bn[k] = (tsel < 0 ? -axv[k] : axv[k]);
+  }
+  double nref[3];
+  for (int k = 0; k < 3; k++) nref[k] = ref1 ? bn[k] : -bn[k];
+  int ia = 0; double bestd = -1;
+  for (int a = 0; a < 3; a++) { double v = fabs(dot3(Ai + 3 * a, nref)); if (v > bestd) { bestd = v; ia = a; } }
+  const double isg = dot3(Ai + 3 * ia, nref) > 0 ? -1.0 : 1.0;
+  const int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
+  const double* Ai1 = Ai + 3 * i1; const double* Ai2 = Ai + 3 * i2; const double* Ar1 = Ar + 3 * r1; const double* Ar2 = Ar + 3 * r2;
+  double fc[3];
+  for (int k = 0; k < 3; k++) fc[k] = pi_[k] + isg * si[ia] * Ai[3 * ia + k] - pr[k];
+  if (lane < 4) {
+    const double sg0 = (lane == 0 || lane == 3) ? 1.0 : -1.0, sg1 = (lane < 2) ? 1.0 : -1.0;
+    double vz[3];
+    for (int k = 0; k < 3; k++) vz[k] = fc[k] + sg0 * si[i1] * Ai1[k] + sg1 * si[i2] * Ai2[k];
+    cs[CS_PX + lane] = dot3(vz, Ar1); cs[CS_PY + lane] = dot3(vz, Ar2);
+  }
+  __syncwarp();
+  // Sutherland-Hodgman against |x| <= hx, |y| <= hy: lane i handles the polygon edge (i, i+1)
+  const double hx = sr[r1], hy = sr[r2];
+  int n = 4;
+  for (int side = 0; side < 4; side++) {
+    const double* px = cs + ((side & 1) ? CS_QX : CS_PX);
+    const double* py = cs + ((side & 1) ? CS_QY : CS_PY);
+    double* qx = cs + ((side & 1) ? CS_PX : CS_QX);
+    double* qy = cs + ((side & 1) ? CS_PY : CS_QY);
+    int emit = 0; double ax_ = 0, ay_ = 0, ix = 0, iy = 0; bool keep = false, crossing = false;
+    if (lane < n) {
+      int j = (lane + 1 == n) ? 0 : lane + 1;
+      ax_ = px[lane]; ay_ = py[lane];
+      double bx = px[j], by = py[j], da, db;
+      if (side == 0) { da = hx - ax_; db = hx - bx; }
+      else if (side == 1) { da = hx + ax_; db = hx + bx; }
+      else if (side == 2) { da = hy - ay_; db = hy - by; }
+      else { da = hy + ay_; db = hy + by; }
+      keep = da >= 0;
+      crossing = (da >= 0) != (db >= 0);
+      if (crossing) { double t = da / (da - db); ix = ax_ + t * (bx - ax_); iy = ay_ + t * (by - ay_); }
+      emit = (keep ? 1 : 0) + (crossing ? 1 : 0);
+    }
+    int incl = emit;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+    int base = incl - emit;
+    int total = __shfl_sync(FULLMASK, incl, 15);
+    if (keep) { qx[base] = ax_; qy[base] = ay_; base++; }
+    if (crossing) { qx[base] = ix; qy[base] = iy; }
+    n = total;
+    __syncwarp();
+    if (n == 0) return ncon;
+  }
+  // after four sides the polygon is back in PX / PY
+  const double o_n = dot3(fc, nref);
+  const double u1 = dot3(Ai1, nref), u2 = dot3(Ai2, nref);
+  const double a11 = dot3(Ai1, Ar1), a12 = dot3(Ai1, Ar2), a21 = dot3(Ai2, Ar1), a22 = dot3(Ai2, Ar2);
+  const double det = a11 * a22 - a12 * a21;
+  const double fx = dot3(fc, Ar1), fy = dot3(fc, Ar2);
+  bool valid = false; double depth = 0, pt[3] = {0, 0, 0};
+  if (lane < n && lane < 16) {
+    double x = cs[CS_PX + lane], y = cs[CS_PY + lane];
+    double dx = x - fx, dy = y - fy, h;
+    if (fabs(det) > 1e-12) {
+      double al = (dx * a22 - dy * a21) / det, be = (dy * a11 - dx * a12) / det;
+      h = o_n + al * u1 + be * u2;
+    } else h = o_n;
+    depth = sr[ax] - h;
+    valid = !(-depth >= 0);
+    for (int k = 0; k < 3; k++) pt[k] = pr[k] + x * Ar1[k] + y * Ar2[k] + (h + 0.5 * depth) * nref[k];
+  }
+  // duplicates: a point within 1e-10 of an earlier penetrating point is dropped
+  bool dup = false;
+  for (int e = 0; e < 15; e++) {
+    double ex = __shfl_sync(FULLMASK, pt[0], e), ey = __shfl_sync(FULLMASK, pt[1], e), ez = __shfl_sync(FULLMASK, pt[2], e);
+    int ev = __shfl_sync(FULLMASK, (int)valid, e);
+    if (e < lane && ev) { double qx_ = pt[0] - ex, qy_ = pt[1] - ey, qz_ = pt[2] - ez; if (qx_ * qx_ + qy_ * qy_ + qz_ * qz_ < 1e-20) dup = true; }
+    if (e + 1 >= n) break;
+  }
+  bool take = valid && !dup;
+  unsigned bal = __ballot_sync(FULLMASK, take);
+  int rank = __popc(bal & ((1u << lane) - 1));
+  int total = __popc(bal);
+  if (total > 8) total = 8;
+  if (take && rank < 8 && ncon + rank < S::MAXC) emit_contact(s, ncon + rank, pair, -depth, pt, bn);
+  return ncon + total;
+}
 
 template <class S>
-__device__ void collide(S& s, const DevModel* __restrict__ m, int lane, int nba) {
-  RawCon rc[8];
-  int n = 0;
-  if (lane < m->d.npair) {
-    int g1 = m->d.pair_g1[lane], g2 = m->d.pair_g2[lane];
-    int b1 = m->d.geom_body[g1], b2 = m->d.geom_body[g2];
-    bool skip = (nba <= CUBE) && (b1 == CUBE || b2 == CUBE);
-    if (!skip) {
-      double p1[3], R1[9], p2[3], R2[9];
-      geom_pose(s.xpos, s.xmat, m, g1, p1, R1);
-      geom_pose(s.xpos, s.xmat, m, g2, p2, R2);
+__device__ __noinline__ void collide(S& s, int lane, int nba) {
+  // broad phase: lane = candidate pair
+  bool near = false;
+  if (lane < c_m.d.npair) {
+    int g1 = c_m.d.pair_g1[lane], g2 = c_m.d.pair_g2[lane];
+    int b1 = c_m.d.geom_body[g1], b2 = c_m.d.geom_body[g2];
+    if (!((nba <= CUBE) && (b1 == CUBE || b2 == CUBE))) {
+      double p1[3], p2[3];
+      {
+        const double* gp = c_m.d.geom_pos[g1];
+        if (b1 < 0) { p1[0] = gp[0]; p1[1] = gp[1]; p1[2] = gp[2]; }
+        else { const double* R = s.xmat + b1 * 9; for (int r = 0; r < 3; r++) p1[r] = s.xpos[b1 * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+        gp = c_m.d.geom_pos[g2];
+        if (b2 < 0) { p2[0] = gp[0]; p2[1] = gp[1]; p2[2] = gp[2]; }
+        else { const double* R = s.xmat + b2 * 9; for (int r = 0; r < 3; r++) p2[r] = s.xpos[b2 * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+      }
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      if (m->d.geom_type[g1] == 0) {
-        double nrm[3] = {R1[2], R1[5], R1[8]};
-        if (dot3(dif, nrm) <= m->d.geom_rbound[g2]) n = plane_box(rc, p1, R1, p2, R2, m->d.geom_size[g2]);
+      if (c_m.d.geom_type[g1] == 0) {
+        const double* gm = c_m.d.geom_mat[g1];    // planes are static in this model
+        double nrm[3] = {gm[2], gm[5], gm[8]};
+        near = dot3(dif, nrm) <= c_m.d.geom_rbound[g2];
       } else {
-        double bound = m->d.geom_rbound[g1] + m->d.geom_rbound[g2];
-        if (dot3(dif, dif) <= bound * bound) n = box_box(rc, p1, R1, m->d.geom_size[g1], p2, R2, m->d.geom_size[g2]);
+        double bound = c_m.d.geom_rbound[g1] + c_m.d.geom_rbound[g2];
+        near = dot3(dif, dif) <= bound * bound;
       }
     }
   }
-  // exclusive prefix over lanes (pair order == contact order)
-  int incl = n;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
-  int base = incl - n;
-  int total = __shfl_sync(FULLMASK, incl, 31);
-  for (int c = 0; c < n; c++) {
-    int idx = base + c;
-    if (idx >= S::MAXC) break;
-    s.cdist[idx] = rc[c].dist;
-    s.cpair[idx] = lane;
-    double f[9];
-    f[0] = rc[c].normal[0]; f[1] = rc[c].normal[1]; f[2] = rc[c].normal[2];
-    // mju_makeFrame
-    double nn = sqrt(dot3(f, f));
-    if (nn < MINVAL) { f[0] = 1; f[1] = f[2] = 0; } else { f[0] /= nn; f[1] /= nn; f[2] /= nn; }
-    f[3] = f[4] = f[5] = 0;
-    if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
-    double t = dot3(f, f + 3);
-    f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
-    nn = sqrt(dot3(f + 3, f + 3));
-    if (nn < MINVAL) { f[3] = 1; f[4] = f[5] = 0; } else { f[3] /= nn; f[4] /= nn; f[5] /= nn; }
-    cross3(f + 6, f, f + 3);
-    for (int k = 0; k < 9; k++) s.cframe[idx * 9 + k] = f[k];
-    for (int k = 0; k < 3; k++) s.cpos[idx * 3 + k] = rc[c].pos[k];
+  unsigned todo = __ballot_sync(FULLMASK, near);
+  int ncon = 0;
+  while (todo) {
+    int p = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int g1 = c_m.d.pair_g1[p], g2 = c_m.d.pair_g2[p];
+    double p1[3], R1[9], p2[3], R2[9];
+    geom_pose(s, g1, p1, R1);
+    geom_pose(s, g2, p2, R2);
+    if (c_m.d.geom_type[g1] == 0) ncon = plane_box_coop(s, lane, p, ncon, p1, R1, p2, R2, c_m.d.geom_size[g2]);
+    else ncon = box_box_coop(s, lane, p, ncon, p1, R1, c_m.d.geom_size[g1], p2, R2, c_m.d.geom_size[g2]);
+    __syncwarp();
   }
   if (lane == 0) {
-    if (total > S::MAXC) { s.overflow += total - S::MAXC; total = S::MAXC; }
-    s.ncon = total;
+    if (ncon > S::MAXC) { s.overflow += ncon - S::MAXC; ncon = S::MAXC; }
+    s.ncon = ncon;
   }
   __syncwarp();
 }
@@ -635,6 +714,7 @@ __device__ double impedance(const double* solimp_in, double pos) {
   if (x >= 1 || x <= 0) return (x >= 1 ? s1 : s0);
   double y;
   if (s4 == 1) y = x;
+  else if (s4 == 2) { y = (x <= s3) ? (1 / s3) * (x * x) : 1 - (1 / (1 - s3)) * ((1 - x) * (1 - x)); }   // pow(v, 2) == v * v, pow(v, 1) == v
   else if (x <= s3) { double a = 1 / pow(s3, s4 - 1); y = a * pow(x, s4); }
   else { double b = 1 / pow(1 - s3, s4 - 1); y = 1 - b * pow(1 - x, s4); }
   return s0 + y * (s1 - s0);
@@ -644,11 +724,11 @@ __device__ double impedance(const double* solimp_in, double pos) {
 // point Jacobian column of dof j for a world point attached to body b (0 if j does not move b)
 template <class S>
 __device__ __forceinline__ void jac_col(const S& s, const DevModel* __restrict__ m, int b, int j, const double* pt, double* lin, double* rot) {
-  if (b >= 0 && ((m->d.ancmask[b] >> j) & 1u)) {
+  if (b >= 0 && ((c_m.d.ancmask[b] >> j) & 1u)) {
     const double* cd = s.cdof + j * 6;
     double off[3];
     if (b == CUBE) { off[0] = pt[0] - s.refcube[0]; off[1] = pt[1] - s.refcube[1]; off[2] = pt[2] - s.refcube[2]; }
-    else { off[0] = pt[0] - m->d.ref_robot[0]; off[1] = pt[1] - m->d.ref_robot[1]; off[2] = pt[2] - m->d.ref_robot[2]; }
+    else { off[0] = pt[0] - c_m.d.ref_robot[0]; off[1] = pt[1] - c_m.d.ref_robot[1]; off[2] = pt[2] - c_m.d.ref_robot[2]; }
     double t[3];
     cross3(t, cd, off);
     lin[0] = cd[3] + t[0]; lin[1] = cd[4] + t[1]; lin[2] = cd[5] + t[2];
@@ -693,21 +773,21 @@ __device__ __forceinline__ double row_dot(S& s, int r, const double* v) {
 // and the reference acceleration of every row.  Returns false if the layout's capacity is exceeded.
 template <class S>
 __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
-  const double h = m->d.timestep;
+  const double h = c_m.d.timestep;
   // connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1)
   if (lane < 4) {
     int e = lane >> 1, side = lane & 1;
-    int b = side ? m->d.con_body2[e] : m->d.con_body1[e];
-    const double* a = side ? m->d.con_anchor2[e] : m->d.con_anchor1[e];
+    int b = side ? c_m.d.con_body2[e] : c_m.d.con_body1[e];
+    const double* a = side ? c_m.d.con_anchor2[e] : c_m.d.con_anchor1[e];
     const double* R = s.xmat + b * 9;
     for (int r = 0; r < 3; r++) s.anchors[lane * 3 + r] = s.xpos[b * 3 + r] + R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
   }
   // limits: lane j < 12, lower then upper (both can not be active for a positive-width range)
   int lim = 0, neg = 0;
-  if (lane < NH && m->d.jnt_limited[lane]) {
+  if (lane < NH && c_m.d.jnt_limited[lane]) {
     double v = s.qpos[lane];
-    if (v - m->d.jnt_range[lane][0] < 0) lim = 1;
-    else if (m->d.jnt_range[lane][1] - v < 0) { lim = 1; neg = 1; }
+    if (v - c_m.d.jnt_range[lane][0] < 0) lim = 1;
+    else if (c_m.d.jnt_range[lane][1] - v < 0) { lim = 1; neg = 1; }
   }
   unsigned bal = __ballot_sync(FULLMASK, lim);
   const int nU = __popc(bal);
@@ -715,7 +795,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   if (lane == 0) {
     int nRc = 0, nC = 0, nF = 0, nc = s.ncon;
     for (int c = 0; c < nc; c++) {
-      const PairParam& pp = m->pair[s.cpair[c]];
+      const PairParam& pp = c_m.pair[s.cpair[c]];
       int rows = 2 * (pp.dim - 1);
       if (pp.ptype == 0) nRc += rows; else if (pp.ptype == 1) nC += rows; else nF += rows;
     }
@@ -726,7 +806,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       s.overflow += 1;
       while (nc > 0 && !fits) {
         nc--;
-        const PairParam& pp = m->pair[s.cpair[nc]];
+        const PairParam& pp = c_m.pair[s.cpair[nc]];
         int rows = 2 * (pp.dim - 1);
         if (pp.ptype == 0) { nRc -= rows; nR -= rows; } else if (pp.ptype == 1) nC -= rows; else nF -= rows;
         fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
@@ -735,7 +815,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     }
     int r0 = 7, r1 = nR, r2 = nR + nC, orow = 7 + nU;
     for (int c = 0; c < nc; c++) {
-      const PairParam& pp = m->pair[s.cpair[c]];
+      const PairParam& pp = c_m.pair[s.cpair[c]];
       int rows = 2 * (pp.dim - 1), base;
       if (pp.ptype == 0) { base = r0; r0 += rows; } else if (pp.ptype == 1) { base = r1; r1 += rows; } else { base = r2; r2 += rows; }
       s.crow[c] = base;
@@ -758,17 +838,17 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     int row = w / NH, j = w % NH;
     int e = row / 3, r = row % 3;
     double l1[3], l2[3], rt[3];
-    jac_col(s, m, m->d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
-    jac_col(s, m, m->d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
+    jac_col(s, m, c_m.d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
+    jac_col(s, m, c_m.d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
     s.pool[row * SR + j] = l1[r] - l2[r];
   }
   if (lane < NH) {
     int j = lane;
     double v = 0;
-    if (j == m->d.jeq_dof1) v = 1;
-    if (j == m->d.jeq_dof2) {
-      double dif = s.qpos[j] - m->d.qpos0[j];
-      const double* pc = m->d.jeq_polycoef;
+    if (j == c_m.d.jeq_dof1) v = 1;
+    if (j == c_m.d.jeq_dof2) {
+      double dif = s.qpos[j] - c_m.d.qpos0[j];
+      const double* pc = c_m.d.jeq_polycoef;
       v = -(pc[1] + 2 * pc[2] * dif + 3 * pc[3] * dif * dif + 4 * pc[4] * dif * dif * dif);
     }
     s.pool[6 * SR + j] = v;
@@ -777,10 +857,10 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   const int ncon = s.ncon;
   for (int w = lane; w < ncon * NV; w += 32) {
     int c = w / NV, j = w % NV;
-    const PairParam& pp = m->pair[s.cpair[c]];
+    const PairParam& pp = c_m.pair[s.cpair[c]];
     if (pp.ptype == 0 && j >= NH) continue;
     if (pp.ptype == 1 && j < NH) continue;
-    int b1 = m->d.geom_body[pp.g1], b2 = m->d.geom_body[pp.g2];
+    int b1 = c_m.d.geom_body[pp.g1], b2 = c_m.d.geom_body[pp.g2];
     const double* pt = s.cpos + c * 3;
     const double* f = s.cframe + c * 9;
     double l1[3], r1[3], l2[3], r2[3];
@@ -813,24 +893,24 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     double pos, diag, pyr = 0;
     if (kind == 0) {
       pos = s.anchors[(2 * idx) * 3 + sub] - s.anchors[(2 * idx + 1) * 3 + sub];
-      solref = m->d.con_solref[idx]; solimp = m->d.con_solimp[idx]; diag = m->d.con_diag[idx];
+      solref = c_m.d.con_solref[idx]; solimp = c_m.d.con_solimp[idx]; diag = c_m.d.con_diag[idx];
     } else if (kind == 1) {
-      int d1 = m->d.jeq_dof1, d2 = m->d.jeq_dof2;
-      double p1 = s.qpos[d1] - m->d.qpos0[d1], dif = s.qpos[d2] - m->d.qpos0[d2];
-      const double* pc = m->d.jeq_polycoef;
+      int d1 = c_m.d.jeq_dof1, d2 = c_m.d.jeq_dof2;
+      double p1 = s.qpos[d1] - c_m.d.qpos0[d1], dif = s.qpos[d2] - c_m.d.qpos0[d2];
+      const double* pc = c_m.d.jeq_polycoef;
       pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
-      solref = m->d.jeq_solref; solimp = m->d.jeq_solimp; diag = m->d.jeq_diag;
+      solref = c_m.d.jeq_solref; solimp = c_m.d.jeq_solimp; diag = c_m.d.jeq_diag;
     } else if (kind == 2) {
       double v = s.qpos[idx];
-      pos = (meta & 0x100) ? m->d.jnt_range[idx][1] - v : v - m->d.jnt_range[idx][0];
-      solref = m->d.jnt_solref[idx]; solimp = m->d.jnt_solimp[idx]; diag = m->d.dof_invweight0[idx];
+      pos = (meta & 0x100) ? c_m.d.jnt_range[idx][1] - v : v - c_m.d.jnt_range[idx][0];
+      solref = c_m.d.jnt_solref[idx]; solimp = c_m.d.jnt_solimp[idx]; diag = c_m.d.dof_invweight0[idx];
     } else {
-      const PairParam& pp = m->pair[s.cpair[idx]];
+      const PairParam& pp = c_m.pair[s.cpair[idx]];
       double mu = pp.friction[0];
       pos = s.cdist[idx];
       solref = pp.solref; solimp = pp.solimp;
       diag = pp.tran + mu * mu * pp.tran;     // the pyramid's first-row diagApprox; all rows share R = 2 mu^2 R_first
-      pyr = mu / sqrt(m->d.impratio);
+      pyr = mu / sqrt(c_m.d.impratio);
     }
     double sr0 = solref[0], sr1 = solref[1];
     if (sr0 > 0) sr0 = fmax(sr0, 2 * h);
@@ -854,7 +934,7 @@ template <class S>
 __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    unsigned mask = m->d.ancmask[b];
+    unsigned mask = c_m.d.ancmask[b];
     double acc = 0;
     while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j]; }
     s.cvel[w] = acc;
@@ -864,7 +944,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
     int j = lane;
     double vel[6];
     if (j < NH) {
-      int p = m->d.parent[j];
+      int p = c_m.d.parent[j];
       for (int c = 0; c < 6; c++) vel[c] = (p >= 0 ? s.cvel[p * 6 + c] : 0.0);
       cross_motion(s.cdof_dot + j * 6, vel, s.cdof + j * 6);
     } else if (j < 15) {
@@ -878,8 +958,8 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    unsigned mask = m->d.ancmask[b];
-    double acc = (c >= 3 ? -m->d.gravity[c - 3] : 0.0);
+    unsigned mask = c_m.d.ancmask[b];
+    double acc = (c >= 3 ? -c_m.d.gravity[c - 3] : 0.0);
     while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j]; }
     s.cacc[w] = acc;
   }
@@ -897,7 +977,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    int e = b + m->d.subtree_size[b];
+    int e = b + c_m.d.subtree_size[b];
     if (e > nba) e = nba;
     double acc = 0;
     for (int k = e - 1; k >= b; k--) acc += s.cacc[k * 6 + c];
@@ -906,7 +986,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   if (lane < nva) {
     const double* a = s.cdof + lane * 6;
-    const double* b = s.cvel + m->d.dof_body[lane] * 6;
+    const double* b = s.cvel + c_m.d.dof_body[lane] * 6;
     s.qfrc_bias[lane] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
   }
   __syncwarp();
@@ -917,22 +997,22 @@ template <class S>
 __device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   double force = 0;
   if (lane < NU) {
-    const double* mom = m->d.act_moment[lane];
+    const double* mom = c_m.d.act_moment[lane];
     double len = 0, vel = 0;
     for (int i = 0; i < NH; i++) { double c = mom[i]; if (c != 0) { len += c * s.qpos[i]; vel += c * s.qvel[i]; } }
     double ctrl = s.ctrl[lane];
-    if (m->d.act_ctrllimited[lane]) ctrl = fmax(m->d.act_ctrlrange[lane][0], fmin(m->d.act_ctrlrange[lane][1], ctrl));
-    const double* bp = m->d.act_bias[lane];
-    force = m->d.act_gain[lane] * ctrl + bp[0] + bp[1] * len + bp[2] * vel;
-    if (m->d.act_forcelimited[lane]) force = fmax(m->d.act_forcerange[lane][0], fmin(m->d.act_forcerange[lane][1], force));
+    if (c_m.d.act_ctrllimited[lane]) ctrl = fmax(c_m.d.act_ctrlrange[lane][0], fmin(c_m.d.act_ctrlrange[lane][1], ctrl));
+    const double* bp = c_m.d.act_bias[lane];
+    force = c_m.d.act_gain[lane] * ctrl + bp[0] + bp[1] * len + bp[2] * vel;
+    if (c_m.d.act_forcelimited[lane]) force = fmax(c_m.d.act_forcerange[lane][0], fmin(c_m.d.act_forcerange[lane][1], force));
   }
   double qa = 0;
 #pragma unroll
   for (int a = 0; a < NU; a++) {
     double fa = __shfl_sync(FULLMASK, force, a);
-    if (lane < NV) qa += m->d.act_moment[a][lane] * fa;
+    if (lane < NV) qa += c_m.d.act_moment[a][lane] * fa;
   }
-  if (lane < nva) s.qfrc_smooth[lane] = -m->d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
+  if (lane < nva) s.qfrc_smooth[lane] = -c_m.d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
   __syncwarp();
 }
 
@@ -1048,8 +1128,7 @@ struct Newton {
   }
   __device__ void newton_direction() {
     build_H();
-    chol_sys(s.H, s.H, s.invd, 0.0, lane, nva, coupled);
-    double mg = solve_sys(s.H, s.invd, lane, nva, coupled, lane < nva ? s.grad[lane] : 0.0);
+    double mg = factor_solve(s.H, s.H, 0.0, lane, nva, coupled, lane < nva ? s.grad[lane] : 0.0);
     if (lane < nva) s.search[lane] = -mg;
     __syncwarp();
   }
@@ -1072,7 +1151,7 @@ struct Newton {
     if (lane < nva) sn = s.search[lane] * s.search[lane];
     double snorm = sqrt(warp_sum(sn));
     if (snorm < MINVAL) return 0;
-    double gtol = m->d.tolerance * m->d.ls_tolerance * snorm / scale;
+    double gtol = c_m.d.tolerance * c_m.d.ls_tolerance * snorm / scale;
     double mv = mulM_row(s, lane, nva, s.search);
     if (lane < nva) s.Mv[lane] = mv;
     rows_times(s.search, s.eJv, false);
@@ -1088,7 +1167,7 @@ struct Newton {
         qa[t] = 0.5 * D * ja * ja; qb[t] = D * ja * jv; qc[t] = 0.5 * D * jv * jv;
       } else { qa[t] = qb[t] = qc[t] = 0; }
     }
-    const int lsmax = m->d.ls_iterations;
+    const int lsmax = c_m.d.ls_iterations;
     Pt p0, p1, p2, pmid, p1n, p2n;
     p0.alpha = 0; ls_eval(p0);
     p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(p1);
@@ -1106,17 +1185,20 @@ struct Newton {
     p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n);
     while (iter < lsmax) {
       pmid.alpha = 0.5 * (p1.alpha + p2.alpha); ls_eval(pmid); iter++;
-      Pt* cand[3] = {&p1n, &p2n, &pmid};
-      int besti = -1;
-      for (int i = 0; i < 3; i++)
-        if (fabs(cand[i]->d0) < gtol && (besti < 0 || cand[i]->cost < cand[besti]->cost)) besti = i;
-      if (besti >= 0) return cand[besti]->alpha;
+      // candidates in the order p1next, p2next, midpoint
+      double balpha = 0, bcost = 0; bool found = false;
+      if (fabs(p1n.d0) < gtol) { balpha = p1n.alpha; bcost = p1n.cost; found = true; }
+      if (fabs(p2n.d0) < gtol && (!found || p2n.cost < bcost)) { balpha = p2n.alpha; bcost = p2n.cost; found = true; }
+      if (fabs(pmid.d0) < gtol && (!found || pmid.cost < bcost)) { balpha = pmid.alpha; bcost = pmid.cost; found = true; }
+      if (found) return balpha;
       int b1 = 0, b2 = 0;
-      for (int i = 0; i < 3; i++) {
-        Pt c = *cand[i];
-        if (c.d0 * dir < 0 && (c.alpha - p2.alpha) * dir > 0 && (p1.alpha - c.alpha) * dir > 0) { p2 = c; b2 = 1; }
-        else if (c.d0 * dir > 0 && (p1.alpha - c.alpha) * dir > 0 && (c.alpha - p2.alpha) * dir > 0) { p1 = c; b1 = 1; }
-      }
+#define LS_BRACKET(c)                                                                                                   \
+      if ((c).d0 * dir < 0 && ((c).alpha - p2.alpha) * dir > 0 && (p1.alpha - (c).alpha) * dir > 0) { p2 = (c); b2 = 1; }     \
+      else if ((c).d0 * dir > 0 && (p1.alpha - (c).alpha) * dir > 0 && ((c).alpha - p2.alpha) * dir > 0) { p1 = (c); b1 = 1; }
+      { Pt c = p1n; LS_BRACKET(c) }
+      { Pt c = p2n; LS_BRACKET(c) }
+      { Pt c = pmid; LS_BRACKET(c) }
+#undef LS_BRACKET
       if (!b1 && !b2) break;
       if (b1) { p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n); }
       if (b2) { p2n.alpha = p2.alpha - p2.d0 / p2.d1; ls_eval(p2n); }
@@ -1125,7 +1207,7 @@ struct Newton {
   }
 
   __device__ void solve() {
-    const double scale = 1.0 / (m->d.meaninertia * (double)NV);
+    const double scale = 1.0 / (c_m.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
     rows_times(s.warm, s.eJaref, true);
@@ -1147,7 +1229,7 @@ struct Newton {
     update_cost_grad();
     newton_direction();
     int iter = 0;
-    const int maxiter = m->d.iterations;
+    const int maxiter = c_m.d.iterations;
     while (iter < maxiter) {
       double alpha = line_search(scale);
       if (alpha == 0) break;
@@ -1160,7 +1242,7 @@ struct Newton {
       double gn = 0;
       if (lane < nva) gn = s.grad[lane] * s.grad[lane];
       double improvement = scale * (oldcost - cost), gradient = scale * sqrt(warp_sum(gn));
-      if (improvement < m->d.tolerance || gradient < m->d.tolerance) break;
+      if (improvement < c_m.d.tolerance || gradient < c_m.d.tolerance) break;
       newton_direction();
     }
     if (lane == 0) s.iters += iter;
@@ -1171,17 +1253,16 @@ struct Newton {
 
 // forward(): everything mj_forward does for this model.  Returns false if the layout overflowed.
 template <class S>
-__device__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+__device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   fk(s, m, lane, nba);
   cinert_cdof(s, m, lane, nba, nva);
   crb_mass(s, m, lane, nba, nva);
   velocity_rne(s, m, lane, nba, nva);
   actuation_smooth(s, m, lane, nva);
-  chol_sys(s.M, s.H, s.invd, 0.0, lane, nva, false);
-  double qs = solve_sys(s.H, s.invd, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] : 0.0);
+  double qs = factor_solve(s.M, s.H, 0.0, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] : 0.0);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
-  collide(s, m, lane, nba);
+  collide(s, lane, nba);
   bool ok = make_rows(s, m, lane, nva);
   if (!ok && !S::IS_BIG) return false;
   Newton<S> nw{s, m, lane, nva, s.nefc};
@@ -1191,10 +1272,10 @@ __device__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba,
 
 // euler(): (M + h*diag(damping))^-1 (qfrc_smooth + qfrc_constraint), semi-implicit advance.
 template <class S>
-__device__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
-  const double h = m->d.timestep;
-  chol_sys(s.M, s.H, s.invd, lane < nva ? h * m->d.damping[lane] : 0.0, lane, nva, false);
-  double qacc = solve_sys(s.H, s.invd, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
+__device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
+  const double h = c_m.d.timestep;
+  double qacc = factor_solve(s.M, s.H, lane < nva ? h * c_m.d.damping[lane] : 0.0, lane, nva, false,
+                             lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
   if (lane < nva) s.qvel[lane] += h * qacc;
   __syncwarp();
   if (lane < NH) s.qpos[lane] += h * s.qvel[lane];
@@ -1238,7 +1319,7 @@ __device__ double philox_uniform(uint64_t seed, uint32_t env, unsigned long long
 __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& cfg, uint64_t seed, uint32_t env, unsigned long long& ctr, double* g) {
   g[0] = -0.12 + (0.12 - (-0.12)) * philox_uniform(seed, env, ctr);
   g[1] = -0.06 + (0.06 - (-0.06)) * philox_uniform(seed, env, ctr);
-  g[2] = m->d.height_offset;
+  g[2] = c_m.d.height_offset;
   if (cfg.target_in_the_air) {
     if (philox_uniform(seed, env, ctr) < 0.5) g[2] += 0.0 + (0.1 - 0.0) * philox_uniform(seed, env, ctr);
   }
@@ -1247,16 +1328,16 @@ __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& 
 // observation (mycobot.py:342-388): written from the frames currently in shared memory (stale by one
 // substep after a step, fresh after forward), qpos / qvel current.
 template <class S>
-__device__ void write_obs(S& s, const DevModel* __restrict__ m, const mcb_task_cfg& cfg, int lane, int env, double* obs, double* ag, double* dg, double* ag_out3) {
-  const double dt = cfg.frame_skip * m->d.timestep;
-  int eb = m->d.eef_body;
+__device__ __noinline__ void write_obs(S& s, const DevModel* __restrict__ m, const mcb_task_cfg& cfg, int lane, int env, double* obs, double* ag, double* dg, double* ag_out3) {
+  const double dt = cfg.frame_skip * c_m.d.timestep;
+  int eb = c_m.d.eef_body;
   const double* R = s.xmat + eb * 9;
-  const double* ep = m->d.eef_pos;
+  const double* ep = c_m.d.eef_pos;
   double grip[3], gvel[3] = {0, 0, 0};
   for (int r = 0; r < 3; r++) grip[r] = s.xpos[eb * 3 + r] + R[3 * r] * ep[0] + R[3 * r + 1] * ep[1] + R[3 * r + 2] * ep[2];
   {
-    unsigned mask = m->d.ancmask[eb];
-    double off[3] = {grip[0] - m->d.ref_robot[0], grip[1] - m->d.ref_robot[1], grip[2] - m->d.ref_robot[2]};
+    unsigned mask = c_m.d.ancmask[eb];
+    double off[3] = {grip[0] - c_m.d.ref_robot[0], grip[1] - c_m.d.ref_robot[1], grip[2] - c_m.d.ref_robot[2]};
     while (mask) {
       int j = __ffs(mask) - 1; mask &= mask - 1;
       const double* cd = s.cdof + j * 6;
@@ -1343,21 +1424,21 @@ __device__ void store_state(const S& s, double* __restrict__ st, int lane) {
 
 // reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.  false: layout overflow.
 template <class S>
-__device__ bool reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
-  for (int w = lane; w < NQ; w += 32) s.qpos[w] = m->d.init_qpos[w];
+__device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
+  for (int w = lane; w < NQ; w += 32) s.qpos[w] = c_m.d.init_qpos[w];
   if (lane < NV) s.qvel[lane] = 0;
-  if (lane < NU) s.ctrl[lane] = m->d.init_ctrl[lane];
+  if (lane < NU) s.ctrl[lane] = c_m.d.init_ctrl[lane];
   __syncwarp();
   if (!forward(s, m, lane, nba, nva)) return false;
-  double oxy[2] = {m->d.initial_gripper_xpos[0], m->d.initial_gripper_xpos[1]};
+  double oxy[2] = {c_m.d.initial_gripper_xpos[0], c_m.d.initial_gripper_xpos[1]};
   double g[3];
   if (lane == 0) {
     if (a.cfg.has_object) {
       if (a.inj_xy) { oxy[0] = a.inj_xy[(size_t)env * 2]; oxy[1] = a.inj_xy[(size_t)env * 2 + 1]; }
       else {
         int guard = 0;
-        while (sqrt((oxy[0] - m->d.initial_gripper_xpos[0]) * (oxy[0] - m->d.initial_gripper_xpos[0]) +
-                    (oxy[1] - m->d.initial_gripper_xpos[1]) * (oxy[1] - m->d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
+        while (sqrt((oxy[0] - c_m.d.initial_gripper_xpos[0]) * (oxy[0] - c_m.d.initial_gripper_xpos[0]) +
+                    (oxy[1] - c_m.d.initial_gripper_xpos[1]) * (oxy[1] - c_m.d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
           sample_goal(m, a.cfg, a.seed, env, ctr, g);
           oxy[0] = g[0]; oxy[1] = g[1];
         }
@@ -1544,8 +1625,8 @@ __global__ void init_state_kernel(double* state, int* elapsed, double* ep_return
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
   for (int k = 0; k < MCB_STATE_STRIDE; k++) st[k] = 0;
-  for (int k = 0; k < NQ; k++) st[k] = m->d.init_qpos[k];
-  for (int k = 0; k < NU; k++) st[37 + k] = m->d.init_ctrl[k];
+  for (int k = 0; k < NQ; k++) st[k] = c_m.d.init_qpos[k];
+  for (int k = 0; k < NU; k++) st[37 + k] = c_m.d.init_ctrl[k];
   elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
 }
 
@@ -1697,6 +1778,7 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   }
   CK(cudaMalloc(&m->dev, sizeof(DevModel)));
   CK(cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyToSymbol(c_m, &h, sizeof(DevModel)));
   *out = m;
   return 0;
 }

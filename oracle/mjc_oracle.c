@@ -527,7 +527,8 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
   double det = a11 * a22 - a12 * a21;
   double fx = dot3(fc, Ar[r1]), fy = dot3(fc, Ar[r2]);
   int n = clip_poly(px, py, 4, sr[r1], sr[r2]);
-  int cnt = 0;
+  int cnt = 0, ncand = 0;
+  double cand[16][3];
   for (int c = 0; c < n && cnt < 8; c++) {
     /* recover height above reference center along nref */
     double dx = px[c] - fx, dy = py[c] - fy, h;
@@ -537,13 +538,16 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
     } else h = o_n;
     double depth = sr[ax] - h;
     if (-depth >= margin) continue;
-    /* skip duplicates */
+    /* skip duplicates: a point within 1e-10 of an EARLIER PENETRATING point (accepted or not) is dropped */
+    double pt[3];
+    for (int k = 0; k < 3; k++) pt[k] = pr[k] + px[c] * Ar[r1][k] + py[c] * Ar[r2][k] + (h + 0.5 * depth) * nref[k];
     int dup = 0;
-    for (int e = 0; e < cnt; e++) {
-      double q[3];
-      for (int k = 0; k < 3; k++) q[k] = pr[k] + px[c] * Ar[r1][k] + py[c] * Ar[r2][k] + (h + 0.5 * depth) * nref[k] - out[e].pos[k];
+    for (int e = 0; e < ncand; e++) {
+      double q[3] = {pt[0] - cand[e][0], pt[1] - cand[e][1], pt[2] - cand[e][2]};
       if (dot3(q, q) < 1e-20) dup = 1;
     }
+    for (int k = 0; k < 3; k++) cand[ncand][k] = pt[k];
+    ncand++;
     if (dup) continue;
     for (int k = 0; k < 3; k++) {
       out[cnt].pos[k] = pr[k] + px[c] * Ar[r1][k] + py[c] * Ar[r2][k] + (h + 0.5 * depth) * nref[k];
