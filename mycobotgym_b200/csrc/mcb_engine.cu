@@ -375,6 +375,13 @@ __device__ __forceinline__ double factor_solve(const double* src, double* dst, d
   if (nva > NH) b = chol_solve_blk<12, 6>(src, dst, dadd, lane, b);
   return b;
 }
+// the same for M and M + h*diag(damping): the free cube's block of M is diagonal (rotational dofs are expressed in
+// the body's principal frame about its centre of mass), so cube lanes just divide
+__device__ __forceinline__ double factor_solve_M(const double* M, double* dst, double dadd, int lane, int nva, double b) {
+  b = chol_solve_blk<0, 12>(M, dst, dadd, lane, b);
+  if (lane >= NH && lane < nva) b = b / (M[TRI(lane, 0) + lane] + dadd);
+  return b;
+}
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
 template <class S>
 __device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const double* v) {
@@ -1252,18 +1259,30 @@ struct Newton {
 };
 
 // forward(): everything mj_forward does for this model.  Returns false if the layout overflowed.
+// `sync`: the warps of a CTA run the substep loop in lockstep (CTA barriers at the stage boundaries) so that they
+// share instruction-cache lines -- the kernel is thousands of straight-line instructions per substep and
+// independent warps drifting apart made instruction fetch the top stall (profiles/r01c).  Every path through
+// forward() executes exactly NSYNC_FWD barriers when sync is set.
+#define NSYNC_FWD 6
+#define FSYNC() do { if (sync) __syncthreads(); } while (0)
 template <class S>
-__device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
+__device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva, bool sync) {
+  FSYNC();
   fk(s, m, lane, nba);
   cinert_cdof(s, m, lane, nba, nva);
+  FSYNC();
   crb_mass(s, m, lane, nba, nva);
   velocity_rne(s, m, lane, nba, nva);
+  FSYNC();
   actuation_smooth(s, m, lane, nva);
-  double qs = factor_solve(s.M, s.H, 0.0, lane, nva, false, lane < nva ? s.qfrc_smooth[lane] : 0.0);
+  double qs = factor_solve_M(s.M, s.H, 0.0, lane, nva, lane < nva ? s.qfrc_smooth[lane] : 0.0);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
+  FSYNC();
   collide(s, lane, nba);
+  FSYNC();
   bool ok = make_rows(s, m, lane, nva);
+  FSYNC();
   if (!ok && !S::IS_BIG) return false;
   Newton<S> nw{s, m, lane, nva, s.nefc};
   nw.solve();
@@ -1274,8 +1293,8 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
 template <class S>
 __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   const double h = c_m.d.timestep;
-  double qacc = factor_solve(s.M, s.H, lane < nva ? h * c_m.d.damping[lane] : 0.0, lane, nva, false,
-                             lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
+  double qacc = factor_solve_M(s.M, s.H, lane < nva ? h * c_m.d.damping[lane] : 0.0, lane, nva,
+                               lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
   if (lane < nva) s.qvel[lane] += h * qacc;
   __syncwarp();
   if (lane < NH) s.qpos[lane] += h * s.qvel[lane];
@@ -1429,7 +1448,7 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
   if (lane < NV) s.qvel[lane] = 0;
   if (lane < NU) s.ctrl[lane] = c_m.d.init_ctrl[lane];
   __syncwarp();
-  if (!forward(s, m, lane, nba, nva)) return false;
+  if (!forward(s, m, lane, nba, nva, false)) return false;
   double oxy[2] = {c_m.d.initial_gripper_xpos[0], c_m.d.initial_gripper_xpos[1]};
   double g[3];
   if (lane == 0) {
@@ -1454,7 +1473,7 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
     s.goal[0] = g[0]; s.goal[1] = g[1]; s.goal[2] = g[2];
   }
   __syncwarp();
-  return forward(s, m, lane, nba, nva);
+  return forward(s, m, lane, nba, nva, false);
 }
 
 template <class S>
@@ -1495,24 +1514,29 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The env kernel: one warp (= one CTA) per env.  BIG = false is the first launch over all envs; envs whose
-// constraint set overflows the small layout leave every output untouched and enqueue themselves on redo_list,
-// which the BIG = true launch then serves (grid-stride over the list).
+// The env kernel: one warp per env.  BIG = false is the first launch over all envs, WPB warps per CTA running the
+// substep loop in lockstep; envs whose constraint set overflows the small layout leave every output untouched and
+// enqueue themselves on redo_list, which the BIG = true launch (one warp per CTA, grid-stride over the list) serves.
+#define WPB_SMALL 16
 template <bool BIG>
-__global__ void __launch_bounds__(32, BIG ? 4 : 16) mcb_env_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef EnvS<BIG> S;
-  const int lane = threadIdx.x & 31;
-  S& s = *reinterpret_cast<S*>(smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wpb = BIG ? 1 : WPB_SMALL;
+  S& s = *reinterpret_cast<S*>(smem_raw + (size_t)wid * sizeof(S));
   const DevModel* __restrict__ m = a.m;
   const mcb_task_cfg& cfg = a.cfg;
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
   const int nwork = BIG ? *a.redo_count : a.n_envs;
+  const bool lockstep = !BIG;
 
-  for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
-    const int env = BIG ? a.redo_list[item] : item;
-    if (a.mode == MODE_RESET && a.mask && !a.mask[env]) continue;
+  for (int item0 = blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
+    const int item = item0 + wid;
+    bool valid = item < nwork;
+    const int env = valid ? (BIG ? a.redo_list[item] : item) : 0;
+    if (valid && a.mode == MODE_RESET && a.mask && !a.mask[env]) valid = false;
 
     // zero what has a static sparsity pattern or is read before it is first written
     for (int w = lane; w < NTRI; w += 32) { s.M[w] = 0; s.H[w] = 0; }
@@ -1523,21 +1547,21 @@ __global__ void __launch_bounds__(32, BIG ? 4 : 16) mcb_env_kernel(const StepArg
     if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; s.search[lane] = 0; s.Mv[lane] = 0; }
     if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
     __syncwarp();
-    load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
-    unsigned long long ctr = a.rng_ctr[env];
+    unsigned long long ctr = 0;
+    if (valid) { load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane); ctr = a.rng_ctr[env]; }
     double achieved[3];
     int substeps = 0;
-    bool ok = true;
+    bool ok = valid;
 
     if (a.mode == MODE_RESET) {
-      ok = reset_env(s, a, m, lane, env, nba, nva, ctr);
+      if (ok) ok = reset_env(s, a, m, lane, env, nba, nva, ctr);
       if (ok) {
         write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
         if (lane == 0) { a.elapsed[env] = 0; a.ep_return[env] = 0; }
       }
       substeps = 2;
     } else if (a.mode == MODE_FORWARD) {
-      ok = forward(s, m, lane, nba, nva);
+      if (ok) ok = forward(s, m, lane, nba, nva, false);
       if (ok) {
         write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
         if (a.debug && env == a.debug_env) debug_dump(s, a, lane, nva);
@@ -1545,21 +1569,23 @@ __global__ void __launch_bounds__(32, BIG ? 4 : 16) mcb_env_kernel(const StepArg
       substeps = 1;
     } else {
       // MyCobotEnv.step, joint controller: ctrl = clip(action, -1, 1) widened to double (mycobot.py:133,192-193)
-      if (lane < NU) {
+      if (ok && lane < NU) {
         float act = a.actions[(size_t)env * NU + lane];
         act = fminf(1.0f, fmaxf(-1.0f, act));
         s.ctrl[lane] = (double)act;
       }
       __syncwarp();
-      for (int it = 0; it < cfg.frame_skip && ok; it++) {
-        ok = forward(s, m, lane, nba, nva);
+      for (int it = 0; it < cfg.frame_skip; it++) {
+        if (ok) ok = forward(s, m, lane, nba, nva, lockstep);
+        else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) __syncthreads(); }
+        if (lockstep) __syncthreads();
         if (ok) euler(s, m, lane, nva);
       }
       substeps = cfg.frame_skip;
       if (ok && cfg.block_gripper) {  // _step_callback (mycobot.py:300-306)
         if (lane == 0) { s.qpos[7] = 0; s.qpos[9] = 0; }
         __syncwarp();
-        ok = forward(s, m, lane, nba, nva);
+        ok = forward(s, m, lane, nba, nva, false);
         substeps++;
       }
       if (ok) {
@@ -1593,19 +1619,21 @@ __global__ void __launch_bounds__(32, BIG ? 4 : 16) mcb_env_kernel(const StepArg
       }
     }
     __syncwarp();
-    if (!ok) {
-      // small layout overflowed: leave the env untouched for the big-layout launch
-      // (observation rows written above are rewritten by it; state, counters and statistics are not yet committed)
-      if (lane == 0) { int k = atomicAdd(a.redo_count, 1); a.redo_list[k] = env; }
-      continue;
-    }
-    store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
-    if (lane == 0) {
-      a.rng_ctr[env] = ctr;
-      if (a.mode == MODE_STEP) atomicAdd(a.stats + 4, 1.0);
-      if (BIG && s.overflow) atomicAdd(a.stats + 5, (double)s.overflow);
-      atomicAdd(a.stats + 6, (double)s.iters);
-      atomicAdd(a.stats + 7, (double)substeps);
+    if (valid) {
+      if (!ok) {
+        // small layout overflowed: leave the env untouched for the big-layout launch
+        // (observation rows written above are rewritten by it; state, counters and statistics are not yet committed)
+        if (lane == 0) { int k = atomicAdd(a.redo_count, 1); a.redo_list[k] = env; }
+      } else {
+        store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
+        if (lane == 0) {
+          a.rng_ctr[env] = ctr;
+          if (a.mode == MODE_STEP) atomicAdd(a.stats + 4, 1.0);
+          if (BIG && s.overflow) atomicAdd(a.stats + 5, (double)s.overflow);
+          atomicAdd(a.stats + 6, (double)s.iters);
+          atomicAdd(a.stats + 7, (double)substeps);
+        }
+      }
     }
     __syncwarp();
   }
@@ -1705,7 +1733,7 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
     iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
   } else {
     CK(cudaMemsetAsync(b->redo_count, 0, sizeof(int), st));
-    mcb_env_kernel<false><<<b->n_envs, 32, b->smem_small, st>>>(a);
+    mcb_env_kernel<false><<<(b->n_envs + WPB_SMALL - 1) / WPB_SMALL, 32 * WPB_SMALL, b->smem_small, st>>>(a);
   }
   CK(cudaGetLastError());
   // fallback launch for envs that overflowed the small layout (grid-stride over the device list; usually empty)
@@ -1800,7 +1828,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   b->obs_dim = cfg->has_object ? MCB_OBS_OBJECT : MCB_OBS_REACH;
   if (cfg->nefc_max != 0 && cfg->nefc_max != 48 && cfg->nefc_max != 128) { delete b; return fail("mcb_batch_create: nefc_max must be 0 (two-tier), 48 or 128"); }
   b->big_only = cfg->nefc_max == 128;
-  b->smem_small = sizeof(EnvS<false>);
+  b->smem_small = sizeof(EnvS<false>) * WPB_SMALL;
   b->smem_big = sizeof(EnvS<true>);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, m->device));
