@@ -121,7 +121,7 @@ struct EnvS {
   union {
     struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
     struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
-    double cscr[136];                                                                                                           // collision scratch (between the two)
+    double cscr[152];                                                                                                           // collision scratch (between the two)
   };
   double cdist[MAXC], cpos[MAXC * 3], cframe[MAXC * 9];
   int cpair[MAXC], crow[MAXC];
@@ -338,10 +338,9 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, do
   for (int k = 0; k < N; k++) {
     double bk = __shfl_sync(FULLMASK, b, N0 + k);
     double v = (mine && N0 + k <= i) ? src[ro + k] : 0.0;
+    v += (N0 + k == i) ? dadd : 0.0;      // (a separate "row[i - N0] += dadd" would index row[] dynamically => local memory)
     row[k] = rhs ? bk : v;
   }
-#pragma unroll
-  for (int k = 0; k < N; k++) if (N0 + k == i) row[k] += dadd;
   double myinv = 0.0, x = 0.0;
 #pragma unroll
   for (int j = 0; j < N; j++) {
@@ -417,7 +416,9 @@ __device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const 
 #define CS_PY 85
 #define CS_QX 101
 #define CS_QY 117
-#define CS_N 133
+#define CS_R1 133
+#define CS_R2 142
+#define CS_N 151
 
 template <class S>
 __device__ __forceinline__ void emit_contact(S& s, int idx, int pair, double dist, const double* pos, const double* nrm) {
@@ -441,25 +442,26 @@ __device__ __forceinline__ void emit_contact(S& s, int idx, int pair, double dis
   for (int k = 0; k < 3; k++) s.cpos[idx * 3 + k] = pos[k];
 }
 
-// world pose of geom g into registers (uniform across the warp)
+// world pose of geom g into the shared scratch: lanes [l0, l0+12) write the 9 matrix and 3 position entries
 template <class S>
-__device__ __forceinline__ void geom_pose(const S& s, int g, double* pos, double* mat) {
+__device__ __forceinline__ void geom_pose(S& s, int g, int lane, int l0, double* pos, double* mat) {
+  int e = lane - l0;
+  if (e < 0 || e >= 12) return;
   int b = c_m.d.geom_body[g];
   const double* gp = c_m.d.geom_pos[g];
   const double* gm = c_m.d.geom_mat[g];
-  if (b < 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) pos[k] = gp[k];
-#pragma unroll
-    for (int k = 0; k < 9; k++) mat[k] = gm[k];
+  if (e < 9) {
+    int r = e / 3, c = e % 3;
+    double v;
+    if (b < 0) v = gm[e];
+    else { const double* R = s.xmat + b * 9; v = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c]; }
+    mat[e] = v;
   } else {
-    const double* R = s.xmat + b * 9;
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      pos[r] = s.xpos[b * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
-#pragma unroll
-      for (int c = 0; c < 3; c++) mat[3 * r + c] = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c];
-    }
+    int r = e - 9;
+    double v;
+    if (b < 0) v = gp[r];
+    else { const double* R = s.xmat + b * 9; v = s.xpos[b * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+    pos[r] = v;
   }
 }
 
@@ -495,8 +497,8 @@ __device__ int plane_box_coop(S& s, int lane, int pair, int ncon, const double* 
 template <class S>
 __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1, const double* R1, const double* s1, const double* p2, const double* R2, const double* s2) {
   double* cs = s.cscr;
-  if (lane < 9) { int i = lane / 3, k = lane % 3; cs[CS_A + lane] = R1[3 * k + i]; cs[CS_B + lane] = R2[3 * k + i]; }
-  if (lane < 3) { cs[CS_P1 + lane] = p1[lane]; cs[CS_P2 + lane] = p2[lane]; cs[CS_S1 + lane] = s1[lane]; cs[CS_S2 + lane] = s2[lane]; }
+  if (lane < 9) { int i = lane / 3, k = lane % 3; cs[CS_A + lane] = R1[3 * k + i]; cs[CS_B + lane] = R2[3 * k + i]; }   // R1, R2, p1, p2 are in the scratch
+  if (lane < 3) { cs[CS_S1 + lane] = s1[lane]; cs[CS_S2 + lane] = s2[lane]; }
   __syncwarp();
   if (lane < 9) { int i = lane / 3, j = lane % 3; cs[CS_C + lane] = dot3(cs + CS_A + 3 * i, cs + CS_B + 3 * j); }
   __syncwarp();
@@ -698,9 +700,10 @@ __device__ __noinline__ void collide(S& s, int lane, int nba) {
     int p = __ffs(todo) - 1;
     todo &= todo - 1;
     int g1 = c_m.d.pair_g1[p], g2 = c_m.d.pair_g2[p];
-    double p1[3], R1[9], p2[3], R2[9];
-    geom_pose(s, g1, p1, R1);
-    geom_pose(s, g2, p2, R2);
+    double* p1 = s.cscr + CS_P1; double* p2 = s.cscr + CS_P2; double* R1 = s.cscr + CS_R1; double* R2 = s.cscr + CS_R2;
+    geom_pose(s, g1, lane, 0, p1, R1);
+    geom_pose(s, g2, lane, 12, p2, R2);
+    __syncwarp();
     if (c_m.d.geom_type[g1] == 0) ncon = plane_box_coop(s, lane, p, ncon, p1, R1, p2, R2, c_m.d.geom_size[g2]);
     else ncon = box_box_coop(s, lane, p, ncon, p1, R1, c_m.d.geom_size[g1], p2, R2, c_m.d.geom_size[g2]);
     __syncwarp();
@@ -840,14 +843,15 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     s.rmeta[r] = lane | (neg << 8) | (2 << 12) | RM_INEQ;
     s.omap[r] = 7 + u;
   }
-  // equality Jacobian rows (robot block)
-  for (int w = lane; w < 6 * NH; w += 32) {
-    int row = w / NH, j = w % NH;
-    int e = row / 3, r = row % 3;
+  // equality Jacobian rows (robot block): item = (connect e, dof j) -> its three rows
+  for (int w = lane; w < 2 * NH; w += 32) {
+    int e = w / NH, j = w % NH;
     double l1[3], l2[3], rt[3];
     jac_col(s, m, c_m.d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
     jac_col(s, m, c_m.d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
-    s.pool[row * SR + j] = l1[r] - l2[r];
+    s.pool[(3 * e) * SR + j] = l1[0] - l2[0];
+    s.pool[(3 * e + 1) * SR + j] = l1[1] - l2[1];
+    s.pool[(3 * e + 2) * SR + j] = l1[2] - l2[2];
   }
   if (lane < NH) {
     int j = lane;

@@ -13,6 +13,7 @@ import tempfile
 
 src_csv, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+col = sys.argv[5] if len(sys.argv) > 5 else "# Samples"   # e.g. stall_long_sb, stall_short_sb, stall_wait
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -60,7 +61,7 @@ per_line, per_func = {}, {}
 tot_s = tot_i = 0
 for k in range(n):
     r = data[k]
-    s = float(r[ci["# Samples"]] or 0)
+    s = float(r[ci[col]] or 0)
     ie = float(r[ci["Instructions Executed"]] or 0)
     ln = lines[k]
     a = per_line.setdefault(ln, [0.0, 0.0])
@@ -68,7 +69,7 @@ for k in range(n):
     f = per_func.setdefault(func_of(ln), [0.0, 0.0])
     f[0] += s; f[1] += ie
     tot_s += s; tot_i += ie
-print(f"total samples {tot_s:.0f}, warp instructions executed {tot_i:.3e}")
+print(f"column {col}: total {tot_s:.0f}, warp instructions executed {tot_i:.3e}")
 print("\n== by device function (samples %, instr %)")
 for f, (s, ie) in sorted(per_func.items(), key=lambda kv: -kv[1][0]):
     print(f"  {f:24s} {100 * s / tot_s:6.2f}%  {100 * ie / tot_i:6.2f}%")
