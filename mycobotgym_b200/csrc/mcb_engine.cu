@@ -79,8 +79,14 @@ struct DevModel {
   PairParam pair[MCB_MAXPAIR];
 };
 
-// the flattened model lives in constant memory: one model per process and device (a few KB, broadcast reads)
-__constant__ DevModel c_m;
+// The flattened model is staged into the CTA's shared memory (offset 0 of the dynamic segment, before the per-env
+// slices): most model tables are indexed by lane (body / dof / pair), which serialises in the constant cache and
+// misses in L1 (no L1 is left once shared memory is maxed out); from shared memory they are ordinary LDS.
+extern __shared__ __align__(16) unsigned char smem_raw[];
+#define MODEL_BYTES ((sizeof(DevModel) + 15) / 16 * 16)
+#define MDL (*reinterpret_cast<const DevModel*>(smem_raw))
+
+static_assert(sizeof(DevModel) % sizeof(double) == 0, "DevModel must be a whole number of doubles");
 
 enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_RESET = 2 };
 
@@ -180,16 +186,16 @@ __device__ __forceinline__ void quat2mat(double* m, const double* q) {
 template <class S>
 __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
   if (lane < NH) {
-    double ang = s.qpos[lane] - c_m.d.qpos0[lane];
+    double ang = s.qpos[lane] - MDL.d.qpos0[lane];
     double sn, cs;
     sincos(ang, &sn, &cs);
-    const double* ax = c_m.d.axis[lane];
+    const double* ax = MDL.d.axis[lane];
     double oc = 1.0 - cs;
     double R[9];
     R[0] = cs + oc * ax[0] * ax[0];         R[1] = oc * ax[0] * ax[1] - sn * ax[2]; R[2] = oc * ax[0] * ax[2] + sn * ax[1];
     R[3] = oc * ax[0] * ax[1] + sn * ax[2]; R[4] = cs + oc * ax[1] * ax[1];         R[5] = oc * ax[1] * ax[2] - sn * ax[0];
     R[6] = oc * ax[0] * ax[2] - sn * ax[1]; R[7] = oc * ax[1] * ax[2] + sn * ax[0]; R[8] = cs + oc * ax[2] * ax[2];
-    const double* T = c_m.d.Tmat[lane];
+    const double* T = MDL.d.Tmat[lane];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -202,12 +208,12 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
     s.xpos[CUBE * 3] = s.qpos[12]; s.xpos[CUBE * 3 + 1] = s.qpos[13]; s.xpos[CUBE * 3 + 2] = s.qpos[14];
   }
   __syncwarp();
-  for (int L = 0; L < c_m.nlevel; L++) {
-    int s0 = c_m.level_start[L], n = (c_m.level_start[L + 1] - s0) * 12;
+  for (int L = 0; L < MDL.nlevel; L++) {
+    int s0 = MDL.level_start[L], n = (MDL.level_start[L + 1] - s0) * 12;
     for (int w = lane; w < n; w += 32) {
-      int b = c_m.level_body[s0 + w / 12], e = w % 12;
+      int b = MDL.level_body[s0 + w / 12], e = w % 12;
       if (b == CUBE) continue;
-      int p = c_m.d.parent[b];
+      int p = MDL.d.parent[b];
       if (e < 9) {
         int r = e / 3, c = e % 3;
         double v;
@@ -216,7 +222,7 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
         s.xmat[b * 9 + e] = v;
       } else {
         int r = e - 9;
-        const double* t = c_m.d.Tpos[b];
+        const double* t = MDL.d.Tpos[b];
         double v;
         if (p < 0) v = t[r];
         else v = s.xpos[p * 3 + r] + s.xmat[p * 9 + 3 * r] * t[0] + s.xmat[p * 9 + 3 * r + 1] * t[1] + s.xmat[p * 9 + 3 * r + 2] * t[2];
@@ -235,7 +241,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
   if (lane < nba) {
     int b = lane;
     const double* R = s.xmat + b * 9;
-    const double* ip = c_m.d.ipos[b];
+    const double* ip = MDL.d.ipos[b];
     double com[3], off[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) com[r] = s.xpos[b * 3 + r] + R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];
@@ -244,9 +250,9 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
       for (int r = 0; r < 3; r++) { s.refcube[r] = com[r]; off[r] = 0; }
     } else {
 #pragma unroll
-      for (int r = 0; r < 3; r++) off[r] = com[r] - c_m.d.ref_robot[r];
+      for (int r = 0; r < 3; r++) off[r] = com[r] - MDL.d.ref_robot[r];
     }
-    const double* I = c_m.d.inertia[b];  // xx yy zz xy xz yz
+    const double* I = MDL.d.inertia[b];  // xx yy zz xy xz yz
     double A[9];                         // A = R * Ib
 #pragma unroll
     for (int r = 0; r < 3; r++) {
@@ -254,7 +260,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
       A[3 * r + 1] = R[3 * r] * I[3] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[5];
       A[3 * r + 2] = R[3 * r] * I[4] + R[3 * r + 1] * I[5] + R[3 * r + 2] * I[2];
     }
-    double mass = c_m.d.mass[b];
+    double mass = MDL.d.mass[b];
     double* ci = s.cinert + b * 10;
     ci[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2] + mass * (off[1] * off[1] + off[2] * off[2]);
     ci[1] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5] + mass * (off[0] * off[0] + off[2] * off[2]);
@@ -269,10 +275,10 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
     double* cd = s.cdof + j * 6;
     if (j < NH) {
       const double* R = s.xmat + j * 9;  // hinge j belongs to body j
-      const double* a = c_m.d.axis[j];
+      const double* a = MDL.d.axis[j];
       double ax[3], off[3];
 #pragma unroll
-      for (int r = 0; r < 3; r++) { ax[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; off[r] = c_m.d.ref_robot[r] - s.xpos[j * 3 + r]; }
+      for (int r = 0; r < 3; r++) { ax[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; off[r] = MDL.d.ref_robot[r] - s.xpos[j * 3 + r]; }
       cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
       cross3(cd + 3, ax, off);
     } else {
@@ -281,7 +287,7 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
         cd[0] = cd[1] = cd[2] = 0; cd[3] = (k == 0); cd[4] = (k == 1); cd[5] = (k == 2);
       } else {
         const double* R = s.xmat + CUBE * 9;
-        const double* ip = c_m.d.ipos[CUBE];
+        const double* ip = MDL.d.ipos[CUBE];
         double ax[3] = {R[k - 3], R[k], R[k + 3]}, off[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) off[r] = R[3 * r] * ip[0] + R[3 * r + 1] * ip[1] + R[3 * r + 2] * ip[2];  // refcube - xpos
@@ -300,22 +306,22 @@ template <class S>
 __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   for (int w = lane; w < nba * 10; w += 32) {
     int b = w / 10, k = w % 10;
-    int e = b + c_m.d.subtree_size[b];
+    int e = b + MDL.d.subtree_size[b];
     if (e > nba) e = nba;
     double acc = s.cinert[w];
     for (int c = b + 1; c < e; c++) acc += s.cinert[c * 10 + k];
     s.crb[w] = acc;
   }
   __syncwarp();
-  if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + c_m.d.dof_body[lane] * 10, s.cdof + lane * 6);
+  if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + MDL.d.dof_body[lane] * 10, s.cdof + lane * 6);
   __syncwarp();
-  for (int e = lane; e < c_m.nmnz; e += 32) {
-    int i = c_m.mnz_i[e], j = c_m.mnz_j[e];
+  for (int e = lane; e < MDL.nmnz; e += 32) {
+    int i = MDL.mnz_i[e], j = MDL.mnz_j[e];
     if (i >= nva) continue;
     const double* a = s.cdof + j * 6;
     const double* b = s.buf + i * 6;
     double v = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
-    if (i == j) v += c_m.d.armature[i];
+    if (i == j) v += MDL.d.armature[i];
     s.M[TRI(i, j)] = v;
   }
   __syncwarp();
@@ -447,9 +453,9 @@ template <class S>
 __device__ __forceinline__ void geom_pose(S& s, int g, int lane, int l0, double* pos, double* mat) {
   int e = lane - l0;
   if (e < 0 || e >= 12) return;
-  int b = c_m.d.geom_body[g];
-  const double* gp = c_m.d.geom_pos[g];
-  const double* gm = c_m.d.geom_mat[g];
+  int b = MDL.d.geom_body[g];
+  const double* gp = MDL.d.geom_pos[g];
+  const double* gm = MDL.d.geom_mat[g];
   if (e < 9) {
     int r = e / 3, c = e % 3;
     double v;
@@ -670,26 +676,26 @@ template <class S>
 __device__ __noinline__ void collide(S& s, int lane, int nba) {
   // broad phase: lane = candidate pair
   bool near = false;
-  if (lane < c_m.d.npair) {
-    int g1 = c_m.d.pair_g1[lane], g2 = c_m.d.pair_g2[lane];
-    int b1 = c_m.d.geom_body[g1], b2 = c_m.d.geom_body[g2];
+  if (lane < MDL.d.npair) {
+    int g1 = MDL.d.pair_g1[lane], g2 = MDL.d.pair_g2[lane];
+    int b1 = MDL.d.geom_body[g1], b2 = MDL.d.geom_body[g2];
     if (!((nba <= CUBE) && (b1 == CUBE || b2 == CUBE))) {
       double p1[3], p2[3];
       {
-        const double* gp = c_m.d.geom_pos[g1];
+        const double* gp = MDL.d.geom_pos[g1];
         if (b1 < 0) { p1[0] = gp[0]; p1[1] = gp[1]; p1[2] = gp[2]; }
         else { const double* R = s.xmat + b1 * 9; for (int r = 0; r < 3; r++) p1[r] = s.xpos[b1 * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
-        gp = c_m.d.geom_pos[g2];
+        gp = MDL.d.geom_pos[g2];
         if (b2 < 0) { p2[0] = gp[0]; p2[1] = gp[1]; p2[2] = gp[2]; }
         else { const double* R = s.xmat + b2 * 9; for (int r = 0; r < 3; r++) p2[r] = s.xpos[b2 * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
       }
       double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-      if (c_m.d.geom_type[g1] == 0) {
-        const double* gm = c_m.d.geom_mat[g1];    // planes are static in this model
+      if (MDL.d.geom_type[g1] == 0) {
+        const double* gm = MDL.d.geom_mat[g1];    // planes are static in this model
         double nrm[3] = {gm[2], gm[5], gm[8]};
-        near = dot3(dif, nrm) <= c_m.d.geom_rbound[g2];
+        near = dot3(dif, nrm) <= MDL.d.geom_rbound[g2];
       } else {
-        double bound = c_m.d.geom_rbound[g1] + c_m.d.geom_rbound[g2];
+        double bound = MDL.d.geom_rbound[g1] + MDL.d.geom_rbound[g2];
         near = dot3(dif, dif) <= bound * bound;
       }
     }
@@ -699,13 +705,13 @@ __device__ __noinline__ void collide(S& s, int lane, int nba) {
   while (todo) {
     int p = __ffs(todo) - 1;
     todo &= todo - 1;
-    int g1 = c_m.d.pair_g1[p], g2 = c_m.d.pair_g2[p];
+    int g1 = MDL.d.pair_g1[p], g2 = MDL.d.pair_g2[p];
     double* p1 = s.cscr + CS_P1; double* p2 = s.cscr + CS_P2; double* R1 = s.cscr + CS_R1; double* R2 = s.cscr + CS_R2;
     geom_pose(s, g1, lane, 0, p1, R1);
     geom_pose(s, g2, lane, 12, p2, R2);
     __syncwarp();
-    if (c_m.d.geom_type[g1] == 0) ncon = plane_box_coop(s, lane, p, ncon, p1, R1, p2, R2, c_m.d.geom_size[g2]);
-    else ncon = box_box_coop(s, lane, p, ncon, p1, R1, c_m.d.geom_size[g1], p2, R2, c_m.d.geom_size[g2]);
+    if (MDL.d.geom_type[g1] == 0) ncon = plane_box_coop(s, lane, p, ncon, p1, R1, p2, R2, MDL.d.geom_size[g2]);
+    else ncon = box_box_coop(s, lane, p, ncon, p1, R1, MDL.d.geom_size[g1], p2, R2, MDL.d.geom_size[g2]);
     __syncwarp();
   }
   if (lane == 0) {
@@ -734,11 +740,11 @@ __device__ double impedance(const double* solimp_in, double pos) {
 // point Jacobian column of dof j for a world point attached to body b (0 if j does not move b)
 template <class S>
 __device__ __forceinline__ void jac_col(const S& s, const DevModel* __restrict__ m, int b, int j, const double* pt, double* lin, double* rot) {
-  if (b >= 0 && ((c_m.d.ancmask[b] >> j) & 1u)) {
+  if (b >= 0 && ((MDL.d.ancmask[b] >> j) & 1u)) {
     const double* cd = s.cdof + j * 6;
     double off[3];
     if (b == CUBE) { off[0] = pt[0] - s.refcube[0]; off[1] = pt[1] - s.refcube[1]; off[2] = pt[2] - s.refcube[2]; }
-    else { off[0] = pt[0] - c_m.d.ref_robot[0]; off[1] = pt[1] - c_m.d.ref_robot[1]; off[2] = pt[2] - c_m.d.ref_robot[2]; }
+    else { off[0] = pt[0] - MDL.d.ref_robot[0]; off[1] = pt[1] - MDL.d.ref_robot[1]; off[2] = pt[2] - MDL.d.ref_robot[2]; }
     double t[3];
     cross3(t, cd, off);
     lin[0] = cd[3] + t[0]; lin[1] = cd[4] + t[1]; lin[2] = cd[5] + t[2];
@@ -783,21 +789,21 @@ __device__ __forceinline__ double row_dot(S& s, int r, const double* v) {
 // and the reference acceleration of every row.  Returns false if the layout's capacity is exceeded.
 template <class S>
 __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
-  const double h = c_m.d.timestep;
+  const double h = MDL.d.timestep;
   // connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1)
   if (lane < 4) {
     int e = lane >> 1, side = lane & 1;
-    int b = side ? c_m.d.con_body2[e] : c_m.d.con_body1[e];
-    const double* a = side ? c_m.d.con_anchor2[e] : c_m.d.con_anchor1[e];
+    int b = side ? MDL.d.con_body2[e] : MDL.d.con_body1[e];
+    const double* a = side ? MDL.d.con_anchor2[e] : MDL.d.con_anchor1[e];
     const double* R = s.xmat + b * 9;
     for (int r = 0; r < 3; r++) s.anchors[lane * 3 + r] = s.xpos[b * 3 + r] + R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
   }
   // limits: lane j < 12, lower then upper (both can not be active for a positive-width range)
   int lim = 0, neg = 0;
-  if (lane < NH && c_m.d.jnt_limited[lane]) {
+  if (lane < NH && MDL.d.jnt_limited[lane]) {
     double v = s.qpos[lane];
-    if (v - c_m.d.jnt_range[lane][0] < 0) lim = 1;
-    else if (c_m.d.jnt_range[lane][1] - v < 0) { lim = 1; neg = 1; }
+    if (v - MDL.d.jnt_range[lane][0] < 0) lim = 1;
+    else if (MDL.d.jnt_range[lane][1] - v < 0) { lim = 1; neg = 1; }
   }
   unsigned bal = __ballot_sync(FULLMASK, lim);
   const int nU = __popc(bal);
@@ -805,7 +811,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   if (lane == 0) {
     int nRc = 0, nC = 0, nF = 0, nc = s.ncon;
     for (int c = 0; c < nc; c++) {
-      const PairParam& pp = c_m.pair[s.cpair[c]];
+      const PairParam& pp = MDL.pair[s.cpair[c]];
       int rows = 2 * (pp.dim - 1);
       if (pp.ptype == 0) nRc += rows; else if (pp.ptype == 1) nC += rows; else nF += rows;
     }
@@ -816,7 +822,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       s.overflow += 1;
       while (nc > 0 && !fits) {
         nc--;
-        const PairParam& pp = c_m.pair[s.cpair[nc]];
+        const PairParam& pp = MDL.pair[s.cpair[nc]];
         int rows = 2 * (pp.dim - 1);
         if (pp.ptype == 0) { nRc -= rows; nR -= rows; } else if (pp.ptype == 1) nC -= rows; else nF -= rows;
         fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
@@ -825,7 +831,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     }
     int r0 = 7, r1 = nR, r2 = nR + nC, orow = 7 + nU;
     for (int c = 0; c < nc; c++) {
-      const PairParam& pp = c_m.pair[s.cpair[c]];
+      const PairParam& pp = MDL.pair[s.cpair[c]];
       int rows = 2 * (pp.dim - 1), base;
       if (pp.ptype == 0) { base = r0; r0 += rows; } else if (pp.ptype == 1) { base = r1; r1 += rows; } else { base = r2; r2 += rows; }
       s.crow[c] = base;
@@ -847,8 +853,8 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   for (int w = lane; w < 2 * NH; w += 32) {
     int e = w / NH, j = w % NH;
     double l1[3], l2[3], rt[3];
-    jac_col(s, m, c_m.d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
-    jac_col(s, m, c_m.d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
+    jac_col(s, m, MDL.d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
+    jac_col(s, m, MDL.d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
     s.pool[(3 * e) * SR + j] = l1[0] - l2[0];
     s.pool[(3 * e + 1) * SR + j] = l1[1] - l2[1];
     s.pool[(3 * e + 2) * SR + j] = l1[2] - l2[2];
@@ -856,10 +862,10 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   if (lane < NH) {
     int j = lane;
     double v = 0;
-    if (j == c_m.d.jeq_dof1) v = 1;
-    if (j == c_m.d.jeq_dof2) {
-      double dif = s.qpos[j] - c_m.d.qpos0[j];
-      const double* pc = c_m.d.jeq_polycoef;
+    if (j == MDL.d.jeq_dof1) v = 1;
+    if (j == MDL.d.jeq_dof2) {
+      double dif = s.qpos[j] - MDL.d.qpos0[j];
+      const double* pc = MDL.d.jeq_polycoef;
       v = -(pc[1] + 2 * pc[2] * dif + 3 * pc[3] * dif * dif + 4 * pc[4] * dif * dif * dif);
     }
     s.pool[6 * SR + j] = v;
@@ -868,10 +874,10 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   const int ncon = s.ncon;
   for (int w = lane; w < ncon * NV; w += 32) {
     int c = w / NV, j = w % NV;
-    const PairParam& pp = c_m.pair[s.cpair[c]];
+    const PairParam& pp = MDL.pair[s.cpair[c]];
     if (pp.ptype == 0 && j >= NH) continue;
     if (pp.ptype == 1 && j < NH) continue;
-    int b1 = c_m.d.geom_body[pp.g1], b2 = c_m.d.geom_body[pp.g2];
+    int b1 = MDL.d.geom_body[pp.g1], b2 = MDL.d.geom_body[pp.g2];
     const double* pt = s.cpos + c * 3;
     const double* f = s.cframe + c * 9;
     double l1[3], r1[3], l2[3], r2[3];
@@ -904,24 +910,24 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     double pos, diag, pyr = 0;
     if (kind == 0) {
       pos = s.anchors[(2 * idx) * 3 + sub] - s.anchors[(2 * idx + 1) * 3 + sub];
-      solref = c_m.d.con_solref[idx]; solimp = c_m.d.con_solimp[idx]; diag = c_m.d.con_diag[idx];
+      solref = MDL.d.con_solref[idx]; solimp = MDL.d.con_solimp[idx]; diag = MDL.d.con_diag[idx];
     } else if (kind == 1) {
-      int d1 = c_m.d.jeq_dof1, d2 = c_m.d.jeq_dof2;
-      double p1 = s.qpos[d1] - c_m.d.qpos0[d1], dif = s.qpos[d2] - c_m.d.qpos0[d2];
-      const double* pc = c_m.d.jeq_polycoef;
+      int d1 = MDL.d.jeq_dof1, d2 = MDL.d.jeq_dof2;
+      double p1 = s.qpos[d1] - MDL.d.qpos0[d1], dif = s.qpos[d2] - MDL.d.qpos0[d2];
+      const double* pc = MDL.d.jeq_polycoef;
       pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
-      solref = c_m.d.jeq_solref; solimp = c_m.d.jeq_solimp; diag = c_m.d.jeq_diag;
+      solref = MDL.d.jeq_solref; solimp = MDL.d.jeq_solimp; diag = MDL.d.jeq_diag;
     } else if (kind == 2) {
       double v = s.qpos[idx];
-      pos = (meta & 0x100) ? c_m.d.jnt_range[idx][1] - v : v - c_m.d.jnt_range[idx][0];
-      solref = c_m.d.jnt_solref[idx]; solimp = c_m.d.jnt_solimp[idx]; diag = c_m.d.dof_invweight0[idx];
+      pos = (meta & 0x100) ? MDL.d.jnt_range[idx][1] - v : v - MDL.d.jnt_range[idx][0];
+      solref = MDL.d.jnt_solref[idx]; solimp = MDL.d.jnt_solimp[idx]; diag = MDL.d.dof_invweight0[idx];
     } else {
-      const PairParam& pp = c_m.pair[s.cpair[idx]];
+      const PairParam& pp = MDL.pair[s.cpair[idx]];
       double mu = pp.friction[0];
       pos = s.cdist[idx];
       solref = pp.solref; solimp = pp.solimp;
       diag = pp.tran + mu * mu * pp.tran;     // the pyramid's first-row diagApprox; all rows share R = 2 mu^2 R_first
-      pyr = mu / sqrt(c_m.d.impratio);
+      pyr = mu / sqrt(MDL.d.impratio);
     }
     double sr0 = solref[0], sr1 = solref[1];
     if (sr0 > 0) sr0 = fmax(sr0, 2 * h);
@@ -945,7 +951,7 @@ template <class S>
 __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    unsigned mask = c_m.d.ancmask[b];
+    unsigned mask = MDL.d.ancmask[b];
     double acc = 0;
     while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j]; }
     s.cvel[w] = acc;
@@ -955,7 +961,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
     int j = lane;
     double vel[6];
     if (j < NH) {
-      int p = c_m.d.parent[j];
+      int p = MDL.d.parent[j];
       for (int c = 0; c < 6; c++) vel[c] = (p >= 0 ? s.cvel[p * 6 + c] : 0.0);
       cross_motion(s.cdof_dot + j * 6, vel, s.cdof + j * 6);
     } else if (j < 15) {
@@ -969,8 +975,8 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    unsigned mask = c_m.d.ancmask[b];
-    double acc = (c >= 3 ? -c_m.d.gravity[c - 3] : 0.0);
+    unsigned mask = MDL.d.ancmask[b];
+    double acc = (c >= 3 ? -MDL.d.gravity[c - 3] : 0.0);
     while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j]; }
     s.cacc[w] = acc;
   }
@@ -988,7 +994,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
-    int e = b + c_m.d.subtree_size[b];
+    int e = b + MDL.d.subtree_size[b];
     if (e > nba) e = nba;
     double acc = 0;
     for (int k = e - 1; k >= b; k--) acc += s.cacc[k * 6 + c];
@@ -997,7 +1003,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   if (lane < nva) {
     const double* a = s.cdof + lane * 6;
-    const double* b = s.cvel + c_m.d.dof_body[lane] * 6;
+    const double* b = s.cvel + MDL.d.dof_body[lane] * 6;
     s.qfrc_bias[lane] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
   }
   __syncwarp();
@@ -1008,22 +1014,22 @@ template <class S>
 __device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   double force = 0;
   if (lane < NU) {
-    const double* mom = c_m.d.act_moment[lane];
+    const double* mom = MDL.d.act_moment[lane];
     double len = 0, vel = 0;
     for (int i = 0; i < NH; i++) { double c = mom[i]; if (c != 0) { len += c * s.qpos[i]; vel += c * s.qvel[i]; } }
     double ctrl = s.ctrl[lane];
-    if (c_m.d.act_ctrllimited[lane]) ctrl = fmax(c_m.d.act_ctrlrange[lane][0], fmin(c_m.d.act_ctrlrange[lane][1], ctrl));
-    const double* bp = c_m.d.act_bias[lane];
-    force = c_m.d.act_gain[lane] * ctrl + bp[0] + bp[1] * len + bp[2] * vel;
-    if (c_m.d.act_forcelimited[lane]) force = fmax(c_m.d.act_forcerange[lane][0], fmin(c_m.d.act_forcerange[lane][1], force));
+    if (MDL.d.act_ctrllimited[lane]) ctrl = fmax(MDL.d.act_ctrlrange[lane][0], fmin(MDL.d.act_ctrlrange[lane][1], ctrl));
+    const double* bp = MDL.d.act_bias[lane];
+    force = MDL.d.act_gain[lane] * ctrl + bp[0] + bp[1] * len + bp[2] * vel;
+    if (MDL.d.act_forcelimited[lane]) force = fmax(MDL.d.act_forcerange[lane][0], fmin(MDL.d.act_forcerange[lane][1], force));
   }
   double qa = 0;
 #pragma unroll
   for (int a = 0; a < NU; a++) {
     double fa = __shfl_sync(FULLMASK, force, a);
-    if (lane < NV) qa += c_m.d.act_moment[a][lane] * fa;
+    if (lane < NV) qa += MDL.d.act_moment[a][lane] * fa;
   }
-  if (lane < nva) s.qfrc_smooth[lane] = -c_m.d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
+  if (lane < nva) s.qfrc_smooth[lane] = -MDL.d.damping[lane] * s.qvel[lane] - s.qfrc_bias[lane] + qa;
   __syncwarp();
 }
 
@@ -1162,7 +1168,7 @@ struct Newton {
     if (lane < nva) sn = s.search[lane] * s.search[lane];
     double snorm = sqrt(warp_sum(sn));
     if (snorm < MINVAL) return 0;
-    double gtol = c_m.d.tolerance * c_m.d.ls_tolerance * snorm / scale;
+    double gtol = MDL.d.tolerance * MDL.d.ls_tolerance * snorm / scale;
     double mv = mulM_row(s, lane, nva, s.search);
     if (lane < nva) s.Mv[lane] = mv;
     rows_times(s.search, s.eJv, false);
@@ -1178,7 +1184,7 @@ struct Newton {
         qa[t] = 0.5 * D * ja * ja; qb[t] = D * ja * jv; qc[t] = 0.5 * D * jv * jv;
       } else { qa[t] = qb[t] = qc[t] = 0; }
     }
-    const int lsmax = c_m.d.ls_iterations;
+    const int lsmax = MDL.d.ls_iterations;
     Pt p0, p1, p2, pmid, p1n, p2n;
     p0.alpha = 0; ls_eval(p0);
     p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(p1);
@@ -1218,7 +1224,7 @@ struct Newton {
   }
 
   __device__ void solve() {
-    const double scale = 1.0 / (c_m.d.meaninertia * (double)NV);
+    const double scale = 1.0 / (MDL.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
     rows_times(s.warm, s.eJaref, true);
@@ -1240,7 +1246,7 @@ struct Newton {
     update_cost_grad();
     newton_direction();
     int iter = 0;
-    const int maxiter = c_m.d.iterations;
+    const int maxiter = MDL.d.iterations;
     while (iter < maxiter) {
       double alpha = line_search(scale);
       if (alpha == 0) break;
@@ -1253,7 +1259,7 @@ struct Newton {
       double gn = 0;
       if (lane < nva) gn = s.grad[lane] * s.grad[lane];
       double improvement = scale * (oldcost - cost), gradient = scale * sqrt(warp_sum(gn));
-      if (improvement < c_m.d.tolerance || gradient < c_m.d.tolerance) break;
+      if (improvement < MDL.d.tolerance || gradient < MDL.d.tolerance) break;
       newton_direction();
     }
     if (lane == 0) s.iters += iter;
@@ -1296,8 +1302,8 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
 // euler(): (M + h*diag(damping))^-1 (qfrc_smooth + qfrc_constraint), semi-implicit advance.
 template <class S>
 __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
-  const double h = c_m.d.timestep;
-  double qacc = factor_solve_M(s.M, s.H, lane < nva ? h * c_m.d.damping[lane] : 0.0, lane, nva,
+  const double h = MDL.d.timestep;
+  double qacc = factor_solve_M(s.M, s.H, lane < nva ? h * MDL.d.damping[lane] : 0.0, lane, nva,
                                lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
   if (lane < nva) s.qvel[lane] += h * qacc;
   __syncwarp();
@@ -1342,7 +1348,7 @@ __device__ double philox_uniform(uint64_t seed, uint32_t env, unsigned long long
 __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& cfg, uint64_t seed, uint32_t env, unsigned long long& ctr, double* g) {
   g[0] = -0.12 + (0.12 - (-0.12)) * philox_uniform(seed, env, ctr);
   g[1] = -0.06 + (0.06 - (-0.06)) * philox_uniform(seed, env, ctr);
-  g[2] = c_m.d.height_offset;
+  g[2] = MDL.d.height_offset;
   if (cfg.target_in_the_air) {
     if (philox_uniform(seed, env, ctr) < 0.5) g[2] += 0.0 + (0.1 - 0.0) * philox_uniform(seed, env, ctr);
   }
@@ -1352,15 +1358,15 @@ __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& 
 // substep after a step, fresh after forward), qpos / qvel current.
 template <class S>
 __device__ __noinline__ void write_obs(S& s, const DevModel* __restrict__ m, const mcb_task_cfg& cfg, int lane, int env, double* obs, double* ag, double* dg, double* ag_out3) {
-  const double dt = cfg.frame_skip * c_m.d.timestep;
-  int eb = c_m.d.eef_body;
+  const double dt = cfg.frame_skip * MDL.d.timestep;
+  int eb = MDL.d.eef_body;
   const double* R = s.xmat + eb * 9;
-  const double* ep = c_m.d.eef_pos;
+  const double* ep = MDL.d.eef_pos;
   double grip[3], gvel[3] = {0, 0, 0};
   for (int r = 0; r < 3; r++) grip[r] = s.xpos[eb * 3 + r] + R[3 * r] * ep[0] + R[3 * r + 1] * ep[1] + R[3 * r + 2] * ep[2];
   {
-    unsigned mask = c_m.d.ancmask[eb];
-    double off[3] = {grip[0] - c_m.d.ref_robot[0], grip[1] - c_m.d.ref_robot[1], grip[2] - c_m.d.ref_robot[2]};
+    unsigned mask = MDL.d.ancmask[eb];
+    double off[3] = {grip[0] - MDL.d.ref_robot[0], grip[1] - MDL.d.ref_robot[1], grip[2] - MDL.d.ref_robot[2]};
     while (mask) {
       int j = __ffs(mask) - 1; mask &= mask - 1;
       const double* cd = s.cdof + j * 6;
@@ -1448,20 +1454,20 @@ __device__ void store_state(const S& s, double* __restrict__ st, int lane) {
 // reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.  false: layout overflow.
 template <class S>
 __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
-  for (int w = lane; w < NQ; w += 32) s.qpos[w] = c_m.d.init_qpos[w];
+  for (int w = lane; w < NQ; w += 32) s.qpos[w] = MDL.d.init_qpos[w];
   if (lane < NV) s.qvel[lane] = 0;
-  if (lane < NU) s.ctrl[lane] = c_m.d.init_ctrl[lane];
+  if (lane < NU) s.ctrl[lane] = MDL.d.init_ctrl[lane];
   __syncwarp();
   if (!forward(s, m, lane, nba, nva, false)) return false;
-  double oxy[2] = {c_m.d.initial_gripper_xpos[0], c_m.d.initial_gripper_xpos[1]};
+  double oxy[2] = {MDL.d.initial_gripper_xpos[0], MDL.d.initial_gripper_xpos[1]};
   double g[3];
   if (lane == 0) {
     if (a.cfg.has_object) {
       if (a.inj_xy) { oxy[0] = a.inj_xy[(size_t)env * 2]; oxy[1] = a.inj_xy[(size_t)env * 2 + 1]; }
       else {
         int guard = 0;
-        while (sqrt((oxy[0] - c_m.d.initial_gripper_xpos[0]) * (oxy[0] - c_m.d.initial_gripper_xpos[0]) +
-                    (oxy[1] - c_m.d.initial_gripper_xpos[1]) * (oxy[1] - c_m.d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
+        while (sqrt((oxy[0] - MDL.d.initial_gripper_xpos[0]) * (oxy[0] - MDL.d.initial_gripper_xpos[0]) +
+                    (oxy[1] - MDL.d.initial_gripper_xpos[1]) * (oxy[1] - MDL.d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
           sample_goal(m, a.cfg, a.seed, env, ctr, g);
           oxy[0] = g[0]; oxy[1] = g[1];
         }
@@ -1524,12 +1530,17 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 #define WPB_SMALL 16
 template <bool BIG>
 __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef EnvS<BIG> S;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpb = BIG ? 1 : WPB_SMALL;
-  S& s = *reinterpret_cast<S*>(smem_raw + (size_t)wid * sizeof(S));
+  S& s = *reinterpret_cast<S*>(smem_raw + MODEL_BYTES + (size_t)wid * sizeof(S));
   const DevModel* __restrict__ m = a.m;
+  {  // stage the model (global -> shared), once per CTA
+    const double* src = reinterpret_cast<const double*>(a.m);
+    double* dst = reinterpret_cast<double*>(smem_raw);
+    for (int w = threadIdx.x; w < (int)(sizeof(DevModel) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
+    __syncthreads();
+  }
   const mcb_task_cfg& cfg = a.cfg;
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
@@ -1657,8 +1668,8 @@ __global__ void init_state_kernel(double* state, int* elapsed, double* ep_return
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
   for (int k = 0; k < MCB_STATE_STRIDE; k++) st[k] = 0;
-  for (int k = 0; k < NQ; k++) st[k] = c_m.d.init_qpos[k];
-  for (int k = 0; k < NU; k++) st[37 + k] = c_m.d.init_ctrl[k];
+  for (int k = 0; k < NQ; k++) st[k] = m->d.init_qpos[k];
+  for (int k = 0; k < NU; k++) st[37 + k] = m->d.init_ctrl[k];
   elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
 }
 
@@ -1810,7 +1821,6 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   }
   CK(cudaMalloc(&m->dev, sizeof(DevModel)));
   CK(cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
-  CK(cudaMemcpyToSymbol(c_m, &h, sizeof(DevModel)));
   *out = m;
   return 0;
 }
@@ -1832,8 +1842,8 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   b->obs_dim = cfg->has_object ? MCB_OBS_OBJECT : MCB_OBS_REACH;
   if (cfg->nefc_max != 0 && cfg->nefc_max != 48 && cfg->nefc_max != 128) { delete b; return fail("mcb_batch_create: nefc_max must be 0 (two-tier), 48 or 128"); }
   b->big_only = cfg->nefc_max == 128;
-  b->smem_small = sizeof(EnvS<false>) * WPB_SMALL;
-  b->smem_big = sizeof(EnvS<true>);
+  b->smem_small = MODEL_BYTES + sizeof(EnvS<false>) * WPB_SMALL;
+  b->smem_big = MODEL_BYTES + sizeof(EnvS<true>);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, m->device));
   b->big_grid = prop.multiProcessorCount * 4;
