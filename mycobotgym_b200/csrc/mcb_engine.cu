@@ -76,6 +76,7 @@ struct DevModel {
   int level_body[NB];
   int nmnz;
   unsigned char mnz_i[NMNZ_MAX], mnz_j[NMNZ_MAX];
+  unsigned char tri_i[176], tri_j[176];   // packed lower-triangle index e -> (row, column)
   PairParam pair[MCB_MAXPAIR];
 };
 
@@ -390,16 +391,24 @@ __device__ __forceinline__ double factor_solve_M(const double* M, double* dst, d
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
 template <class S>
 __device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const double* v) {
-  double acc = 0;
+  double acc = 0, a1 = 0, a2 = 0;
   const int ro = lane * (lane + 1) / 2;
   if (lane < NH) {
 #pragma unroll
-    for (int j = 0; j < NH; j++) acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+    for (int j = 0; j < NH; j += 3) {
+      acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+      a1 += s.M[j + 1 <= lane ? ro + j + 1 : TRI(j + 1, 0) + lane] * v[j + 1];
+      a2 += s.M[j + 2 <= lane ? ro + j + 2 : TRI(j + 2, 0) + lane] * v[j + 2];
+    }
   } else if (lane < nva) {
 #pragma unroll
-    for (int j = NH; j < NV; j++) acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+    for (int j = NH; j < NV; j += 3) {
+      acc += s.M[j <= lane ? ro + j : TRI(j, 0) + lane] * v[j];
+      a1 += s.M[j + 1 <= lane ? ro + j + 1 : TRI(j + 1, 0) + lane] * v[j + 1];
+      a2 += s.M[j + 2 <= lane ? ro + j + 2 : TRI(j + 2, 0) + lane] * v[j + 2];
+    }
   }
-  return acc;
+  return acc + a1 + a2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -767,16 +776,22 @@ __device__ __forceinline__ double row_dot(S& s, int r, const double* v) {
   double acc = 0;
   if (r < s.nR) {
     const double* p = row_r(s, r);
+    double a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-    for (int k = 0; k < NH; k++) acc += p[k] * v[k];
+    for (int k = 0; k < NH; k += 4) { acc += p[k] * v[k]; a1 += p[k + 1] * v[k + 1]; a2 += p[k + 2] * v[k + 2]; a3 += p[k + 3] * v[k + 3]; }
+    acc = (acc + a1) + (a2 + a3);
   } else if (r < s.nR + s.nC) {
     const double* p = row_c(s, r);
+    double a1 = 0, a2 = 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) acc += p[k] * v[NH + k];
+    for (int k = 0; k < 6; k += 3) { acc += p[k] * v[NH + k]; a1 += p[k + 1] * v[NH + k + 1]; a2 += p[k + 2] * v[NH + k + 2]; }
+    acc = acc + a1 + a2;
   } else if (r < s.nR + s.nC + s.nF) {
     const double* p = row_f(s, r);
+    double a1 = 0, a2 = 0;
 #pragma unroll
-    for (int k = 0; k < NV; k++) acc += p[k] * v[k];
+    for (int k = 0; k < NV; k += 3) { acc += p[k] * v[k]; a1 += p[k + 1] * v[k + 1]; a2 += p[k + 2] * v[k + 2]; }
+    acc = acc + a1 + a2;
   } else {
     int meta = s.rmeta[r];
     double x = v[meta & 0xff];
@@ -952,9 +967,12 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
     unsigned mask = MDL.d.ancmask[b];
-    double acc = 0;
-    while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j]; }
-    s.cvel[w] = acc;
+    double acc = 0, ac2 = 0;
+    while (mask) {
+      int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j];
+      if (mask) { int j2 = __ffs(mask) - 1; mask &= mask - 1; ac2 += s.cdof[j2 * 6 + c] * s.qvel[j2]; }
+    }
+    s.cvel[w] = acc + ac2;
   }
   __syncwarp();
   if (lane < nva) {
@@ -976,9 +994,12 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   for (int w = lane; w < nba * 6; w += 32) {
     int b = w / 6, c = w % 6;
     unsigned mask = MDL.d.ancmask[b];
-    double acc = (c >= 3 ? -MDL.d.gravity[c - 3] : 0.0);
-    while (mask) { int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j]; }
-    s.cacc[w] = acc;
+    double acc = (c >= 3 ? -MDL.d.gravity[c - 3] : 0.0), ac2 = 0;
+    while (mask) {
+      int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j];
+      if (mask) { int j2 = __ffs(mask) - 1; mask &= mask - 1; ac2 += s.cdof_dot[j2 * 6 + c] * s.qvel[j2]; }
+    }
+    s.cacc[w] = acc + ac2;
   }
   __syncwarp();
   double f[6];
@@ -1074,8 +1095,19 @@ struct Newton {
     if (lane < nva) {
       double q = 0;
       const int nR = s.nR, nC = s.nC, nF = s.nF, nU = s.nU;
-      if (lane < NH) { for (int r = 0; r < nR; r++) q += s.pool[r * SR + lane] * s.eJv[r]; }
-      else { const double* p = s.pool + nR * SR + (lane - NH); for (int r = 0; r < nC; r++) q += p[r * SC] * s.eJv[nR + r]; }
+      double q1 = 0, q2 = 0, q3 = 0;
+      if (lane < NH) {
+        int r = 0;
+        for (; r + 3 < nR; r += 4) { q += s.pool[r * SR + lane] * s.eJv[r]; q1 += s.pool[(r + 1) * SR + lane] * s.eJv[r + 1]; q2 += s.pool[(r + 2) * SR + lane] * s.eJv[r + 2]; q3 += s.pool[(r + 3) * SR + lane] * s.eJv[r + 3]; }
+        for (; r < nR; r++) q += s.pool[r * SR + lane] * s.eJv[r];
+      } else {
+        const double* p = s.pool + nR * SR + (lane - NH);
+        const double* f = s.eJv + nR;
+        int r = 0;
+        for (; r + 3 < nC; r += 4) { q += p[r * SC] * f[r]; q1 += p[(r + 1) * SC] * f[r + 1]; q2 += p[(r + 2) * SC] * f[r + 2]; q3 += p[(r + 3) * SC] * f[r + 3]; }
+        for (; r < nC; r++) q += p[r * SC] * f[r];
+      }
+      q = (q + q1) + (q2 + q3);
       { const double* p = s.pool + nR * SR + nC * SC + lane; for (int r = 0; r < nF; r++) q += p[r * SF] * s.eJv[nR + nC + r]; }
       for (int u = 0; u < nU; u++) {
         int r = nR + nC + nF + u, meta = s.rmeta[r];
@@ -1091,13 +1123,8 @@ struct Newton {
     const int nR = s.nR, nC = s.nC, nF = s.nF, nU = s.nU;
     int ri[3], rj[3];      // robot-robot entries e = lane + 32 p < 78
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
-      int e = lane + 32 * p, i = 0;
-      while ((i + 1) * (i + 2) / 2 <= e) i++;
-      ri[p] = i; rj[p] = e - i * (i + 1) / 2;
-    }
-    int ci = 0, cj = 0;    // cube-cube entry t = lane < 21
-    { int i = 0; while ((i + 1) * (i + 2) / 2 <= lane) i++; ci = i; cj = lane - i * (i + 1) / 2; }
+    for (int p = 0; p < 3; p++) { int e = lane + 32 * p; ri[p] = MDL.tri_i[e]; rj[p] = MDL.tri_j[e]; }
+    const int ci = MDL.tri_i[lane], cj = MDL.tri_j[lane];    // cube-cube entry t = lane < 21
     double arr[3], acc_cc = 0, arc[3] = {0, 0, 0};
 #pragma unroll
     for (int p = 0; p < 3; p++) arr[p] = (lane + 32 * p < 78) ? s.M[lane + 32 * p] : 0.0;
@@ -1110,11 +1137,13 @@ struct Newton {
       for (int q = 0; q < 3; q++) if (lane + 32 * q < 78) arr[q] += D * p[ri[q]] * p[rj[q]];
     }
     if (nva > NH) {
+      double acc_c2 = 0;
       for (int r = 0; r < nC; r++) {
         if (!active(nR + r, s.eJaref[nR + r])) continue;
         const double* p = s.pool + nR * SR + r * SC;
-        if (lane < 21) acc_cc += s.eD[nR + r] * p[ci] * p[cj];
+        if (lane < 21) { if (r & 1) acc_c2 += s.eD[nR + r] * p[ci] * p[cj]; else acc_cc += s.eD[nR + r] * p[ci] * p[cj]; }
       }
+      acc_cc += acc_c2;
       for (int r = 0; r < nF; r++) {
         int g = nR + nC + r;
         if (!active(g, s.eJaref[g])) continue;
@@ -1795,6 +1824,7 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
       if ((mask >> j) & 1u) { if (n >= NMNZ_MAX) { delete m; return fail("mcb_model_create: too many M non-zeros"); } h.mnz_i[n] = (unsigned char)i; h.mnz_j[n] = (unsigned char)j; n++; }
   }
   h.nmnz = n;
+  for (int i = 0, e = 0; i < NV; i++) for (int j = 0; j <= i; j++, e++) { h.tri_i[e] = (unsigned char)i; h.tri_j[e] = (unsigned char)j; }
   // contact parameter mixing per candidate pair (mj_collideGeoms / mj_contactParam)
   if (d->npair > MCB_MAXPAIR) { delete m; return fail("mcb_model_create: too many pairs"); }
   for (int p = 0; p < d->npair; p++) {
