@@ -156,6 +156,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     kw, per_gpu, flop_per_step = WORKLOADS[args.workload]
     n = args.envs_per_gpu or per_gpu
