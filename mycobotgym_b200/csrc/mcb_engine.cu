@@ -1125,30 +1125,54 @@ struct Newton {
 #pragma unroll
     for (int p = 0; p < 3; p++) { int e = lane + 32 * p; ri[p] = MDL.tri_i[e]; rj[p] = MDL.tri_j[e]; }
     const int ci = MDL.tri_i[lane], cj = MDL.tri_j[lane];    // cube-cube entry t = lane < 21
-    double arr[3], acc_cc = 0, arc[3] = {0, 0, 0};
+    // D_r for active rows, 0 for inactive ones: branch-free accumulation below.  eJv is free here (the constraint
+    // forces it held were consumed by update_cost_grad; line_search refills it with J*search).
+    double* Da = s.eJv;
+    for (int r = lane; r < nefc; r += 32) Da[r] = active(r, s.eJaref[r]) ? s.eD[r] : 0.0;
+    __syncwarp();
+    double arr[3], ar2[3] = {0, 0, 0}, acc_cc = 0, arc[3] = {0, 0, 0};
 #pragma unroll
     for (int p = 0; p < 3; p++) arr[p] = (lane + 32 * p < 78) ? s.M[lane + 32 * p] : 0.0;
     if (lane < 21 && nva > NH) acc_cc = s.M[TRI(NH + ci, NH + cj)];
-    for (int r = 0; r < nR; r++) {
-      if (!active(r, s.eJaref[r])) continue;
-      const double* p = s.pool + r * SR;
-      double D = s.eD[r];
+    {
+      const int o0 = ri[0], o1 = rj[0], o2 = ri[1], o3 = rj[1];
+      const int o4 = (lane + 64 < 78) ? ri[2] : 0, o5 = (lane + 64 < 78) ? rj[2] : 0;   // lanes past the 78 entries recompute entry (0,0): never stored
+      int r = 0;
+      for (; r + 1 < nR; r += 2) {
+        const double* p = s.pool + r * SR;
+        double D0 = Da[r], D1 = Da[r + 1];
+        arr[0] += D0 * p[o0] * p[o1]; ar2[0] += D1 * p[SR + o0] * p[SR + o1];
+        arr[1] += D0 * p[o2] * p[o3]; ar2[1] += D1 * p[SR + o2] * p[SR + o3];
+        arr[2] += D0 * p[o4] * p[o5]; ar2[2] += D1 * p[SR + o4] * p[SR + o5];
+      }
+      if (r < nR) {
+        const double* p = s.pool + r * SR;
+        double D0 = Da[r];
+        arr[0] += D0 * p[o0] * p[o1]; arr[1] += D0 * p[o2] * p[o3]; arr[2] += D0 * p[o4] * p[o5];
+      }
 #pragma unroll
-      for (int q = 0; q < 3; q++) if (lane + 32 * q < 78) arr[q] += D * p[ri[q]] * p[rj[q]];
+      for (int q = 0; q < 3; q++) arr[q] += ar2[q];
     }
     if (nva > NH) {
-      double acc_c2 = 0;
-      for (int r = 0; r < nC; r++) {
-        if (!active(nR + r, s.eJaref[nR + r])) continue;
-        const double* p = s.pool + nR * SR + r * SC;
-        if (lane < 21) { if (r & 1) acc_c2 += s.eD[nR + r] * p[ci] * p[cj]; else acc_cc += s.eD[nR + r] * p[ci] * p[cj]; }
+      {
+        const int c0 = (lane < 21) ? ci : 0, c1 = (lane < 21) ? cj : 0;
+        const double* p = s.pool + nR * SR;
+        const double* Dc = Da + nR;
+        double a1 = 0, a2 = 0, a3 = 0;
+        int r = 0;
+        for (; r + 3 < nC; r += 4) {
+          acc_cc += Dc[r] * p[r * SC + c0] * p[r * SC + c1];
+          a1 += Dc[r + 1] * p[(r + 1) * SC + c0] * p[(r + 1) * SC + c1];
+          a2 += Dc[r + 2] * p[(r + 2) * SC + c0] * p[(r + 2) * SC + c1];
+          a3 += Dc[r + 3] * p[(r + 3) * SC + c0] * p[(r + 3) * SC + c1];
+        }
+        for (; r < nC; r++) acc_cc += Dc[r] * p[r * SC + c0] * p[r * SC + c1];
+        acc_cc += (a1 + a2) + a3;
       }
-      acc_cc += acc_c2;
       for (int r = 0; r < nF; r++) {
         int g = nR + nC + r;
-        if (!active(g, s.eJaref[g])) continue;
         const double* p = s.pool + nR * SR + nC * SC + r * SF;
-        double D = s.eD[g];
+        double D = Da[g];
 #pragma unroll
         for (int q = 0; q < 3; q++) if (lane + 32 * q < 78) arr[q] += D * p[ri[q]] * p[rj[q]];
         if (lane < 21) acc_cc += D * p[NH + ci] * p[NH + cj];
@@ -1167,7 +1191,8 @@ struct Newton {
     if (lane == 0) {
       for (int u = 0; u < nU; u++) {
         int r = nR + nC + nF + u;
-        if (active(r, s.eJaref[r])) { int d = s.rmeta[r] & 0xff; s.H[TRI(d, d)] += s.eD[r]; }
+        int d = s.rmeta[r] & 0xff;
+        s.H[TRI(d, d)] += Da[r];
       }
     }
     __syncwarp();
@@ -1384,74 +1409,83 @@ __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& 
 }
 
 // observation (mycobot.py:342-388): written from the frames currently in shared memory (stale by one
-// substep after a step, fresh after forward), qpos / qvel current.
+// substep after a step, fresh after forward), qpos / qvel current.  Lanes 0-2: gripper position / velocity,
+// 3-5: cube position / velocities, 6: cube Euler angles, 7: gripper joint state; staged through s.grad..s.Mv.
 template <class S>
 __device__ __noinline__ void write_obs(S& s, const DevModel* __restrict__ m, const mcb_task_cfg& cfg, int lane, int env, double* obs, double* ag, double* dg, double* ag_out3) {
   const double dt = cfg.frame_skip * MDL.d.timestep;
-  int eb = MDL.d.eef_body;
-  const double* R = s.xmat + eb * 9;
-  const double* ep = MDL.d.eef_pos;
-  double grip[3], gvel[3] = {0, 0, 0};
-  for (int r = 0; r < 3; r++) grip[r] = s.xpos[eb * 3 + r] + R[3 * r] * ep[0] + R[3 * r + 1] * ep[1] + R[3 * r + 2] * ep[2];
-  {
-    unsigned mask = MDL.d.ancmask[eb];
+  double* o = s.grad;          // grad, search, Mv are contiguous: 54 doubles of scratch, dead outside the solver
+  const bool has_obj = cfg.has_object;
+  __syncwarp();
+  if (lane < 3) {
+    const int r = lane, eb = MDL.d.eef_body;
+    const double* R = s.xmat + eb * 9;
+    const double* ep = MDL.d.eef_pos;
+    double grip[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) grip[q] = s.xpos[eb * 3 + q] + R[3 * q] * ep[0] + R[3 * q + 1] * ep[1] + R[3 * q + 2] * ep[2];
     double off[3] = {grip[0] - MDL.d.ref_robot[0], grip[1] - MDL.d.ref_robot[1], grip[2] - MDL.d.ref_robot[2]};
+    double gv = 0;
+    unsigned mask = MDL.d.ancmask[eb];
     while (mask) {
       int j = __ffs(mask) - 1; mask &= mask - 1;
       const double* cd = s.cdof + j * 6;
       double t[3];
       cross3(t, cd, off);
-      for (int r = 0; r < 3; r++) gvel[r] += (cd[3 + r] + t[r]) * s.qvel[j];
+      gv += (cd[3 + r] + (r == 0 ? t[0] : r == 1 ? t[1] : t[2])) * s.qvel[j];
     }
-  }
-  double o[MCB_OBS_OBJECT];
-  double achieved[3];
-  int nobs;
-  if (cfg.has_object) {
-    const double* Ro = s.xmat + CUBE * 9;
+    o[40 + r] = (r == 0 ? grip[0] : r == 1 ? grip[1] : grip[2]);
+    o[43 + r] = gv;
+  } else if (lane < 6 && has_obj) {
+    const int r = lane - 3;
     double op[3] = {s.xpos[CUBE * 3], s.xpos[CUBE * 3 + 1], s.xpos[CUBE * 3 + 2]};
-    double velp[3], velr[3];
-    // site at the body origin; jacp cols: e_k for the linear dofs, (Rcol_k x (site - refcube)) for rotational
     double off[3] = {op[0] - s.refcube[0], op[1] - s.refcube[1], op[2] - s.refcube[2]};
-    for (int r = 0; r < 3; r++) { velp[r] = 0; velr[r] = 0; }
+    double vp = 0, vr = 0;
     for (int j = 12; j < 18; j++) {
       const double* cd = s.cdof + j * 6;
       double t[3];
       cross3(t, cd, off);
-      for (int r = 0; r < 3; r++) { velp[r] += (cd[3 + r] + t[r]) * s.qvel[j]; velr[r] += cd[r] * s.qvel[j]; }
+      vp += (cd[3 + r] + (r == 0 ? t[0] : r == 1 ? t[1] : t[2])) * s.qvel[j];
+      vr += cd[r] * s.qvel[j];
     }
+    o[46 + r] = (r == 0 ? op[0] : r == 1 ? op[1] : op[2]);
+    o[49 + r] = vp;
+    o[17 + r] = vr * dt;
+  } else if (lane == 6 && has_obj) {
+    const double* Ro = s.xmat + CUBE * 9;
     double cy = sqrt(Ro[8] * Ro[8] + Ro[5] * Ro[5]);
     double e0, e1, e2;
     if (cy > 2.220446049250313e-16 * 4.0) { e2 = -atan2(Ro[1], Ro[0]); e1 = -atan2(-Ro[2], cy); e0 = -atan2(Ro[5], Ro[8]); }
     else { e2 = -atan2(-Ro[3], Ro[4]); e1 = -atan2(-Ro[2], cy); e0 = 0.0; }
-    o[0] = grip[0]; o[1] = grip[1]; o[2] = grip[2];
-    o[3] = op[0]; o[4] = op[1]; o[5] = op[2];
-    o[6] = op[0] - grip[0]; o[7] = op[1] - grip[1]; o[8] = op[2] - grip[2];
-    o[9] = s.qpos[6]; o[10] = s.qpos[8];
     o[11] = e0; o[12] = e1; o[13] = e2;
-    o[14] = velp[0] * dt - gvel[0] * dt; o[15] = velp[1] * dt - gvel[1] * dt; o[16] = velp[2] * dt - gvel[2] * dt;
-    o[17] = velr[0] * dt; o[18] = velr[1] * dt; o[19] = velr[2] * dt;
-    o[20] = gvel[0] * dt; o[21] = gvel[1] * dt; o[22] = gvel[2] * dt;
-    o[23] = s.qvel[6] * dt; o[24] = s.qvel[8] * dt;
-    achieved[0] = op[0]; achieved[1] = op[1]; achieved[2] = op[2];
+  }
+  __syncwarp();
+  int nobs;
+  if (has_obj) {
+    if (lane < 3) {
+      const int r = lane;
+      double grip = o[40 + r], gv = o[43 + r], op = o[46 + r], vp = o[49 + r];
+      o[r] = grip; o[3 + r] = op; o[6 + r] = op - grip;
+      o[14 + r] = vp * dt - gv * dt;
+      o[20 + r] = gv * dt;
+    } else if (lane == 3) {
+      o[9] = s.qpos[6]; o[10] = s.qpos[8]; o[23] = s.qvel[6] * dt; o[24] = s.qvel[8] * dt;
+    }
     nobs = MCB_OBS_OBJECT;
   } else {
-    o[0] = grip[0]; o[1] = grip[1]; o[2] = grip[2];
-    o[3] = s.qpos[6]; o[4] = s.qpos[8];
-    o[5] = gvel[0] * dt; o[6] = gvel[1] * dt; o[7] = gvel[2] * dt;
-    o[8] = s.qvel[6] * dt; o[9] = s.qvel[8] * dt;
-    achieved[0] = grip[0]; achieved[1] = grip[1]; achieved[2] = grip[2];
+    if (lane < 3) { const int r = lane; o[r] = o[40 + r]; o[5 + r] = o[43 + r] * dt; }
+    else if (lane == 3) { o[3] = s.qpos[6]; o[4] = s.qpos[8]; o[8] = s.qvel[6] * dt; o[9] = s.qvel[8] * dt; }
     nobs = MCB_OBS_REACH;
   }
-  if (obs) {
-#pragma unroll
-    for (int k = 0; k < MCB_OBS_OBJECT; k++) if (lane == k && k < nobs) obs[(size_t)env * nobs + k] = o[k];
-  }
+  __syncwarp();
+  const int a0 = has_obj ? 3 : 0;     // achieved goal: cube position (object envs) or gripper position (reach)
+  if (obs && lane < nobs) obs[(size_t)env * nobs + lane] = o[lane];
   if (lane < 3) {
-    if (ag) ag[(size_t)env * 3 + lane] = achieved[lane];
+    if (ag) ag[(size_t)env * 3 + lane] = o[a0 + lane];
     if (dg) dg[(size_t)env * 3 + lane] = s.goal[lane];
   }
-  ag_out3[0] = achieved[0]; ag_out3[1] = achieved[1]; ag_out3[2] = achieved[2];
+  ag_out3[0] = o[a0]; ag_out3[1] = o[a0 + 1]; ag_out3[2] = o[a0 + 2];
+  __syncwarp();
 }
 
 template <class S>
