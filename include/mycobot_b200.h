@@ -91,6 +91,9 @@ typedef struct mcb_model_desc {
   int32_t eef_body;
   double eef_pos[3];
   int32_t obj_body;
+  /* staged reward (mycobot.py:402-448): finger-layer / object geoms, target0 site (XML default: only render() moves it, mycobot.py:309-311) */
+  int32_t geom_finger_r, geom_finger_l, geom_object;
+  double target0_pos[3];
   /* actuators: general, no dynamics, fixed gain, affine bias */
   double act_moment[MCB_NU][MCB_NV];
   double act_gain[MCB_NU];
@@ -114,7 +117,7 @@ typedef struct mcb_task_cfg {
   int32_t has_object;          /* mycobot.py:33 */
   int32_t block_gripper;       /* mycobot.py:34 */
   int32_t target_in_the_air;   /* mycobot.py:38 */
-  int32_t reward_type;         /* 0 sparse (float32 out), 1 dense (float64 out); mycobot.py:289-295 */
+  int32_t reward_type;         /* 0 sparse (float32 out), 1 dense (float64 out), 2 reward_shaping (float64 out, object envs); mycobot.py:289-298 */
   int32_t max_episode_steps;   /* 50 */
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
@@ -158,7 +161,7 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* achiev
  * reference-side VecEnv adapter holding numpy arrays makes. */
 int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, double* h_achieved_goal,
                       double* h_desired_goal, void* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-                      uint8_t* h_success, void* stream);
+                      uint8_t* h_success, double* h_final_obs /* or NULL */, void* stream);
 
 /* state injection / extraction for parity replay: qpos[N,19] qvel[N,18] ctrl[N,7]
  * qacc_warmstart[N,18] goal[N,3] elapsed int32[N]; any pointer may be NULL. */

@@ -71,7 +71,7 @@ def load():
     L.mcb_batch_obs_dim.argtypes = [vp]
     L.mcb_reset.argtypes = [vp] + [vp] * 7
     L.mcb_step.argtypes = [vp] + [vp] * 10
-    L.mcb_step_host.argtypes = [vp] + [vp] * 9
+    L.mcb_step_host.argtypes = [vp] + [vp] * 10
     L.mcb_get_state.argtypes = [vp] + [vp] * 7
     L.mcb_set_state.argtypes = [vp] + [vp] * 7
     L.mcb_forward.argtypes = [vp] + [vp] * 4

@@ -1675,6 +1675,26 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         bool succ = dist < cfg.distance_threshold;
         bool term = succ, trunc = succ || (el >= cfg.max_episode_steps);
         double rew = cfg.reward_type == 0 ? -(double)(dist > cfg.distance_threshold) : -dist;
+        if (cfg.reward_type == 2) {
+          // stage_rewards (mycobot.py:402-448): reach / grasp / lift from the sites and the contact list of the last
+          // forward pass; write_obs left grip_pos in o[0..2] and object_pos in o[3..5]
+          const double* o = s.grad;
+          double gx = o[0] - o[3], gy = o[1] - o[4], gz = o[2] - o[5];
+          double r_reach = (1 - tanh(sqrt(gx * gx + gy * gy + gz * gz))) * 0.2;
+          bool tr = false, tl = false;
+          for (int c = 0; c < s.ncon; c++) {
+            const PairParam& pp = MDL.pair[s.cpair[c]];
+            bool hasobj = pp.g1 == MDL.d.geom_object || pp.g2 == MDL.d.geom_object;
+            if (hasobj && (pp.g1 == MDL.d.geom_finger_r || pp.g2 == MDL.d.geom_finger_r)) tr = true;
+            if (hasobj && (pp.g1 == MDL.d.geom_finger_l || pp.g2 == MDL.d.geom_finger_l)) tl = true;
+          }
+          double r_grasp = (tr && tl) ? 0.5 : 0.0, r_lift = 0.0;
+          if (r_grasp > 0.0) {
+            double tx = o[3] - MDL.d.target0_pos[0], ty = o[4] - MDL.d.target0_pos[1], tz = o[5] - MDL.d.target0_pos[2];
+            r_lift = 0.5 + (1 - tanh(sqrt(tx * tx + ty * ty + tz * tz))) * (0.9 - 0.5);
+          }
+          rew = fmax(fmax(r_reach, r_grasp), r_lift) * 100;
+        }
         double epret = a.ep_return[env] + rew;
         bool done = term || trunc;
         double final_stats[4] = {1.0, succ ? 1.0 : 0.0, epret, (double)el};
@@ -1689,7 +1709,7 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         }
         if (ok && lane == 0) {
           if (cfg.reward_type == 0) ((float*)a.reward)[env] = -(float)(dist > cfg.distance_threshold);
-          else ((double*)a.reward)[env] = -dist;
+          else ((double*)a.reward)[env] = rew;
           a.terminated[env] = term; a.truncated[env] = trunc; a.success[env] = succ;
           if (done) { for (int k = 0; k < 4; k++) atomicAdd(a.stats + k, final_stats[k]); }
           a.elapsed[env] = el; a.ep_return[env] = epret;
@@ -1799,8 +1819,8 @@ struct mcb_batch {
   double* debug;
   int last_launches;
   // staging for the host-buffer entry point
-  float* d_actions; double *d_obs, *d_ag, *d_dg; void* d_reward; uint8_t* d_flags;
-  float* h_actions; double *h_obs, *h_ag, *h_dg; void* h_reward; uint8_t* h_flags;
+  float* d_actions; double *d_obs, *d_ag, *d_dg, *d_fobs; void* d_reward; uint8_t* d_flags;
+  float* h_actions; double *h_obs, *h_ag, *h_dg, *h_fobs; void* h_reward; uint8_t* h_flags;
 };
 
 static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
@@ -1899,6 +1919,7 @@ int32_t mcb_model_destroy(mcb_model* m) {
 
 int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out) {
   if (!m || !cfg || !out || n_envs <= 0) return fail("mcb_batch_create: bad argument");
+  if (cfg->reward_type < 0 || cfg->reward_type > 2 || (cfg->reward_type == 2 && !cfg->has_object)) return fail("mcb_batch_create: reward_type must be 0, 1 or 2 (2 needs has_object)");
   CK(cudaSetDevice(m->device));
   mcb_batch* b = new mcb_batch();
   memset(b, 0, sizeof *b);
@@ -1936,8 +1957,8 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
 int32_t mcb_batch_destroy(mcb_batch* b) {
   if (!b) return 0;
   cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->stats); cudaFree(b->debug); cudaFree(b->redo_count); cudaFree(b->redo_list);
-  if (b->d_actions) { cudaFree(b->d_actions); cudaFree(b->d_obs); cudaFree(b->d_ag); cudaFree(b->d_dg); cudaFree(b->d_reward); cudaFree(b->d_flags); }
-  if (b->h_actions) { cudaFreeHost(b->h_actions); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_ag); cudaFreeHost(b->h_dg); cudaFreeHost(b->h_reward); cudaFreeHost(b->h_flags); }
+  if (b->d_actions) { cudaFree(b->d_actions); cudaFree(b->d_obs); cudaFree(b->d_fobs); cudaFree(b->d_ag); cudaFree(b->d_dg); cudaFree(b->d_reward); cudaFree(b->d_flags); }
+  if (b->h_actions) { cudaFreeHost(b->h_actions); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_fobs); cudaFreeHost(b->h_ag); cudaFreeHost(b->h_dg); cudaFreeHost(b->h_reward); cudaFreeHost(b->h_flags); }
   delete b;
   return 0;
 }
@@ -1999,6 +2020,7 @@ int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, cons
 int32_t mcb_compute_reward(const double* ag, const double* g, int64_t n, double thr, int32_t type, void* out, void* stream) {
   if (n == 0) return 0;
   if (!ag || !g || !out || n < 0) return fail("mcb_compute_reward: bad argument");
+  if (type != 0 && type != 1) return fail("mcb_compute_reward: reward_shaping depends on the simulation state, not on (achieved_goal, goal)");
   reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, g, n, thr, type, out);
   CK(cudaGetLastError());
   return 0;
@@ -2012,7 +2034,7 @@ int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream) 
 }
 
 int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, double* h_ag, double* h_dg, void* h_reward, uint8_t* h_term,
-                      uint8_t* h_trunc, uint8_t* h_succ, void* stream) {
+                      uint8_t* h_trunc, uint8_t* h_succ, double* h_final_obs, void* stream) {
   if (!b || !h_actions) return fail("mcb_step_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   size_t N = (size_t)b->n_envs, od = (size_t)b->obs_dim;
@@ -2020,6 +2042,8 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
   if (!b->d_actions) {
     CK(cudaMalloc(&b->d_actions, N * NU * sizeof(float)));
     CK(cudaMalloc(&b->d_obs, N * od * sizeof(double)));
+    CK(cudaMalloc(&b->d_fobs, N * od * sizeof(double)));
+    CK(cudaMallocHost(&b->h_fobs, N * od * sizeof(double)));
     CK(cudaMalloc(&b->d_ag, N * 3 * sizeof(double)));
     CK(cudaMalloc(&b->d_dg, N * 3 * sizeof(double)));
     CK(cudaMalloc(&b->d_reward, N * sizeof(double)));
@@ -2033,7 +2057,9 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
   }
   memcpy(b->h_actions, h_actions, N * NU * sizeof(float));
   CK(cudaMemcpyAsync(b->d_actions, b->h_actions, N * NU * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (mcb_step(b, b->d_actions, b->d_obs, b->d_ag, b->d_dg, b->d_reward, b->d_flags, b->d_flags + N, b->d_flags + 2 * N, nullptr, stream)) return -1;
+  if (mcb_step(b, b->d_actions, b->d_obs, b->d_ag, b->d_dg, b->d_reward, b->d_flags, b->d_flags + N, b->d_flags + 2 * N,
+               h_final_obs ? b->d_fobs : nullptr, stream)) return -1;
+  if (h_final_obs) CK(cudaMemcpyAsync(b->h_fobs, b->d_fobs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(b->h_obs, b->d_obs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(b->h_ag, b->d_ag, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(b->h_dg, b->d_dg, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -2041,6 +2067,7 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
   CK(cudaMemcpyAsync(b->h_flags, b->d_flags, N * 3, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (h_obs) memcpy(h_obs, b->h_obs, N * od * sizeof(double));
+  if (h_final_obs) memcpy(h_final_obs, b->h_fobs, N * od * sizeof(double));
   if (h_ag) memcpy(h_ag, b->h_ag, N * 3 * sizeof(double));
   if (h_dg) memcpy(h_dg, b->h_dg, N * 3 * sizeof(double));
   if (h_reward) memcpy(h_reward, b->h_reward, N * rbytes);

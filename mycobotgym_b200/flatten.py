@@ -42,6 +42,7 @@ class ModelDesc(C.Structure):
         ("geom_solimp", _d * 5 * NGEOM), ("geom_solmix", _d * NGEOM), ("geom_invweight", _d * 2 * NGEOM),
         ("npair", _i), ("pair_g1", _i * MAXPAIR), ("pair_g2", _i * MAXPAIR),
         ("eef_body", _i), ("eef_pos", _d * 3), ("obj_body", _i),
+        ("geom_finger_r", _i), ("geom_finger_l", _i), ("geom_object", _i), ("target0_pos", _d * 3),
         ("act_moment", _d * NV * NU), ("act_gain", _d * NU), ("act_bias", _d * 3 * NU),
         ("act_ctrlrange", _d * 2 * NU), ("act_forcerange", _d * 2 * NU), ("act_ctrllimited", _i * NU),
         ("act_forcelimited", _i * NU),
@@ -239,6 +240,11 @@ def reduce_model(m) -> ModelDesc:
     ob = int(m["site_bodyid"][s_obj])
     assert ob in jidx and np.all(m["site_pos"][s_obj] == 0)
     d.obj_body = jidx[ob]
+    gn = m["geom_names"]
+    d.geom_finger_r, d.geom_finger_l, d.geom_object = gn.index("right_finger_layer"), gn.index("left_finger_layer"), gn.index("object0")
+    s_t = m["site_names"].index("target0")
+    assert m["site_bodyid"][s_t] == 0
+    _set(d.target0_pos, m["site_pos"][s_t])
 
     _set(d.act_moment, m["actuator_moment"])
     _set(d.act_gain, m["actuator_gain"])

@@ -160,8 +160,10 @@ class MyCobotVectorEnv:
             raise NotImplementedError(f"controller_type={controller_type!r}: only the joint controller is built (SURVEY 8f)")
         if fetch_env:
             raise NotImplementedError("fetch_env: joint controller is not supported for Fetch envs (mycobot.py:96)")
-        if reward_type not in ("sparse", "dense"):
-            raise NotImplementedError(f"reward_type={reward_type!r} (reward_shaping is a 'next' row)")
+        if reward_type not in ("sparse", "dense", "reward_shaping"):
+            raise ValueError(f"unknown reward_type {reward_type!r}")
+        if reward_type == "reward_shaping" and not has_object:
+            raise NotImplementedError("reward_shaping on the reach env needs the hidden cube simulated (it is frozen here, DESIGN.md)")
         if "mocap" in model_path:
             raise NotImplementedError("mocap model variant is a 'next' row")
         if goal_source not in ("device", "reference"):
@@ -183,7 +185,7 @@ class MyCobotVectorEnv:
         self._model, self._desc, self._flat = _device_model(dev_index)
         cfg = flatten.TaskCfg(
             has_object=int(has_object), block_gripper=int(block_gripper), target_in_the_air=int(target_in_the_air),
-            reward_type=0 if reward_type == "sparse" else 1, max_episode_steps=self.max_episode_steps,
+            reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,
             frame_skip=self.frame_skip, auto_reset=int(self.auto_reset and goal_source == "device"), nefc_max=int(nefc_max),
             distance_threshold=self.distance_threshold)
         self._cfg = cfg
@@ -276,6 +278,8 @@ class MyCobotVectorEnv:
 
     def compute_reward(self, achieved_goal, goal, info=None):
         """mycobot.py:289-295 on arbitrary batches (HER relabelling); numpy in -> numpy out, torch in -> torch out."""
+        if self.reward_type == "reward_shaping":
+            raise NotImplementedError("reward_shaping depends on the live simulation state (mycobot.py:296-298), not on (achieved_goal, goal)")
         is_np = not torch.is_tensor(achieved_goal)
         ag = torch.as_tensor(np.asarray(achieved_goal) if is_np else achieved_goal, dtype=torch.float64, device=self.device).contiguous()
         g = torch.as_tensor(np.asarray(goal) if not torch.is_tensor(goal) else goal, dtype=torch.float64, device=self.device).contiguous()
@@ -349,7 +353,7 @@ class MyCobotVectorEnv:
             _lib.check(self._L.mcb_stats(self._batch, _ptr(self._stats), int(reset), self._stream()))
         return self._stats
 
-    def step_host(self, actions_np, out=None):
+    def step_host(self, actions_np, out=None, want_final_obs=False):
         """The same step through HOST buffers (numpy): H2D of actions and D2H of all results inside the call."""
         a = np.ascontiguousarray(actions_np, dtype=np.float32)
         assert a.shape == (self.num_envs, 7)
@@ -358,10 +362,13 @@ class MyCobotVectorEnv:
             out = dict(observation=np.empty((N, self.obs_dim)), achieved_goal=np.empty((N, 3)), desired_goal=np.empty((N, 3)),
                        reward=np.empty(N, dtype=np.float32 if self.reward_type == "sparse" else np.float64),
                        terminated=np.empty(N, dtype=np.uint8), truncated=np.empty(N, dtype=np.uint8), is_success=np.empty(N, dtype=np.uint8))
+            if want_final_obs:
+                out["final_observation"] = np.empty((N, self.obs_dim))
         p = lambda x: x.ctypes.data_as(C.c_void_p)
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_step_host(self._batch, p(a), p(out["observation"]), p(out["achieved_goal"]), p(out["desired_goal"]),
-                                            p(out["reward"]), p(out["terminated"]), p(out["truncated"]), p(out["is_success"]), self._stream()))
+                                            p(out["reward"]), p(out["terminated"]), p(out["truncated"]), p(out["is_success"]),
+                                            p(out["final_observation"]) if "final_observation" in out else None, self._stream()))
         return out
 
     @property

@@ -317,6 +317,23 @@ class OracleEnv:
             return -(d > self.distance_threshold).astype(np.float32)
         if self.reward_type == "dense":
             return -d
+        if self.reward_type == "reward_shaping":
+            return max(self.stage_rewards()) * 100
+
+    def stage_rewards(self):
+        """mycobot.py:402-448; target0 keeps its XML position because only render() moves it (mycobot.py:309-311)."""
+        s, gn = self.sim, self.flat["geom_names"]
+        grip_pos, object_pos = s.site_xpos[self.site_eef], s.site_xpos[self.site_obj]
+        target_pos = s.site_xpos[self.flat["site_names"].index("target0")]
+        r_reach = (1 - np.tanh(goal_distance(grip_pos, object_pos))) * 0.2
+        rl, ll, ob = gn.index("right_finger_layer"), gn.index("left_finger_layer"), gn.index("object0")
+        pairs = {(c["geom1"], c["geom2"]) for c in s.contacts()}
+        touch = lambda g: (g, ob) in pairs or (ob, g) in pairs
+        r_grasp = int(touch(rl) and touch(ll)) * 0.5
+        r_lift = 0.0
+        if r_grasp > 0.0:
+            r_lift = 0.5 + (1 - np.tanh(goal_distance(object_pos, target_pos))) * (0.9 - 0.5)
+        return r_reach, r_grasp, r_lift
 
     def reset(self, seed=None, object_xy=None, goal=None):
         """mycobot.py:506-514 + 207-236.  `object_xy`/`goal` inject sampler outputs (parity harness)."""

@@ -57,7 +57,8 @@ def test_registry_matches_reference_registration():
 
 
 def test_unbuilt_rows_fail_loudly():
-    for kwargs in (dict(controller_type="IK"), dict(controller_type="mocap"), dict(reward_type="reward_shaping"), dict(fetch_env=True)):
+    for kwargs in (dict(controller_type="IK"), dict(controller_type="mocap"), dict(reward_type="reward_shaping", has_object=False),
+                   dict(fetch_env=True)):
         with pytest.raises(NotImplementedError):
             vector_env.MyCobotVectorEnv(num_envs=1, **kwargs)
 

@@ -374,3 +374,50 @@ def test_two_tier_layout_equals_fallback_layout(flat):
         env.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
     assert outs[0][3][4] == n and outs[0][3][5] == 0            # every env stepped exactly once, nothing dropped
+
+
+def test_staged_reward_matches_oracle(flat):
+    # SURVEY 8f-3 (reward_shaping): contact-pair flags exported from the collision stage + tanh shaping
+    from oracle.oracle import OracleEnv
+
+    n = 8
+    qpos, qvel, ctrl = _states(flat, n, 41)
+    g = np.load(os.path.join(GOLDEN, "grasp_pick_sparse.npz"))
+    qpos[3], qvel[3], ctrl[3] = g["qpos0"], g["qvel0"], g["ctrl0"]
+    acts = np.random.default_rng(42).uniform(-1, 1, (n, 7)).astype(np.float32)
+    acts[3] = g["actions"][0]
+    env = _env(num_envs=n, has_object=True, reward_type="reward_shaping", auto_reset=False)
+    env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=np.zeros((n, 18)), goal=np.tile([0.0, 0.0, 0.3], (n, 1)),
+                  elapsed=np.zeros(n, dtype=np.int32))
+    obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
+    assert rew.dtype == torch.float64
+    for i in range(n):
+        oe = OracleEnv(flat, has_object=True, reward_type="reward_shaping")
+        oe.sim.set_state(qpos[i], qvel[i], ctrl[i], np.zeros(18))
+        oe.goal = np.array([0.0, 0.0, 0.3])
+        o, r, te, tr, inf = oe.step(acts[i])
+        assert abs(float(rew[i]) - float(r)) < 1e-7, (i, float(rew[i]), float(r))
+    assert float(rew[3]) > 50 and float(rew[0]) < 20              # env 3 holds the cube, env 0 does not
+    with pytest.raises(NotImplementedError):
+        env.compute_reward(np.zeros((2, 3)), np.zeros((2, 3)), None)
+    env.close()
+
+
+def test_sb3_shaped_adapter():
+    # VecEnv call pattern of scripts/train.py:80-97 and the info keys scripts/eval_model.py:131 reads
+    from mycobotgym_b200.sb3_adapter import MyCobotSB3VecEnv
+
+    n = 32
+    ve = MyCobotSB3VecEnv(n, has_object=True, reward_type="sparse", seed=2)
+    obs = ve.reset()
+    assert obs["observation"].shape == (n, 25) and obs["observation"].dtype == np.float64
+    for t in range(50):
+        ve.step_async(np.zeros((n, 7), dtype=np.float32))
+        obs, rew, dones, infos = ve.step_wait()
+    assert dones.all() and rew.dtype == np.float32 and len(infos) == n
+    assert infos[0]["TimeLimit.truncated"] and infos[0]["is_success"] is False
+    assert infos[0]["episode"] == {"r": -50.0, "l": 50} and infos[0]["terminal_observation"]["observation"].shape == (25,)
+    assert not np.array_equal(infos[0]["terminal_observation"]["observation"], obs["observation"][0])
+    r = ve.env_method("compute_reward", np.zeros((7, 3)), np.full((7, 3), 0.1), None)[0]
+    assert r.shape == (7,) and np.all(r == -1.0)
+    ve.close()

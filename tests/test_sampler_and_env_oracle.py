@@ -115,3 +115,19 @@ def test_oracle_reproduces_committed_golden(flat, name):
         np.testing.assert_allclose(o["observation"], g["obs"][t], atol=1e-12)
         assert float(r) == pytest.approx(float(g["reward"][t]), abs=1e-12)
         assert te == bool(g["terminated"][t]) and tr == bool(g["truncated"][t])
+
+
+def test_staged_reward_on_the_oracle(flat):
+    # mycobot.py:402-448: reach term only while the cube is not held; grasp / lift terms once both finger layers touch it
+    env = OracleEnv(flat, has_object=True, reward_type="reward_shaping")
+    random.seed(3)
+    env.reset(seed=3)
+    o, r, te, tr, info = env.step(np.zeros(7, dtype=np.float32))
+    d = np.linalg.norm(o["observation"][0:3] - o["observation"][3:6])
+    assert r == pytest.approx((1 - np.tanh(d)) * 0.2 * 100, abs=1e-12) and r < 20
+    g = np.load(os.path.join(GOLDEN, "grasp_pick_sparse.npz"))
+    env.sim.set_state(g["qpos0"], g["qvel0"], g["ctrl0"], g["warm0"])
+    o, r, te, tr, info = env.step(g["actions"][0])
+    tgt = np.array([-0.15, 0.0, 0.21])                       # target0 site, mycobot280_main.xml:83
+    lift = 0.5 + (1 - np.tanh(np.linalg.norm(o["observation"][3:6] - tgt))) * 0.4
+    assert r == pytest.approx(lift * 100, abs=1e-9) and r > 50
