@@ -31,6 +31,8 @@ WORKLOADS = {
     "reach": (dict(has_object=False, reward_type="dense"), 4096, 0.60e6),
     "push": (dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse"), 16384, 1.27e6),
     "pick": (dict(has_object=True, reward_type="sparse"), 16384, 1.25e6),
+    # IK controller (the reference's default): 5 x (6x6 DLS solve + 20 substeps) per env-step
+    "ik": (dict(has_object=True, reward_type="sparse", controller_type="IK"), 16384, 5 * 1.25e6),
 }
 METRIC = "env-steps/sec (pick-and-place, 16K envs/GPU) at 1/2/4/8 B200 vs CPU MuJoCo"
 UNIT = "env-steps/s"
@@ -44,7 +46,8 @@ def _cpu_worker(job):
     flat = mjcf.load_compiled()
     kw, _, _ = WORKLOADS[workload]
     okw = dict(has_object=kw.get("has_object", True), block_gripper=kw.get("block_gripper", False),
-               target_in_the_air=kw.get("target_in_the_air", True), reward_type=kw.get("reward_type", "sparse"))
+               target_in_the_air=kw.get("target_in_the_air", True), reward_type=kw.get("reward_type", "sparse"),
+               controller_type=kw.get("controller_type", "joint"))
     envs = [OracleEnv(flat, **okw) for _ in range(envs_per_worker)]
     rng = np.random.default_rng(tid)
     for e in envs:
@@ -169,7 +172,7 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    acts = torch.rand(K + W, n, 7, device=dev, generator=gen) * 2 - 1
+    acts = torch.rand(K + W, n, env.action_dim, device=dev, generator=gen) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     for t in range(W):
         env.step(acts[t])
@@ -216,7 +219,7 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * K / float(e2e_s.item())
     rbytes = 4 if kw["reward_type"] == "sparse" else 8
-    h2d, d2h = n * 7 * 4, n * ((env.obs_dim + 6) * 8 + rbytes + 3)
+    h2d, d2h = n * env.action_dim * 4, n * ((env.obs_dim + 6) * 8 + rbytes + 3)
 
     if rank == 0:
         L = _lib.load()
@@ -232,7 +235,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, joint controller, 20 substeps/step, uniform random actions "
+            "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, {kw.get('controller_type', 'joint')} controller, "
+                                   f"{100 if kw.get('controller_type') == 'IK' else 20} substeps/step, uniform random actions "
                                    f"U[-1,1]^7 float32, 50-step TimeLimit (episode clocks staggered), auto-reset with on-device goal resampling",
                        "envs_per_gpu": n, "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},

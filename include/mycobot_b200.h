@@ -36,7 +36,7 @@ extern "C" {
 #define MCB_MAXPAIR 12
 #define MCB_OBS_OBJECT 25
 #define MCB_OBS_REACH 10
-#define MCB_STATE_STRIDE 72 /* doubles per env in the resident state record */
+#define MCB_STATE_STRIDE 72 /* doubles per env in the resident state record: qpos19 qvel18 ctrl7 warm18 goal3 qprev6 pad1 */
 
 /* Flattened, reduced model (host memory; copied to the device by mcb_model_create).
  * Replaces the compiled mjModel the reference builds in MujocoEnv.__init__ (mycobot.py:69-75). */
@@ -110,6 +110,11 @@ typedef struct mcb_model_desc {
   double height_offset;
   double init_qpos[MCB_NQ];
   double init_ctrl[MCB_NU];
+  /* the same four for fetch envs, which start from keyframe 0 (mycobot.py:451-452, mycobot280.xml:4-9) */
+  double key_initial_gripper_xpos[3];
+  double key_height_offset;
+  double key_qpos[MCB_NQ];
+  double key_ctrl[MCB_NU];
 } mcb_model_desc;
 
 /* Task configuration == the reference constructor kwargs (mycobot.py:30-46) + TimeLimit (__init__.py:34). */
@@ -122,6 +127,10 @@ typedef struct mcb_task_cfg {
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
   int32_t nefc_max;            /* 0 (default): two-tier layout (48-row common case + 128-row fallback launch); 128: fallback layout only */
+  int32_t controller_type;     /* 0 joint (action 7), 1 IK (action 7, or 4 with fetch_env); mycobot.py:36,134-170,190-193 */
+  int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
+  int32_t control_steps;       /* IK: DLS solves per env-step, each followed by frame_skip substeps (5; mycobot.py:35,162) */
+  int32_t reserved_;
   double distance_threshold;   /* 0.01 */
 } mcb_task_cfg;
 
@@ -142,6 +151,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
 int32_t mcb_batch_destroy(mcb_batch* b);
 int32_t mcb_batch_num_envs(const mcb_batch* b);
 int32_t mcb_batch_obs_dim(const mcb_batch* b);
+int32_t mcb_batch_action_dim(const mcb_batch* b);   /* 7, or 4 for the fetch IK variant (mycobot.py:90-97) */
 
 /* replaces MyCobotEnv.reset / reset_model / _sample_goal (mycobot.py:207-243,506-514).
  * mask: uint8[N] or NULL (= all).  obj_xy: double[N,2] or NULL (device sampler).  goals: double[N,3] or NULL.
@@ -149,8 +159,8 @@ int32_t mcb_batch_obs_dim(const mcb_batch* b);
 int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals,
                   double* obs, double* achieved_goal, double* desired_goal, void* stream);
 
-/* replaces MyCobotEnv.step, joint controller (mycobot.py:132-133,190-205) incl. TimeLimit truncation.
- * actions float32[N,7]; reward float32[N] (sparse) or float64[N] (dense); flags uint8[N].
+/* replaces MyCobotEnv.step, joint (mycobot.py:132-133,190-205) and IK (mycobot.py:134-170, utils.py:499-556) controllers
+ * incl. TimeLimit truncation.  actions float32[N, action_dim]; reward float32[N] (sparse) or float64[N] (dense); flags uint8[N].
  * final_obs double[N,obs_dim] or NULL: terminal observation of envs that auto-reset in this call. */
 int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* achieved_goal, double* desired_goal,
                  void* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* success, double* final_obs,
@@ -164,11 +174,15 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
                       uint8_t* h_success, double* h_final_obs /* or NULL */, void* stream);
 
 /* state injection / extraction for parity replay: qpos[N,19] qvel[N,18] ctrl[N,7]
- * qacc_warmstart[N,18] goal[N,3] elapsed int32[N]; any pointer may be NULL. */
+ * qacc_warmstart[N,18] goal[N,3] elapsed int32[N]; any pointer may be NULL.  qprev[N,6] = the arm joint
+ * positions the reference's *stale* site poses belong to (data.site_xpos is one substep old after mj_step; the IK
+ * controller reads it at the start of the next step, mycobot.py:136,151).  Setting qpos without qprev marks the
+ * frames fresh (qprev := qpos), which is the state after reset / mj_forward. */
 int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* qacc_warmstart, double* goal,
-                      int32_t* elapsed, void* stream);
+                      int32_t* elapsed, double* qprev, void* stream);
 int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl,
-                      const double* qacc_warmstart, const double* goal, const int32_t* elapsed, void* stream);
+                      const double* qacc_warmstart, const double* goal, const int32_t* elapsed, const double* qprev,
+                      void* stream);
 
 /* replaces mujoco.mj_forward on every env (mycobot.py:213,229,306); refreshes qacc_warmstart; optional obs out */
 int32_t mcb_forward(mcb_batch* b, double* obs, double* achieved_goal, double* desired_goal, void* stream);

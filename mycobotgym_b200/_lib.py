@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = [
     "mcb_version", "mcb_last_error", "mcb_model_desc_size", "mcb_task_cfg_size", "mcb_model_create",
-    "mcb_model_destroy", "mcb_batch_create", "mcb_batch_destroy", "mcb_batch_num_envs", "mcb_batch_obs_dim",
+    "mcb_model_destroy", "mcb_batch_create", "mcb_batch_destroy", "mcb_batch_num_envs", "mcb_batch_obs_dim", "mcb_batch_action_dim",
     "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
     "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
     "mcb_time_step_kernel",
@@ -69,11 +69,12 @@ def load():
     L.mcb_batch_destroy.argtypes = [vp]
     L.mcb_batch_num_envs.argtypes = [vp]
     L.mcb_batch_obs_dim.argtypes = [vp]
+    L.mcb_batch_action_dim.argtypes = [vp]
     L.mcb_reset.argtypes = [vp] + [vp] * 7
     L.mcb_step.argtypes = [vp] + [vp] * 10
     L.mcb_step_host.argtypes = [vp] + [vp] * 10
-    L.mcb_get_state.argtypes = [vp] + [vp] * 7
-    L.mcb_set_state.argtypes = [vp] + [vp] * 7
+    L.mcb_get_state.argtypes = [vp] + [vp] * 8
+    L.mcb_set_state.argtypes = [vp] + [vp] * 8
     L.mcb_forward.argtypes = [vp] + [vp] * 4
     L.mcb_compute_reward.argtypes = [vp, vp, i64, dbl, i32, vp, vp]
     L.mcb_stats.argtypes = [vp, vp, i32, vp]

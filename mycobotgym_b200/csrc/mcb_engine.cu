@@ -125,6 +125,8 @@ struct EnvS {
   double M[NTRI], H[NTRI];
   double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
   double anchors[12];
+  double qprev[6];   // arm qpos the frames in shared memory were computed from (the reference's stale site poses)
+  double ik[14];     // IK controller: target position (3), target quaternion (4), pose error (6)
   union {
     struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
     struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
@@ -1383,6 +1385,12 @@ __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lan
   __syncwarp();
 }
 
+// start-of-episode constants: the model's qpos0 set, or keyframe 0 for fetch envs (mycobot.py:451-472)
+__device__ __forceinline__ const double* init_qpos_of(const mcb_task_cfg& c) { return c.fetch_env ? MDL.d.key_qpos : MDL.d.init_qpos; }
+__device__ __forceinline__ const double* init_ctrl_of(const mcb_task_cfg& c) { return c.fetch_env ? MDL.d.key_ctrl : MDL.d.init_ctrl; }
+__device__ __forceinline__ const double* grip0_of(const mcb_task_cfg& c) { return c.fetch_env ? MDL.d.key_initial_gripper_xpos : MDL.d.initial_gripper_xpos; }
+__device__ __forceinline__ double hoff_of(const mcb_task_cfg& c) { return c.fetch_env ? MDL.d.key_height_offset : MDL.d.height_offset; }
+
 // Philox4x32-10 counter RNG: one stream per env, key = seed, counter = (env, draw index)
 __device__ __forceinline__ void philox_round(uint32_t* c, uint32_t k0, uint32_t k1) {
   uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
@@ -1402,7 +1410,7 @@ __device__ double philox_uniform(uint64_t seed, uint32_t env, unsigned long long
 __device__ void sample_goal(const DevModel* __restrict__ m, const mcb_task_cfg& cfg, uint64_t seed, uint32_t env, unsigned long long& ctr, double* g) {
   g[0] = -0.12 + (0.12 - (-0.12)) * philox_uniform(seed, env, ctr);
   g[1] = -0.06 + (0.06 - (-0.06)) * philox_uniform(seed, env, ctr);
-  g[2] = MDL.d.height_offset;
+  g[2] = hoff_of(cfg);
   if (cfg.target_in_the_air) {
     if (philox_uniform(seed, env, ctr) < 0.5) g[2] += 0.0 + (0.1 - 0.0) * philox_uniform(seed, env, ctr);
   }
@@ -1497,6 +1505,7 @@ __device__ void load_state(S& s, const double* __restrict__ st, int lane) {
     else if (w < 44) s.ctrl[w - 37] = v;
     else if (w < 62) s.warm[w - 44] = v;
     else if (w < 65) s.goal[w - 62] = v;
+    else if (w < 71) s.qprev[w - 65] = v;
   }
   __syncwarp();
 }
@@ -1509,28 +1518,137 @@ __device__ void store_state(const S& s, double* __restrict__ st, int lane) {
     else if (w < 44) v = s.ctrl[w - 37];
     else if (w < 62) v = s.warm[w - 44];
     else if (w < 65) v = s.goal[w - 62];
+    else if (w < 71) v = s.qprev[w - 65];
     st[w] = v;
   }
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// IK controller (mycobot.py:134-170, utils.py:499-556): damped-least-squares step on the EEF site pose.
+// mju_mat2Quat / mju_mulQuat / mju_quat2Vel and rotations.euler2quat restated; scalar work on lane 0.
+__device__ void mat2quat_d(double* q, const double* m) {
+  if (m[0] + m[4] + m[8] > 0) {
+    q[0] = 0.5 * sqrt(1 + m[0] + m[4] + m[8]);
+    q[1] = 0.25 * (m[7] - m[5]) / q[0]; q[2] = 0.25 * (m[2] - m[6]) / q[0]; q[3] = 0.25 * (m[3] - m[1]) / q[0];
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    q[1] = 0.5 * sqrt(1 + m[0] - m[4] - m[8]);
+    q[0] = 0.25 * (m[7] - m[5]) / q[1]; q[2] = 0.25 * (m[1] + m[3]) / q[1]; q[3] = 0.25 * (m[2] + m[6]) / q[1];
+  } else if (m[4] > m[8]) {
+    q[2] = 0.5 * sqrt(1 - m[0] + m[4] - m[8]);
+    q[0] = 0.25 * (m[2] - m[6]) / q[2]; q[1] = 0.25 * (m[1] + m[3]) / q[2]; q[3] = 0.25 * (m[5] + m[7]) / q[2];
+  } else {
+    q[3] = 0.5 * sqrt(1 - m[0] - m[4] + m[8]);
+    q[0] = 0.25 * (m[3] - m[1]) / q[3]; q[1] = 0.25 * (m[2] + m[6]) / q[3]; q[2] = 0.25 * (m[5] + m[7]) / q[3];
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+__device__ __forceinline__ void mulquat_d(double* r, const double* a, const double* b) {
+  double t0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double t1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+// EEF site position from the frames in shared memory (its orientation is the body's: the site has no own rotation)
+template <class S>
+__device__ __forceinline__ void eef_pos_of(const S& s, double* pos) {
+  const int eb = MDL.d.eef_body;
+  const double* R = s.xmat + eb * 9;
+  const double* ep = MDL.d.eef_pos;
+#pragma unroll
+  for (int r = 0; r < 3; r++) pos[r] = s.xpos[eb * 3 + r] + R[3 * r] * ep[0] + R[3 * r + 1] * ep[1] + R[3 * r + 2] * ep[2];
+}
+// target pose of this env-step from the (stale) site pose and the clipped float32 action
+template <class S>
+__device__ void ik_target(S& s, const mcb_task_cfg& cfg, const float* act, int lane) {
+  if (lane == 0) {
+    double pos[3];
+    eef_pos_of(s, pos);
+    for (int k = 0; k < 3; k++) s.ik[k] = pos[k] + (double)(act[k] * 0.2f);          // float32 product, float64 sum (numpy semantics)
+    if (cfg.fetch_env) { s.ik[3] = 0; s.ik[4] = -0.707; s.ik[5] = 0; s.ik[6] = 0.707; }
+    else {
+      double e0 = (double)(act[3] * 0.5f), e1 = (double)(act[4] * 0.5f), e2 = (double)(act[5] * 0.5f);
+      double ai = e2 / 2, aj = -e1 / 2, ak = e0 / 2;
+      double si, ci, sj, cj, sk, ck;
+      sincos(ai, &si, &ci); sincos(aj, &sj, &cj); sincos(ak, &sk, &ck);
+      double cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+      double qr[4] = {cj * cc + sj * ss, cj * cs - sj * sc, -(cj * ss + sj * cc), cj * sc - sj * cs};
+      double qe[4];
+      mat2quat_d(qe, s.xmat + MDL.d.eef_body * 9);
+      mulquat_d(s.ik + 3, qr, qe);
+    }
+  }
+  __syncwarp();
+}
+// one DLS solve: ctrl[0..5] += (J'J + 0.3 I)^-1 J' err, J = 6 x 6 site Jacobian w.r.t. the arm dofs (all other columns of
+// the reference's 6 x 18 Jacobian are zero for this site, so its 18 x 18 least-squares problem decouples exactly)
+template <class S>
+__device__ void ik_update_ctrl(S& s, int lane, double grip_ctrl) {
+  double* Jm = s.grad;          // 36 doubles of scratch: grad, search, Mv are contiguous and dead outside the solver
+  double site[3];
+  eef_pos_of(s, site);
+  if (lane == 0) {
+    for (int k = 0; k < 3; k++) s.ik[7 + k] = s.ik[k] - site[k];
+    double qe[4], neg[4], er[4];
+    mat2quat_d(qe, s.xmat + MDL.d.eef_body * 9);
+    neg[0] = qe[0]; neg[1] = -qe[1]; neg[2] = -qe[2]; neg[3] = -qe[3];
+    mulquat_d(er, s.ik + 3, neg);
+    double ax[3] = {er[1], er[2], er[3]};
+    double sn = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    if (sn < MINVAL) { ax[0] = 1; ax[1] = ax[2] = 0; } else { ax[0] /= sn; ax[1] /= sn; ax[2] /= sn; }
+    double speed = 2 * atan2(sn, er[0]);
+    if (speed > 3.14159265358979323846) speed -= 2 * 3.14159265358979323846;
+    speed /= 50;
+    for (int k = 0; k < 3; k++) s.ik[10 + k] = ax[k] * speed;
+  }
+  if (lane < 6) {
+    const double* cd = s.cdof + lane * 6;
+    double off[3] = {site[0] - MDL.d.ref_robot[0], site[1] - MDL.d.ref_robot[1], site[2] - MDL.d.ref_robot[2]};
+    double t[3];
+    cross3(t, cd, off);
+    Jm[0 * 6 + lane] = cd[3] + t[0]; Jm[1 * 6 + lane] = cd[4] + t[1]; Jm[2 * 6 + lane] = cd[5] + t[2];
+    Jm[3 * 6 + lane] = cd[0]; Jm[4 * 6 + lane] = cd[1]; Jm[5 * 6 + lane] = cd[2];
+  }
+  __syncwarp();
+  if (lane < 21) {
+    int i = MDL.tri_i[lane], j = MDL.tri_j[lane];
+    double h = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) h += Jm[k * 6 + i] * Jm[k * 6 + j];
+    if (i == j) h += 0.3;
+    s.H[lane] = h;
+  }
+  double b = 0;
+  if (lane < 6) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) b += Jm[k * 6 + lane] * s.ik[7 + k];
+  }
+  __syncwarp();
+  double dq = chol_solve_blk<0, 6>(s.H, s.H, 0.0, lane, b);
+  if (lane < 6) s.ctrl[lane] += dq;
+  else if (lane == 6) s.ctrl[6] = grip_ctrl;
+  __syncwarp();
+}
+
 // reset_model (mycobot.py:207-236): init state, forward, cube xy, forward, goal.  false: layout overflow.
 template <class S>
 __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* __restrict__ m, int lane, int env, int nba, int nva, unsigned long long& ctr) {
-  for (int w = lane; w < NQ; w += 32) s.qpos[w] = MDL.d.init_qpos[w];
+  for (int w = lane; w < NQ; w += 32) s.qpos[w] = init_qpos_of(a.cfg)[w];
   if (lane < NV) s.qvel[lane] = 0;
-  if (lane < NU) s.ctrl[lane] = MDL.d.init_ctrl[lane];
+  if (lane < NU) s.ctrl[lane] = init_ctrl_of(a.cfg)[lane];
   __syncwarp();
   if (!forward(s, m, lane, nba, nva, false)) return false;
-  double oxy[2] = {MDL.d.initial_gripper_xpos[0], MDL.d.initial_gripper_xpos[1]};
+  const double gx0 = grip0_of(a.cfg)[0], gy0 = grip0_of(a.cfg)[1];
+  double oxy[2] = {gx0, gy0};
   double g[3];
   if (lane == 0) {
     if (a.cfg.has_object) {
       if (a.inj_xy) { oxy[0] = a.inj_xy[(size_t)env * 2]; oxy[1] = a.inj_xy[(size_t)env * 2 + 1]; }
       else {
         int guard = 0;
-        while (sqrt((oxy[0] - MDL.d.initial_gripper_xpos[0]) * (oxy[0] - MDL.d.initial_gripper_xpos[0]) +
-                    (oxy[1] - MDL.d.initial_gripper_xpos[1]) * (oxy[1] - MDL.d.initial_gripper_xpos[1])) < 0.1 && guard++ < 10000) {
+        while (sqrt((oxy[0] - gx0) * (oxy[0] - gx0) + (oxy[1] - gy0) * (oxy[1] - gy0)) < 0.1 && guard++ < 10000) {
           sample_goal(m, a.cfg, a.seed, env, ctr, g);
           oxy[0] = g[0]; oxy[1] = g[1];
         }
@@ -1546,7 +1664,10 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
     s.goal[0] = g[0]; s.goal[1] = g[1]; s.goal[2] = g[2];
   }
   __syncwarp();
-  return forward(s, m, lane, nba, nva, false);
+  bool ok = forward(s, m, lane, nba, nva, false);
+  if (lane < 6) s.qprev[lane] = s.qpos[lane];     // frames are fresh after reset
+  __syncwarp();
+  return ok;
 }
 
 template <class S>
@@ -1641,29 +1762,72 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
     } else if (a.mode == MODE_FORWARD) {
       if (ok) ok = forward(s, m, lane, nba, nva, false);
       if (ok) {
+        if (lane < 6) s.qprev[lane] = s.qpos[lane];
+        __syncwarp();
         write_obs(s, m, cfg, lane, env, a.obs, a.ag, a.dg, achieved);
         if (a.debug && env == a.debug_env) debug_dump(s, a, lane, nva);
       }
       substeps = 1;
     } else {
-      // MyCobotEnv.step, joint controller: ctrl = clip(action, -1, 1) widened to double (mycobot.py:133,192-193)
-      if (ok && lane < NU) {
-        float act = a.actions[(size_t)env * NU + lane];
-        act = fminf(1.0f, fmaxf(-1.0f, act));
-        s.ctrl[lane] = (double)act;
+      const bool ik = cfg.controller_type == 1;
+      const int adim = (ik && cfg.fetch_env) ? 4 : NU;
+      float act[NU];
+#pragma unroll
+      for (int k = 0; k < NU; k++) act[k] = 0.0f;
+      if (ok) {
+        // action = clip(action, -1, 1) in float32 (mycobot.py:133)
+#pragma unroll
+        for (int k = 0; k < NU; k++) if (k < adim) act[k] = fminf(1.0f, fmaxf(-1.0f, a.actions[(size_t)env * adim + k]));
+      }
+      double grip_ctrl = 0;
+      int nblocks = 1;
+      if (!ik) {
+        // joint controller: ctrl = action widened to double (mycobot.py:192-193 -> MujocoEnv.do_simulation)
+        if (ok && lane < NU) {
+          float v = 0.0f;
+#pragma unroll
+          for (int k = 0; k < NU; k++) if (lane == k) v = act[k];
+          s.ctrl[lane] = (double)v;
+        }
+      } else {
+        // IK controller (mycobot.py:134-170): the target comes from the site pose the reference still holds from the
+        // previous step's last forward pass, i.e. from the frames at qprev
+        if (ok) {
+          double qsave = lane < 6 ? s.qpos[lane] : 0.0;
+          if (lane < 6) s.qpos[lane] = s.qprev[lane];
+          __syncwarp();
+          fk(s, m, lane, NB - 1);
+          cinert_cdof(s, m, lane, NB - 1, NH);
+          if (lane < 6) s.qpos[lane] = qsave;
+          __syncwarp();
+          ik_target(s, cfg, act, lane);
+        }
+        float ag = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NU; k++) if (k == adim - 1) ag = act[k];
+        grip_ctrl = 0.5 + (double)ag * 0.5;          // actuation_center + action[-1] * actuation_range (mycobot.py:158-160)
+        nblocks = cfg.control_steps;
       }
       __syncwarp();
-      for (int it = 0; it < cfg.frame_skip; it++) {
-        if (ok) ok = forward(s, m, lane, nba, nva, lockstep);
-        else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) __syncthreads(); }
-        if (lockstep) __syncthreads();
-        if (ok) euler(s, m, lane, nva);
+      for (int blk = 0; blk < nblocks; blk++) {
+        if (ik && ok) ik_update_ctrl(s, lane, grip_ctrl);
+        for (int it = 0; it < cfg.frame_skip; it++) {
+          if (ok) ok = forward(s, m, lane, nba, nva, lockstep);
+          else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) __syncthreads(); }
+          if (lockstep) __syncthreads();
+          if (ok) {
+            if (lane < 6) s.qprev[lane] = s.qpos[lane];     // the frames now in shared memory belong to this qpos
+            euler(s, m, lane, nva);
+          }
+        }
       }
-      substeps = cfg.frame_skip;
+      substeps = cfg.frame_skip * nblocks;
       if (ok && cfg.block_gripper) {  // _step_callback (mycobot.py:300-306)
         if (lane == 0) { s.qpos[7] = 0; s.qpos[9] = 0; }
         __syncwarp();
         ok = forward(s, m, lane, nba, nva, false);
+        if (lane < 6) s.qprev[lane] = s.qpos[lane];
+        __syncwarp();
         substeps++;
       }
       if (ok) {
@@ -1746,28 +1910,32 @@ __global__ void reward_kernel(const double* __restrict__ ag, const double* __res
   else ((double*)out)[i] = -d;
 }
 
-__global__ void init_state_kernel(double* state, int* elapsed, double* ep_return, unsigned long long* ctr, const DevModel* m, int n) {
+__global__ void init_state_kernel(double* state, int* elapsed, double* ep_return, unsigned long long* ctr, const DevModel* m, int n, int fetch) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
   for (int k = 0; k < MCB_STATE_STRIDE; k++) st[k] = 0;
-  for (int k = 0; k < NQ; k++) st[k] = m->d.init_qpos[k];
-  for (int k = 0; k < NU; k++) st[37 + k] = m->d.init_ctrl[k];
+  const double* q0 = fetch ? m->d.key_qpos : m->d.init_qpos;
+  const double* c0 = fetch ? m->d.key_ctrl : m->d.init_ctrl;
+  for (int k = 0; k < NQ; k++) st[k] = q0[k];
+  for (int k = 0; k < NU; k++) st[37 + k] = c0[k];
+  for (int k = 0; k < 6; k++) st[65 + k] = q0[k];
   elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
 }
 
 // gather / scatter between the resident state record and caller arrays
-__global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int* el, int write) {
+__global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int* el, double* qprev, int write) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
   if (write) {
-    if (qpos) for (int k = 0; k < NQ; k++) st[k] = qpos[(size_t)i * NQ + k];
+    if (qpos) { for (int k = 0; k < NQ; k++) st[k] = qpos[(size_t)i * NQ + k]; for (int k = 0; k < 6; k++) st[65 + k] = st[k]; }
     if (qvel) for (int k = 0; k < NV; k++) st[19 + k] = qvel[(size_t)i * NV + k];
     if (ctrl) for (int k = 0; k < NU; k++) st[37 + k] = ctrl[(size_t)i * NU + k];
     if (warm) for (int k = 0; k < NV; k++) st[44 + k] = warm[(size_t)i * NV + k];
     if (goal) for (int k = 0; k < 3; k++) st[62 + k] = goal[(size_t)i * 3 + k];
     if (el) elapsed[i] = el[i];
+    if (qprev) for (int k = 0; k < 6; k++) st[65 + k] = qprev[(size_t)i * 6 + k];
   } else {
     if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = st[k];
     if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = st[19 + k];
@@ -1775,6 +1943,7 @@ __global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos
     if (warm) for (int k = 0; k < NV; k++) warm[(size_t)i * NV + k] = st[44 + k];
     if (goal) for (int k = 0; k < 3; k++) goal[(size_t)i * 3 + k] = st[62 + k];
     if (el) el[i] = elapsed[i];
+    if (qprev) for (int k = 0; k < 6; k++) qprev[(size_t)i * 6 + k] = st[65 + k];
   }
 }
 
@@ -1844,8 +2013,8 @@ extern "C" {
 
 const char* mcb_version(void) {
   static char buf[160];
-  snprintf(buf, sizeof buf, "mycobot_b200 0.2 (sm_100a; shared memory per env: %zu B common layout, %zu B fallback layout)",
-           sizeof(EnvS<false>), sizeof(EnvS<true>));
+  snprintf(buf, sizeof buf, "mycobot_b200 0.3 (sm_100a; shared memory per env: %zu B common layout, %zu B fallback layout; model %zu B; CTA %zu B)",
+           sizeof(EnvS<false>), sizeof(EnvS<true>), (size_t)MODEL_BYTES, (size_t)(MODEL_BYTES + sizeof(EnvS<false>) * WPB_SMALL));
   return buf;
 }
 const char* mcb_last_error(void) { return g_err.c_str(); }
@@ -1919,6 +2088,9 @@ int32_t mcb_model_destroy(mcb_model* m) {
 
 int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out) {
   if (!m || !cfg || !out || n_envs <= 0) return fail("mcb_batch_create: bad argument");
+  if (cfg->controller_type < 0 || cfg->controller_type > 1) return fail("mcb_batch_create: controller_type must be 0 (joint) or 1 (IK)");
+  if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
+  if (cfg->controller_type == 1 && (cfg->control_steps < 1 || cfg->control_steps > 50)) return fail("mcb_batch_create: control_steps out of range");
   if (cfg->reward_type < 0 || cfg->reward_type > 2 || (cfg->reward_type == 2 && !cfg->has_object)) return fail("mcb_batch_create: reward_type must be 0, 1 or 2 (2 needs has_object)");
   CK(cudaSetDevice(m->device));
   mcb_batch* b = new mcb_batch();
@@ -1947,7 +2119,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   CK(cudaMemset(b->redo_count, 0, sizeof(int)));
   CK(cudaMalloc(&b->debug, DEBUG_DOUBLES * sizeof(double)));
   CK(cudaMemset(b->stats, 0, 8 * sizeof(double)));
-  init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs);
+  init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs, cfg->fetch_env);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   *out = b;
@@ -1964,6 +2136,7 @@ int32_t mcb_batch_destroy(mcb_batch* b) {
 }
 int32_t mcb_batch_num_envs(const mcb_batch* b) { return b ? b->n_envs : -1; }
 int32_t mcb_batch_obs_dim(const mcb_batch* b) { return b ? b->obs_dim : -1; }
+int32_t mcb_batch_action_dim(const mcb_batch* b) { return b ? ((b->cfg.controller_type == 1 && b->cfg.fetch_env) ? 4 : NU) : -1; }
 
 int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals, double* obs, double* ag, double* dg, void* stream) {
   if (!b) return fail("mcb_reset: null batch");
@@ -2002,17 +2175,17 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
   return total;
 }
 
-int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int32_t* elapsed, void* stream) {
+int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int32_t* elapsed, double* qprev, void* stream) {
   if (!b) return fail("mcb_get_state: null batch");
-  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, 0);
+  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, qprev, 0);
   CK(cudaGetLastError());
   return 0;
 }
 int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const double* goal,
-                      const int32_t* elapsed, void* stream) {
+                      const int32_t* elapsed, const double* qprev, void* stream) {
   if (!b) return fail("mcb_set_state: null batch");
   state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, (double*)qpos, (double*)qvel, (double*)ctrl,
-                                                                             (double*)warm, (double*)goal, (int*)elapsed, 1);
+                                                                             (double*)warm, (double*)goal, (int*)elapsed, (double*)qprev, 1);
   CK(cudaGetLastError());
   return 0;
 }
@@ -2038,9 +2211,10 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
   if (!b || !h_actions) return fail("mcb_step_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   size_t N = (size_t)b->n_envs, od = (size_t)b->obs_dim;
+  const size_t ad = (size_t)mcb_batch_action_dim(b);
   size_t rbytes = b->cfg.reward_type == 0 ? sizeof(float) : sizeof(double);
   if (!b->d_actions) {
-    CK(cudaMalloc(&b->d_actions, N * NU * sizeof(float)));
+    CK(cudaMalloc(&b->d_actions, N * ad * sizeof(float)));
     CK(cudaMalloc(&b->d_obs, N * od * sizeof(double)));
     CK(cudaMalloc(&b->d_fobs, N * od * sizeof(double)));
     CK(cudaMallocHost(&b->h_fobs, N * od * sizeof(double)));
@@ -2048,15 +2222,15 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
     CK(cudaMalloc(&b->d_dg, N * 3 * sizeof(double)));
     CK(cudaMalloc(&b->d_reward, N * sizeof(double)));
     CK(cudaMalloc(&b->d_flags, N * 3));
-    CK(cudaMallocHost(&b->h_actions, N * NU * sizeof(float)));
+    CK(cudaMallocHost(&b->h_actions, N * ad * sizeof(float)));
     CK(cudaMallocHost(&b->h_obs, N * od * sizeof(double)));
     CK(cudaMallocHost(&b->h_ag, N * 3 * sizeof(double)));
     CK(cudaMallocHost(&b->h_dg, N * 3 * sizeof(double)));
     CK(cudaMallocHost(&b->h_reward, N * sizeof(double)));
     CK(cudaMallocHost(&b->h_flags, N * 3));
   }
-  memcpy(b->h_actions, h_actions, N * NU * sizeof(float));
-  CK(cudaMemcpyAsync(b->d_actions, b->h_actions, N * NU * sizeof(float), cudaMemcpyHostToDevice, st));
+  memcpy(b->h_actions, h_actions, N * ad * sizeof(float));
+  CK(cudaMemcpyAsync(b->d_actions, b->h_actions, N * ad * sizeof(float), cudaMemcpyHostToDevice, st));
   if (mcb_step(b, b->d_actions, b->d_obs, b->d_ag, b->d_dg, b->d_reward, b->d_flags, b->d_flags + N, b->d_flags + 2 * N,
                h_final_obs ? b->d_fobs : nullptr, stream)) return -1;
   if (h_final_obs) CK(cudaMemcpyAsync(b->h_fobs, b->d_fobs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -49,6 +49,7 @@ class ModelDesc(C.Structure):
         ("timestep", _d), ("gravity", _d * 3), ("tolerance", _d), ("ls_tolerance", _d), ("meaninertia", _d),
         ("impratio", _d), ("iterations", _i), ("ls_iterations", _i),
         ("initial_gripper_xpos", _d * 3), ("height_offset", _d), ("init_qpos", _d * NQ), ("init_ctrl", _d * NU),
+        ("key_initial_gripper_xpos", _d * 3), ("key_height_offset", _d), ("key_qpos", _d * NQ), ("key_ctrl", _d * NU),
     ]
 
 
@@ -56,6 +57,7 @@ class TaskCfg(C.Structure):
     _fields_ = [
         ("has_object", _i), ("block_gripper", _i), ("target_in_the_air", _i), ("reward_type", _i),
         ("max_episode_steps", _i), ("frame_skip", _i), ("auto_reset", _i), ("nefc_max", _i),
+        ("controller_type", _i), ("fetch_env", _i), ("control_steps", _i), ("reserved_", _i),
         ("distance_threshold", _d),
     ]
 
@@ -236,6 +238,7 @@ def reduce_model(m) -> ModelDesc:
     w = int(m["body_weldid"][sb])
     pos, quat = _rel_pose(m, sb, w)
     d.eef_body = jidx[w]
+    assert abs(abs(quat[0]) - 1) < 1e-12 and np.all(m["site_quat"][s_eef] == [1, 0, 0, 0]), "EEF site must share its body's orientation"
     _set(d.eef_pos, pos + quat2mat(quat) @ m["site_pos"][s_eef])
     ob = int(m["site_bodyid"][s_obj])
     assert ob in jidx and np.all(m["site_pos"][s_obj] == 0)
@@ -264,4 +267,12 @@ def reduce_model(m) -> ModelDesc:
     d.height_offset = float((xpos[ob] + xmat[ob] @ m["site_pos"][s_obj])[2])
     _set(d.init_qpos, m["qpos0"])
     _set(d.init_ctrl, np.zeros(NU))
+    # fetch envs: mj_resetDataKeyframe(0) then forward (mycobot.py:451-472)
+    kq = m["key_qpos"][0].copy()
+    kq[15:19] /= np.linalg.norm(kq[15:19])
+    fkk = mjcf.fk_numpy(m, kq)
+    _set(d.key_initial_gripper_xpos, fkk[0][seb] + fkk[2][seb] @ m["site_pos"][s_eef])
+    d.key_height_offset = float((fkk[0][ob] + fkk[2][ob] @ m["site_pos"][s_obj])[2])
+    _set(d.key_qpos, m["key_qpos"][0])
+    _set(d.key_ctrl, m["key_ctrl"][0])
     return d

@@ -7,8 +7,8 @@ attrs `goal`, `distance_threshold`, `reward_type`) for `num_envs` environments a
 and task logic runs in the CUDA library behind include/mycobot_b200.h; torch only owns the device
 buffers and the stream.  TimeLimit(50) (mycobotgym/__init__.py:34) is folded into the kernel.
 
-Only the joint controller is built (ids `MyCobot{Reach,PickAndPlace}-{Dense,Sparse}-joint-v0`);
-IK / mocap / reward_shaping raise NotImplementedError (SURVEY.md section 8f "next" rows).
+Built controllers: joint (`...-joint-v0`) and IK incl. the Fetch variants (`...-IK-v0`, `MyCobotFetch...-IK-v0`);
+mocap ids and the image envs (`-v1`) raise NotImplementedError (SURVEY.md section 8f "next" rows).
 """
 from __future__ import annotations
 
@@ -156,10 +156,10 @@ class MyCobotVectorEnv:
                  distance_threshold=0.01, initial_qpos=None, fetch_env=False, reward_type="sparse", frame_skip=20,
                  max_episode_steps=50, device="cuda:0", seed=0, auto_reset=True, goal_source="device", nefc_max=0,
                  **kwargs):
-        if controller_type != "joint":
-            raise NotImplementedError(f"controller_type={controller_type!r}: only the joint controller is built (SURVEY 8f)")
-        if fetch_env:
-            raise NotImplementedError("fetch_env: joint controller is not supported for Fetch envs (mycobot.py:96)")
+        if controller_type not in ("joint", "IK"):
+            raise NotImplementedError(f"controller_type={controller_type!r}: the joint and IK controllers are built; mocap is a 'next' row (SURVEY 8f)")
+        if fetch_env and controller_type == "joint":
+            raise AssertionError("Joint controller not supported for Fetch env")        # mycobot.py:96
         if reward_type not in ("sparse", "dense", "reward_shaping"):
             raise ValueError(f"unknown reward_type {reward_type!r}")
         if reward_type == "reward_shaping" and not has_object:
@@ -187,13 +187,15 @@ class MyCobotVectorEnv:
             has_object=int(has_object), block_gripper=int(block_gripper), target_in_the_air=int(target_in_the_air),
             reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,
             frame_skip=self.frame_skip, auto_reset=int(self.auto_reset and goal_source == "device"), nefc_max=int(nefc_max),
-            distance_threshold=self.distance_threshold)
+            controller_type=0 if controller_type == "joint" else 1, fetch_env=int(bool(fetch_env)), control_steps=int(control_steps),
+            reserved_=0, distance_threshold=self.distance_threshold)
         self._cfg = cfg
         with torch.cuda.device(dev_index):
             h = C.c_void_p()
             _lib.check(self._L.mcb_batch_create(self._model, self.num_envs, C.byref(cfg), int(seed), C.byref(h)))
         self._batch = h
         self.obs_dim = self._L.mcb_batch_obs_dim(h)
+        self.action_dim = self._L.mcb_batch_action_dim(h)          # 7, or 4 for the fetch IK variant (mycobot.py:90-97)
         N, dev = self.num_envs, self.device
         f64 = torch.float64
         self._obs = torch.zeros(N, self.obs_dim, dtype=f64, device=dev)
@@ -205,12 +207,12 @@ class MyCobotVectorEnv:
         self._trunc = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._succ = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._stats = torch.zeros(8, dtype=f64, device=dev)
-        self.initial_gripper_xpos = np.array(self._desc.initial_gripper_xpos[:])
-        self.height_offset = float(self._desc.height_offset)
+        self.initial_gripper_xpos = np.array((self._desc.key_initial_gripper_xpos if fetch_env else self._desc.initial_gripper_xpos)[:])
+        self.height_offset = float(self._desc.key_height_offset if fetch_env else self._desc.height_offset)
         self._sampler = ReferenceGoalSampler(N, self.height_offset, self.initial_gripper_xpos[:2], self.has_object,
                                              self.target_in_the_air)
-        self.single_action_space = Box(-1.0, 1.0, (7,), np.float32)
-        self.action_space = Box(-1.0, 1.0, (N, 7), np.float32)
+        self.single_action_space = Box(-1.0, 1.0, (self.action_dim,), np.float32)
+        self.action_space = Box(-1.0, 1.0, (N, self.action_dim), np.float32)
         self.single_observation_space = Dict(
             desired_goal=Box(-np.inf, np.inf, (3,), np.float64), achieved_goal=Box(-np.inf, np.inf, (3,), np.float64),
             observation=Box(-np.inf, np.inf, (self.obs_dim,), np.float64))
@@ -257,8 +259,8 @@ class MyCobotVectorEnv:
         torch CUDA tensor (or anything convertible)."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
-        if tuple(actions.shape) != (self.num_envs, 7):
-            raise ValueError(f"Action dimension mismatch. Expected {(self.num_envs, 7)}, found {tuple(actions.shape)}")
+        if tuple(actions.shape) != (self.num_envs, self.action_dim):
+            raise ValueError(f"Action dimension mismatch. Expected {(self.num_envs, self.action_dim)}, found {tuple(actions.shape)}")
         actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_step(self._batch, _ptr(actions), _ptr(self._obs), _ptr(self._ag), _ptr(self._dg),
@@ -298,13 +300,14 @@ class MyCobotVectorEnv:
         N, dev = self.num_envs, self.device
         st = dict(qpos=torch.empty(N, 19, dtype=torch.float64, device=dev), qvel=torch.empty(N, 18, dtype=torch.float64, device=dev),
                   ctrl=torch.empty(N, 7, dtype=torch.float64, device=dev), qacc_warmstart=torch.empty(N, 18, dtype=torch.float64, device=dev),
-                  goal=torch.empty(N, 3, dtype=torch.float64, device=dev), elapsed=torch.empty(N, dtype=torch.int32, device=dev))
+                  goal=torch.empty(N, 3, dtype=torch.float64, device=dev), elapsed=torch.empty(N, dtype=torch.int32, device=dev),
+                  qprev=torch.empty(N, 6, dtype=torch.float64, device=dev))
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_get_state(self._batch, _ptr(st["qpos"]), _ptr(st["qvel"]), _ptr(st["ctrl"]),
-                                            _ptr(st["qacc_warmstart"]), _ptr(st["goal"]), _ptr(st["elapsed"]), self._stream()))
+                                            _ptr(st["qacc_warmstart"]), _ptr(st["goal"]), _ptr(st["elapsed"]), _ptr(st["qprev"]), self._stream()))
         return st
 
-    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None):
+    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None, qprev=None):
         def prep(x, shape, dt):
             if x is None:
                 return None
@@ -314,7 +317,8 @@ class MyCobotVectorEnv:
 
         N = self.num_envs
         ts = [prep(qpos, (N, 19), torch.float64), prep(qvel, (N, 18), torch.float64), prep(ctrl, (N, 7), torch.float64),
-              prep(qacc_warmstart, (N, 18), torch.float64), prep(goal, (N, 3), torch.float64), prep(elapsed, (N,), torch.int32)]
+              prep(qacc_warmstart, (N, 18), torch.float64), prep(goal, (N, 3), torch.float64), prep(elapsed, (N,), torch.int32),
+              prep(qprev, (N, 6), torch.float64)]
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_set_state(self._batch, *[_ptr(t) for t in ts], self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
@@ -356,7 +360,7 @@ class MyCobotVectorEnv:
     def step_host(self, actions_np, out=None, want_final_obs=False):
         """The same step through HOST buffers (numpy): H2D of actions and D2H of all results inside the call."""
         a = np.ascontiguousarray(actions_np, dtype=np.float32)
-        assert a.shape == (self.num_envs, 7)
+        assert a.shape == (self.num_envs, self.action_dim)
         N = self.num_envs
         if out is None:
             out = dict(observation=np.empty((N, self.obs_dim)), achieved_goal=np.empty((N, 3)), desired_goal=np.empty((N, 3)),

@@ -256,12 +256,72 @@ class ReferenceSampler:
         return np.array(goal)
 
 
+# ----------------------------------------------------------------------------------------
+# helpers of the IK branch: mujoco.mju_mat2Quat / mju_mulQuat / mju_negQuat / mju_quat2Vel (engine_util_spatial.c)
+# and gymnasium_robotics.utils.rotations.euler2quat, restated
+
+
+def mju_mat2quat(mat):
+    m = np.asarray(mat, dtype=np.float64).ravel()
+    q = np.zeros(4)
+    if m[0] + m[4] + m[8] > 0:
+        q[0] = 0.5 * np.sqrt(1 + m[0] + m[4] + m[8])
+        q[1] = 0.25 * (m[7] - m[5]) / q[0]
+        q[2] = 0.25 * (m[2] - m[6]) / q[0]
+        q[3] = 0.25 * (m[3] - m[1]) / q[0]
+    elif m[0] > m[4] and m[0] > m[8]:
+        q[1] = 0.5 * np.sqrt(1 + m[0] - m[4] - m[8])
+        q[0] = 0.25 * (m[7] - m[5]) / q[1]
+        q[2] = 0.25 * (m[1] + m[3]) / q[1]
+        q[3] = 0.25 * (m[2] + m[6]) / q[1]
+    elif m[4] > m[8]:
+        q[2] = 0.5 * np.sqrt(1 - m[0] + m[4] - m[8])
+        q[0] = 0.25 * (m[2] - m[6]) / q[2]
+        q[1] = 0.25 * (m[1] + m[3]) / q[2]
+        q[3] = 0.25 * (m[5] + m[7]) / q[2]
+    else:
+        q[3] = 0.5 * np.sqrt(1 - m[0] - m[4] + m[8])
+        q[0] = 0.25 * (m[3] - m[1]) / q[3]
+        q[1] = 0.25 * (m[2] + m[6]) / q[3]
+        q[2] = 0.25 * (m[5] + m[7]) / q[3]
+    return q / np.linalg.norm(q)
+
+
+def mju_mulquat(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                     a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+                     a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def mju_quat2vel(quat, dt):
+    axis = np.array(quat[1:4], dtype=np.float64)
+    sin_a_2 = np.linalg.norm(axis)
+    axis = axis / sin_a_2 if sin_a_2 >= 1e-15 else np.array([1.0, 0, 0])
+    speed = 2 * np.arctan2(sin_a_2, quat[0])
+    if speed > np.pi:
+        speed -= 2 * np.pi
+    return axis * (speed / dt)
+
+
+def euler2quat(euler):
+    euler = np.asarray(euler, dtype=np.float64)
+    ai, aj, ak = euler[2] / 2, -euler[1] / 2, euler[0] / 2
+    si, sj, sk = np.sin(ai), np.sin(aj), np.sin(ak)
+    ci, cj, ck = np.cos(ai), np.cos(aj), np.cos(ak)
+    cc, cs, sc, ss = ci * ck, ci * sk, si * ck, si * sk
+    return np.array([cj * cc + sj * ss, cj * cs - sj * sc, -(cj * ss + sj * cc), cj * sc - sj * cs])
+
+
 class OracleEnv:
-    """Restatement of MyCobotEnv (joint controller) + TimeLimit(50) on the CPU oracle."""
+    """Restatement of MyCobotEnv (joint and IK controllers, incl. the Fetch IK variant) + TimeLimit(50) on the CPU oracle."""
 
     def __init__(self, flat, has_object=True, block_gripper=False, target_in_the_air=True, distance_threshold=0.01,
-                 reward_type="sparse", frame_skip=20, max_episode_steps=50):
+                 reward_type="sparse", frame_skip=20, max_episode_steps=50, controller_type="joint", fetch_env=False,
+                 control_steps=5):
         self.flat = flat
+        self.controller_type, self.fetch_env, self.control_steps = controller_type, fetch_env, control_steps
+        assert controller_type in ("joint", "IK") and not (fetch_env and controller_type == "joint")
         self.has_object, self.block_gripper = has_object, block_gripper
         self.target_in_the_air, self.distance_threshold = target_in_the_air, distance_threshold
         self.reward_type, self.frame_skip, self.max_episode_steps = reward_type, frame_skip, max_episode_steps
@@ -273,7 +333,11 @@ class OracleEnv:
         self.j_rf, self.j_lf = jn.index("right_finger_joint"), jn.index("left_finger_joint")
         self.j_obj = jn.index("object0:joint")
         self.goal = np.zeros(3)
-        # _env_setup (mycobot.py:450-481), non-fetch
+        # _env_setup (mycobot.py:450-481): fetch envs start from keyframe 0 (mycobot280.xml:4-9)
+        if fetch_env:
+            self.sim.qpos[:] = flat["key_qpos"][0]
+            self.sim.qvel[:] = flat["key_qvel"][0]
+            self.sim.ctrl[:] = flat["key_ctrl"][0]
         self.sim.forward()
         self.initial_gripper_xpos = self.sim.site_xpos[self.site_eef].copy()
         self.height_offset = float(self.sim.site_xpos[self.site_obj][2])
@@ -363,11 +427,39 @@ class OracleEnv:
         self.elapsed = 0
         return self._get_obs(), {}
 
+    # mycobotgym/utils.py:499-556 (IKController.compute_qpos_delta / solve_DLS)
+    def _ik_delta(self, target_pos, target_quat):
+        s = self.sim
+        err = np.empty(6)
+        err[:3] = target_pos - s.site_xpos[self.site_eef]
+        eef_q = mju_mat2quat(s.site_xmat[self.site_eef])
+        neg = np.array([eef_q[0], -eef_q[1], -eef_q[2], -eef_q[3]])
+        err[3:] = mju_quat2vel(mju_mulquat(target_quat, neg), 50)
+        jp, jr = s.jac_site(self.site_eef)
+        jac = np.concatenate((jp, jr), axis=0)
+        hess = jac.T.dot(jac) + np.eye(jac.shape[1]) * 0.3
+        return np.linalg.lstsq(hess, jac.T.dot(err), rcond=-1)[0]
+
     def step(self, action):
         action = np.clip(np.asarray(action, dtype=np.float32), np.float32(-1.0), np.float32(1.0))
         s = self.sim
-        s.ctrl[:] = action.astype(np.float64)  # do_simulation: ctrl[:] = action (absolute; mycobot.py:192-193)
-        s.step(self.frame_skip)
+        if self.controller_type == "IK":      # mycobot.py:134-170
+            target_pos = s.site_xpos[self.site_eef] + action[:3] * np.float32(0.2)     # float32 product, float64 sum
+            if self.fetch_env:
+                target_quat = np.array([0, -0.707, 0, 0.707])
+            else:
+                quat_rot = euler2quat(action[3:6] * np.float32(0.5))
+                target_quat = mju_mulquat(quat_rot, mju_mat2quat(s.site_xmat[self.site_eef]))
+            ctrl_action = np.zeros(7)
+            ctrl_action[-1] = 0.5 + np.float64(action[-1]) * 0.5                         # actuation_center / range of ctrlrange [0, 1]
+            for _ in range(self.control_steps):
+                delta = self._ik_delta(target_pos, target_quat)
+                ctrl_action[:6] = s.ctrl[:6] + delta[:6]
+                s.ctrl[:] = ctrl_action
+                s.step(self.frame_skip)
+        else:
+            s.ctrl[:] = action.astype(np.float64)  # do_simulation: ctrl[:] = action (absolute; mycobot.py:192-193)
+            s.step(self.frame_skip)
         if self.block_gripper:  # mycobot.py:300-306
             s.qpos[self.flat["jnt_qposadr"][self.j_rf]] = 0.0
             s.qpos[self.flat["jnt_qposadr"][self.j_lf]] = 0.0

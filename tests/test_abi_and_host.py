@@ -57,10 +57,11 @@ def test_registry_matches_reference_registration():
 
 
 def test_unbuilt_rows_fail_loudly():
-    for kwargs in (dict(controller_type="IK"), dict(controller_type="mocap"), dict(reward_type="reward_shaping", has_object=False),
-                   dict(fetch_env=True)):
+    for kwargs in (dict(controller_type="mocap"), dict(reward_type="reward_shaping", has_object=False)):
         with pytest.raises(NotImplementedError):
             vector_env.MyCobotVectorEnv(num_envs=1, **kwargs)
+    with pytest.raises(AssertionError):                      # mycobot.py:96
+        vector_env.MyCobotVectorEnv(num_envs=1, fetch_env=True, controller_type="joint")
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure path")

@@ -421,3 +421,68 @@ def test_sb3_shaped_adapter():
     r = ve.env_method("compute_reward", np.zeros((7, 3)), np.full((7, 3), 0.1), None)[0]
     assert r.shape == (7,) and np.all(r == -1.0)
     ve.close()
+
+
+@pytest.mark.parametrize("fetch_env,has_object", [(False, True), (True, True), (False, False)])
+def test_ik_controller_matches_oracle(flat, fetch_env, has_object):
+    # IK controller (mycobot.py:134-170, utils.py:499-556), 5 x (DLS solve + 20 substeps) per env-step.
+    # Every step is a single-step comparison: before it the oracle is re-synchronised to the GPU state, including the
+    # STALE site frames the reference's IK reads (kinematics at qprev).  Step 0 starts from fresh frames (reset).
+    from oracle.oracle import OracleEnv
+
+    n, adim = 6, (4 if fetch_env else 7)
+    env = _env(num_envs=n, has_object=has_object, reward_type="dense", controller_type="IK", fetch_env=fetch_env, auto_reset=False,
+               goal_source="reference")
+    assert env.action_dim == adim and env.single_action_space.shape == (adim,)
+    oes = [OracleEnv(flat, has_object=has_object, reward_type="dense", controller_type="IK", fetch_env=fetch_env) for _ in range(n)]
+    ftight = mjcf_tight(flat)
+    oes_tight = [OracleEnv(ftight, has_object=has_object, reward_type="dense", controller_type="IK", fetch_env=fetch_env) for _ in range(n)]
+    random.seed(11)
+    xy, goals = [], []
+    for i, oe in enumerate(oes):
+        oe.reset(seed=100 + i)
+        xy.append(oe.sim.qpos[12:14].copy()); goals.append(oe.goal.copy())
+        oes_tight[i].goal = oe.goal.copy()
+    obs, _ = env.reset(object_xy=np.array(xy) if has_object else None, goals=np.array(goals))
+    assert abs(env.height_offset - oes[0].height_offset) < 1e-12
+    np.testing.assert_allclose(env.initial_gripper_xpos, oes[0].initial_gripper_xpos, atol=1e-12)
+    rng = np.random.default_rng(12)
+    nq, nv = (19, 18) if has_object else (12, 12)
+
+    def sync(oe, st, i):
+        q_stale = st["qpos"][i].copy()
+        q_stale[:6] = st["qprev"][i]
+        oe.sim.set_state(q_stale, st["qvel"][i], st["ctrl"][i], st["qacc_warmstart"][i])
+        oe.sim.kinematics()                                   # the frames the reference still holds from its last mj_step
+        oe.sim.qpos[:] = st["qpos"][i]
+
+    for t in range(3):
+        st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+        for i in range(n):
+            sync(oes[i], st, i)
+            sync(oes_tight[i], st, i)
+            oes_tight[i].sim.qvel[:6] *= 1 + 2.2e-16          # ... and a one-ulp perturbation of the arm velocities
+        assert t == 0 or np.abs(st["qprev"] - st["qpos"][:, :6]).max() > 1e-6        # stale path really exercised
+        acts = rng.uniform(-1, 1, (n, adim)).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
+        after = env.get_state()
+        for i, oe in enumerate(oes):
+            o, r, te, tr, inf = oe.step(acts[i])
+            oes_tight[i].step(acts[i])
+            # 100 substeps of the bang-bang PD loop are chaotic: a one-ulp change of qvel can move the result by
+            # 1e-7.  The bound is 1e-7 or 100x what a one-ulp perturbation + solver tolerance 1e-13 moves the oracle itself (<= 1e-4).
+            sens = np.abs(oes_tight[i].sim.qpos[:nq] - oe.sim.qpos[:nq]).max()
+            tol = min(max(1e-7, 100 * sens), 1e-4)      # the GPU differs from the oracle in many roundings, not in one ulp
+            np.testing.assert_allclose(after["qpos"][i, :nq].cpu().numpy(), oe.sim.qpos[:nq], atol=tol, rtol=0, err_msg=f"step {t} env {i}")
+            np.testing.assert_allclose(after["ctrl"][i].cpu().numpy(), oe.sim.ctrl, atol=tol, rtol=0, err_msg=f"ctrl step {t} env {i}")
+            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol * 10, rtol=0)
+            assert abs(float(rew[i]) - float(r)) < tol * 10 and bool(term[i]) == te
+    env.close()
+
+
+def mjcf_tight(flat):
+    from mycobotgym_b200 import mjcf
+
+    f = mjcf.FlatModel(flat)
+    f["tolerance"] = 1e-13
+    return f

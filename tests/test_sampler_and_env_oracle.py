@@ -131,3 +131,32 @@ def test_staged_reward_on_the_oracle(flat):
     tgt = np.array([-0.15, 0.0, 0.21])                       # target0 site, mycobot280_main.xml:83
     lift = 0.5 + (1 - np.tanh(np.linalg.norm(o["observation"][3:6] - tgt))) * 0.4
     assert r == pytest.approx(lift * 100, abs=1e-9) and r > 50
+
+
+def test_ik_controller_on_the_oracle(flat):
+    # mycobot.py:134-170 + utils.py:499-556: the EEF site is driven towards current_pos + 0.2 * action[:3]
+    for fetch in (False, True):
+        env = OracleEnv(flat, has_object=True, controller_type="IK", fetch_env=fetch)
+        random.seed(0)
+        o, _ = env.reset(seed=0)
+        g0 = o["observation"][:3].copy()
+        if fetch:
+            assert abs(env.height_offset - 0.209981) < 1e-9                     # keyframe cube height (mycobot280.xml:6)
+            np.testing.assert_allclose(env.initial_gripper_xpos, [-0.05154491, 0.01053502, 0.3448586], atol=5e-9)
+        a = np.zeros(4 if fetch else 7, dtype=np.float32)
+        a[0] = 0.5
+        for _ in range(3):
+            o, r, te, tr, info = env.step(a)
+        moved = o["observation"][:3] - g0
+        assert 0.03 < moved[0] < 0.3 and abs(moved[1]) < 0.05
+        assert abs(env.sim.ctrl[6] - 0.5) < 1e-15                                # gripper: centre + 0 * range
+    # the reference solves an 18 x 18 damped least-squares problem; only the 6 arm columns of the site Jacobian are non-zero
+    env = OracleEnv(flat, has_object=True, controller_type="IK")
+    env.reset(seed=1)
+    jp, jr = env.sim.jac_site(env.site_eef)
+    assert np.all(jp[:, 6:] == 0) and np.all(jr[:, 6:] == 0)
+    J6 = np.concatenate((jp, jr))[:, :6]
+    err = np.array([0.01, -0.02, 0.03, 0.001, 0.002, -0.001])
+    full = np.linalg.lstsq(np.concatenate((jp, jr)).T @ np.concatenate((jp, jr)) + 0.3 * np.eye(18), np.concatenate((jp, jr)).T @ err, rcond=-1)[0]
+    np.testing.assert_allclose(full[:6], np.linalg.solve(J6.T @ J6 + 0.3 * np.eye(6), J6.T @ err), atol=1e-14)
+    assert np.abs(full[6:]).max() < 1e-16
