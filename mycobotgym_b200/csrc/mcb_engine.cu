@@ -1838,8 +1838,17 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         double dist = sqrt(dx * dx + dy * dy + dz * dz);
         bool succ = dist < cfg.distance_threshold;
         bool term = succ, trunc = succ || (el >= cfg.max_episode_steps);
+        // bad-simulation guard (the role of mj_checkPos / mj_checkVel / mj_checkAcc in mj_step): a non-finite or exploded
+        // state ends the episode (truncated) so that auto-reset restores a sane state; counted in stats[5]
+        bool bad = false;
+        {
+          double v = lane < NQ ? s.qpos[lane] : 0.0, w = lane < NV ? s.qvel[lane] : 0.0;
+          bad = __any_sync(FULLMASK, !(fabs(v) < 1e10) || !(fabs(w) < 1e10));
+        }
+        if (bad) { succ = false; term = false; trunc = true; if (lane == 0) atomicAdd(a.stats + 5, 1.0); }
         double rew = cfg.reward_type == 0 ? -(double)(dist > cfg.distance_threshold) : -dist;
-        if (cfg.reward_type == 2) {
+        if (bad) { dist = 1e10; rew = cfg.reward_type == 0 ? -1.0 : 0.0; }
+        if (cfg.reward_type == 2 && !bad) {
           // stage_rewards (mycobot.py:402-448): reach / grasp / lift from the sites and the contact list of the last
           // forward pass; write_obs left grip_pos in o[0..2] and object_pos in o[3..5]
           const double* o = s.grad;
@@ -1862,7 +1871,7 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         double epret = a.ep_return[env] + rew;
         bool done = term || trunc;
         double final_stats[4] = {1.0, succ ? 1.0 : 0.0, epret, (double)el};
-        if (done && cfg.auto_reset) {
+        if ((done && cfg.auto_reset) || bad) {
           if (a.final_obs) {
             double dummy[3];
             write_obs(s, m, cfg, lane, env, a.final_obs, nullptr, nullptr, dummy);

@@ -743,14 +743,116 @@ def set_const(m):
 # ----------------------------------------------------------------------------------
 
 
-def flatmodel_from_mjmodel(mjm):  # pragma: no cover - needs mujoco
-    """Fill the same table from a live `mujoco.MjModel` (the reference's compiled model,
-    `mycobot.py:69-75`).  Only primitive geoms are kept; see module docstring."""
-    import mujoco  # noqa: F401
+def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco, which is not installable in this image
+    """Fill the same table from a live `mujoco.MjModel` -- the reference's compiled model (`MujocoEnv.__init__`,
+    mycobot.py:69-75).  Field names follow mjModel.  Only plane / box geoms are kept as collision geoms (mesh hulls are
+    a documented gap); `set_const()` is NOT re-run: invweight0 / meaninertia / connect anchors come from MuJoCo's own
+    mj_setConst, so diffing this table against `compile_mjcf()` checks the mini-compiler field by field
+    (`diff_flatmodels`).  Untested here (no mujoco wheel offline)."""
+    import mujoco
 
-    raise NotImplementedError(
-        "mujoco is not installable in this image; hook kept so a maintainer with MuJoCo 2.3.2 can diff "
-        "the mini-compiler against mj_setConst (see INTEGRATION.md)")
+    m = FlatModel()
+    nv, nq, nbody, njnt = mjm.nv, mjm.nq, mjm.nbody, mjm.njnt
+    m["nq"], m["nv"], m["nbody"], m["njnt"] = int(nq), int(nv), int(nbody), int(njnt)
+    m["timestep"] = float(mjm.opt.timestep)
+    m["gravity"] = np.array(mjm.opt.gravity, dtype=np.float64)
+    m["tolerance"], m["iterations"] = float(mjm.opt.tolerance), int(mjm.opt.iterations)
+    m["ls_iterations"], m["ls_tolerance"], m["impratio"] = int(mjm.opt.ls_iterations), float(mjm.opt.ls_tolerance), float(mjm.opt.impratio)
+
+    def name(objtype, i):
+        return mujoco.mj_id2name(mjm, objtype, i) or ""
+
+    m["body_names"] = [name(mujoco.mjtObj.mjOBJ_BODY, i) for i in range(nbody)]
+    for k in ("body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.int32)
+    for k in ("body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_subtreemass"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.float64)
+    m["body_invweight0"] = np.array(mjm.body_invweight0, dtype=np.float64).reshape(nbody, 2)
+    m["jnt_names"] = [name(mujoco.mjtObj.mjOBJ_JOINT, i) for i in range(njnt)]
+    for k in ("jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.int32)
+    for k in ("jnt_pos", "jnt_axis", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.float64)
+    for k in ("dof_bodyid", "dof_jntid", "dof_parentid", "dof_Madr"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.int32)
+    for k in ("dof_armature", "dof_damping", "dof_invweight0"):
+        m[k] = np.array(getattr(mjm, k), dtype=np.float64)
+    m["nM"] = int(mjm.nM)
+    m["qpos0"] = np.array(mjm.qpos0, dtype=np.float64)
+    keep = [g for g in range(mjm.ngeom) if mjm.geom_type[g] in (GEOM_TYPES["plane"], GEOM_TYPES["box"])]
+    m["ngeom"] = len(keep)
+    m["geom_names"] = [name(mujoco.mjtObj.mjOBJ_GEOM, g) for g in keep]
+    for k, dt in (("geom_type", np.int32), ("geom_bodyid", np.int32), ("geom_contype", np.int32), ("geom_conaffinity", np.int32),
+                  ("geom_condim", np.int32), ("geom_pos", np.float64), ("geom_quat", np.float64), ("geom_size", np.float64),
+                  ("geom_friction", np.float64), ("geom_solref", np.float64), ("geom_solimp", np.float64), ("geom_solmix", np.float64),
+                  ("geom_margin", np.float64), ("geom_gap", np.float64), ("geom_rbound", np.float64)):
+        m[k] = np.array(getattr(mjm, k), dtype=dt)[keep]
+    m["nsite"] = int(mjm.nsite)
+    m["site_names"] = [name(mujoco.mjtObj.mjOBJ_SITE, i) for i in range(mjm.nsite)]
+    m["site_bodyid"] = np.array(mjm.site_bodyid, dtype=np.int32)
+    m["site_pos"], m["site_quat"] = np.array(mjm.site_pos, dtype=np.float64), np.array(mjm.site_quat, dtype=np.float64)
+    ex = [sorted((int(sig) >> 16, int(sig) & 0xFFFF)) for sig in mjm.exclude_signature]
+    m["exclude"] = np.array(ex, dtype=np.int32).reshape(-1, 2)
+    m["ntendon"] = int(mjm.ntendon)
+    ten_J = np.zeros((mjm.ntendon, nv))
+    for t in range(mjm.ntendon):
+        for w in range(mjm.tendon_adr[t], mjm.tendon_adr[t] + mjm.tendon_num[t]):
+            assert mjm.wrap_type[w] == mujoco.mjtWrap.mjWRAP_JOINT
+            ten_J[t, mjm.jnt_dofadr[mjm.wrap_objid[w]]] = mjm.wrap_prm[w]
+    m["ten_J"] = ten_J
+    m["neq"] = int(mjm.neq)
+    m["eq_type"] = np.array([{int(mujoco.mjtEq.mjEQ_CONNECT): EQ_CONNECT, int(mujoco.mjtEq.mjEQ_WELD): EQ_WELD,
+                              int(mujoco.mjtEq.mjEQ_JOINT): EQ_JOINT}[int(t)] for t in mjm.eq_type], dtype=np.int32)
+    m["eq_obj1id"], m["eq_obj2id"] = np.array(mjm.eq_obj1id, dtype=np.int32), np.array(mjm.eq_obj2id, dtype=np.int32)
+    m["eq_data"] = np.array(mjm.eq_data, dtype=np.float64)[:, :7]
+    m["eq_solref"], m["eq_solimp"] = np.array(mjm.eq_solref, dtype=np.float64), np.array(mjm.eq_solimp, dtype=np.float64)
+    nu = mjm.nu
+    m["nu"] = int(nu)
+    moment = np.zeros((nu, nv))
+    for a in range(nu):
+        tid = int(mjm.actuator_trnid[a, 0])
+        if mjm.actuator_trntype[a] == mujoco.mjtTrn.mjTRN_JOINT:
+            moment[a, mjm.jnt_dofadr[tid]] = mjm.actuator_gear[a, 0]
+        elif mjm.actuator_trntype[a] == mujoco.mjtTrn.mjTRN_TENDON:
+            moment[a] = ten_J[tid] * mjm.actuator_gear[a, 0]
+        else:
+            raise NotImplementedError("actuator transmission")
+    m["actuator_moment"] = moment
+    m["actuator_gain"] = np.array(mjm.actuator_gainprm[:, 0], dtype=np.float64)
+    m["actuator_biasprm"] = np.array(mjm.actuator_biasprm[:, :3], dtype=np.float64)
+    m["actuator_ctrllimited"] = np.array(mjm.actuator_ctrllimited, dtype=np.int32)
+    m["actuator_ctrlrange"] = np.array(mjm.actuator_ctrlrange, dtype=np.float64)
+    m["actuator_forcelimited"] = np.array(mjm.actuator_forcelimited, dtype=np.int32)
+    m["actuator_forcerange"] = np.array(mjm.actuator_forcerange, dtype=np.float64)
+    m["nkey"] = int(mjm.nkey)
+    m["key_qpos"] = np.array(mjm.key_qpos, dtype=np.float64).reshape(mjm.nkey, nq)
+    m["key_qvel"] = np.array(mjm.key_qvel, dtype=np.float64).reshape(mjm.nkey, nv)
+    m["key_ctrl"] = np.array(mjm.key_ctrl, dtype=np.float64).reshape(mjm.nkey, nu)
+    m["stat_meaninertia"] = float(mjm.stat.meaninertia)
+    m["M0"] = mass_matrix_numpy(m, fk_numpy(m, m["qpos0"]))
+    m["compile_log"] = ["filled from a live mujoco.MjModel; mesh geoms dropped from collision"]
+    return m
+
+
+def diff_flatmodels(a, b, rtol=1e-9):
+    """Field-by-field comparison of two FlatModels (mini-compiler vs live mjModel).  Returns {field: max abs diff}."""
+    out = {}
+    for k in sorted(set(a) | set(b)):
+        if k not in a or k not in b:
+            out[k] = "missing"
+            continue
+        va, vb = a[k], b[k]
+        if isinstance(va, np.ndarray):
+            if va.shape != np.asarray(vb).shape:
+                out[k] = f"shape {va.shape} vs {np.asarray(vb).shape}"
+            elif va.size and not np.allclose(va, vb, rtol=rtol, atol=1e-12):
+                out[k] = float(np.abs(va - vb).max())
+        elif isinstance(va, float):
+            if abs(va - vb) > rtol * max(1.0, abs(va)):
+                out[k] = abs(va - vb)
+        elif va != vb and k != "compile_log":
+            out[k] = (va, vb)
+    return out
 
 
 ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")

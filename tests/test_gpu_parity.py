@@ -486,3 +486,21 @@ def mjcf_tight(flat):
     f = mjcf.FlatModel(flat)
     f["tolerance"] = 1e-13
     return f
+
+
+def test_bad_simulation_guard_resets_the_env():
+    # the role of mj_checkPos / mj_checkVel in mj_step: a non-finite state must not poison the batch
+    n = 8
+    env = _env(num_envs=n, has_object=True, reward_type="sparse", seed=9)
+    env.reset()
+    st = env.get_state()
+    qvel = st["qvel"].clone()
+    qvel[2, 0] = float("nan")
+    qvel[5, 3] = 1e30
+    env.set_state(qvel=qvel)
+    obs, rew, term, trunc, info = env.step(torch.zeros(n, 7))
+    assert trunc[2] and trunc[5] and not term[2] and int(trunc.sum()) == 2
+    st = env.get_state()
+    assert bool(torch.isfinite(st["qpos"]).all()) and bool(torch.isfinite(st["qvel"]).all()) and bool(torch.isfinite(obs["observation"]).all())
+    assert env.stats().cpu().numpy()[5] == 2
+    env.close()
