@@ -330,27 +330,28 @@ __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba
   __syncwarp();
 }
 
-// chol_solve_blk<N0, N>(): Cholesky A = L L' of the diagonal block rows/cols [N0, N0+N) of a packed symmetric
+// chol_solve_blk<N0, N, DADD>(): Cholesky A = L L' of the diagonal block rows/cols [N0, N0+N) of a packed symmetric
 // matrix (src -> dst, may alias) AND the solution of A x = b, in one pass.  Lane i owns row i in registers;
-// finished rows are broadcast through dst.  Lane 31 carries the right-hand side as an extra row, so the forward
-// substitution costs nothing extra; the back substitution is a branch-free shuffle chain.  `dadd` is added to the
-// lane's diagonal entry first (Euler: h * damping).  Lanes outside the block get their b back.
-// Fully unrolled: every shared-memory offset is an immediate, no index arithmetic in the inner loops.
-template <int N0, int N>
-__device__ __noinline__ double chol_solve_blk(const double* src, double* dst, double dadd, int lane, double b) {
+// finished rows are broadcast through dst.  Lane 31 carries the right-hand side (read from the shared vector
+// `bsrc`) as an extra row, so the forward substitution costs nothing extra; its entries go to the lanes through
+// the shared scratch `ytmp`; the back substitution is a branch-free shuffle chain.  DADD: `dadd` is added to the
+// lane's diagonal entry first (Euler: h * damping).  Lanes outside the block return 0.
+// Fully unrolled: every shared-memory offset is an immediate, no index arithmetic or selects in the inner loops.
+template <int N0, int N, bool DADD>
+__device__ __noinline__ double chol_solve_blk(const double* src, double* dst, const double* bsrc, double* ytmp, double dadd, int lane) {
   const int i = lane;
   const bool mine = (i >= N0 && i < N0 + N);
   const bool rhs = (i == 31);
   const int ro = i * (i + 1) / 2 + N0;
+  const double* base = rhs ? bsrc + N0 : src + ro;      // lane 31 loads b, the others their matrix row
   double row[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
-    double bk = __shfl_sync(FULLMASK, b, N0 + k);
-    double v = (mine && N0 + k <= i) ? src[ro + k] : 0.0;
-    v += (N0 + k == i) ? dadd : 0.0;      // (a separate "row[i - N0] += dadd" would index row[] dynamically => local memory)
-    row[k] = rhs ? bk : v;
+    double v = (rhs || (mine && N0 + k <= i)) ? base[k] : 0.0;
+    if (DADD) v += (N0 + k == i) ? dadd : 0.0;     // (a separate "row[i - N0] += dadd" would index row[] dynamically => local memory)
+    row[k] = v;
   }
-  double myinv = 0.0, x = 0.0;
+  double myinv = 0.0;
 #pragma unroll
   for (int j = 0; j < N; j++) {
     const double* rj = dst + TRI(N0 + j, N0);
@@ -358,37 +359,40 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, do
 #pragma unroll
     for (int k = 0; k < j; k++) { if (k & 1) s1 -= row[k] * rj[k]; else s0 -= row[k] * rj[k]; }
     double sv = s0 + s1;
+    if (i == N0 + j && sv < MINVAL) sv = MINVAL;     // rank-deficiency guard on the pivot (mju_cholFactor's mindiag)
     double sjj = __shfl_sync(FULLMASK, sv, N0 + j);
-    if (sjj < MINVAL) sjj = MINVAL;
     double inv = rsqrt(sjj);
-    double l = (i == N0 + j) ? sjj * inv : sv * inv;
+    double l = sv * inv;                               // pivot lane: sqrt(sjj); lane 31: entry j of L^-1 b
     row[j] = l;
     if (mine && i >= N0 + j) dst[ro + j] = l;
-    double yj = __shfl_sync(FULLMASK, l, 31);   // entry j of L^-1 b
-    if (i == N0 + j) { myinv = inv; x = yj; }
+    if (rhs) ytmp[N0 + j] = l;
+    if (i == N0 + j) myinv = inv;
     __syncwarp();
   }
+  double x = mine ? ytmp[i] : 0.0;
 #pragma unroll
   for (int k = N0 + N - 1; k >= N0; k--) {
     double xk = __shfl_sync(FULLMASK, x * myinv, k);
     double lk = (i < k && i >= N0) ? dst[TRI(k, 0) + i] : 0.0;
     x = (i == k) ? xk : fma(-lk, xk, x);
   }
-  return mine ? x : b;
+  return x;
 }
-// factor + solve with the block structure: coupled => one 18 x 18 block, else robot 12 x 12 and cube 6 x 6
-__device__ __forceinline__ double factor_solve(const double* src, double* dst, double dadd, int lane, int nva, bool coupled, double b) {
-  if (coupled) return chol_solve_blk<0, 18>(src, dst, dadd, lane, b);
-  b = chol_solve_blk<0, 12>(src, dst, dadd, lane, b);
-  if (nva > NH) b = chol_solve_blk<12, 6>(src, dst, dadd, lane, b);
-  return b;
+// factor + solve with the block structure: coupled => one 18 x 18 block, else robot 12 x 12 and cube 6 x 6.
+// b is read from the shared vector bsrc; ytmp is an 18-double shared scratch.
+__device__ __forceinline__ double factor_solve(const double* src, double* dst, const double* bsrc, double* ytmp, int lane, int nva, bool coupled) {
+  if (coupled) return chol_solve_blk<0, 18, false>(src, dst, bsrc, ytmp, 0.0, lane);
+  double x = chol_solve_blk<0, 12, false>(src, dst, bsrc, ytmp, 0.0, lane);
+  if (nva > NH) { double xc = chol_solve_blk<12, 6, false>(src, dst, bsrc, ytmp, 0.0, lane); if (lane >= NH) x = xc; }
+  return x;
 }
 // the same for M and M + h*diag(damping): the free cube's block of M is diagonal (rotational dofs are expressed in
 // the body's principal frame about its centre of mass), so cube lanes just divide
-__device__ __forceinline__ double factor_solve_M(const double* M, double* dst, double dadd, int lane, int nva, double b) {
-  b = chol_solve_blk<0, 12>(M, dst, dadd, lane, b);
-  if (lane >= NH && lane < nva) b = b / (M[TRI(lane, 0) + lane] + dadd);
-  return b;
+template <bool DADD>
+__device__ __forceinline__ double factor_solve_M(const double* M, double* dst, const double* bsrc, double* ytmp, double dadd, int lane, int nva) {
+  double x = chol_solve_blk<0, 12, DADD>(M, dst, bsrc, ytmp, dadd, lane);
+  if (lane >= NH && lane < nva) x = bsrc[lane] / (M[TRI(lane, 0) + lane] + dadd);
+  return x;
 }
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
 template <class S>
@@ -1201,7 +1205,7 @@ struct Newton {
   }
   __device__ void newton_direction() {
     build_H();
-    double mg = factor_solve(s.H, s.H, 0.0, lane, nva, coupled, lane < nva ? s.grad[lane] : 0.0);
+    double mg = factor_solve(s.H, s.H, s.grad, s.Mv, lane, nva, coupled);
     if (lane < nva) s.search[lane] = -mg;
     __syncwarp();
   }
@@ -1341,7 +1345,7 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
   velocity_rne(s, m, lane, nba, nva);
   FSYNC();
   actuation_smooth(s, m, lane, nva);
-  double qs = factor_solve_M(s.M, s.H, 0.0, lane, nva, lane < nva ? s.qfrc_smooth[lane] : 0.0);
+  double qs = factor_solve_M<false>(s.M, s.H, s.qfrc_smooth, s.Mv, 0.0, lane, nva);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
   FSYNC();
@@ -1359,8 +1363,9 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
 template <class S>
 __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   const double h = MDL.d.timestep;
-  double qacc = factor_solve_M(s.M, s.H, lane < nva ? h * MDL.d.damping[lane] : 0.0, lane, nva,
-                               lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0);
+  if (lane < NV) s.search[lane] = lane < nva ? s.qfrc_smooth[lane] + s.qfrc_con[lane] : 0.0;   // search / Mv are free outside the solver
+  __syncwarp();
+  double qacc = factor_solve_M<true>(s.M, s.H, s.search, s.Mv, lane < nva ? h * MDL.d.damping[lane] : 0.0, lane, nva);
   if (lane < nva) s.qvel[lane] += h * qacc;
   __syncwarp();
   if (lane < NH) s.qpos[lane] += h * s.qvel[lane];
@@ -1626,7 +1631,9 @@ __device__ void ik_update_ctrl(S& s, int lane, double grip_ctrl) {
     for (int k = 0; k < 6; k++) b += Jm[k * 6 + lane] * s.ik[7 + k];
   }
   __syncwarp();
-  double dq = chol_solve_blk<0, 6>(s.H, s.H, 0.0, lane, b);
+  if (lane < 6) s.ik[7 + lane] = b;       // the pose error is consumed (barrier above); reuse its slots for the right-hand side
+  __syncwarp();
+  double dq = chol_solve_blk<0, 6, false>(s.H, s.H, s.ik + 7, s.Mv, 0.0, lane);
   if (lane < 6) s.ctrl[lane] += dq;
   else if (lane == 6) s.ctrl[6] = grip_ctrl;
   __syncwarp();
