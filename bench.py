@@ -83,30 +83,33 @@ def cpu_port_throughput(workload, budget_env_steps, workers=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one `nvidia-smi -lms 100`
+    process whose lines are collected until stop()."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
 
-    def stop(self):
-        self._stop_evt.set()
+    def stop(self, t0=None, t1=None):
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=6)
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if t0 is not None and not (t0 <= t <= t1):
+                continue
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
             except Exception:
@@ -183,6 +186,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.5)                    # let nvidia-smi start streaming before the timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
@@ -201,7 +205,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if sampler else None
     value = world * n * K / (total_ms * 1e-3)
 
     # e2e: the same step through host buffers (pinned staging inside the C ABI), H2D + D2H inside the timed region
@@ -244,7 +248,9 @@ def run_ours(args):
             "gpu_launches": K * env.last_step_launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of mcb_env_kernel<0> for this workload at 16384 envs, from
+                         # the ncu --set full capture summarised in profiles/r01i_ncu_summary_final.txt (14.09 MB + 50.53 MB)
+                         "traffic": 64.62e6 if (args.workload == "pick" and n == 16384) else None, "traffic_unit": "B/launch",
                          "note": "dominant kernel = mcb_env_kernel (the whole step); algorithmic FLOP/env-step from DESIGN.md; "
                                  "peak = DFMA micro-kernel measured in this run (FP64 peak is not in MEASURED_PEAKS.json)",
                          "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
