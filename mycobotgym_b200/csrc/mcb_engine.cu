@@ -856,14 +856,22 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       int rows = 2 * (pp.dim - 1), base;
       if (pp.ptype == 0) { base = r0; r0 += rows; } else if (pp.ptype == 1) { base = r1; r1 += rows; } else { base = r2; r2 += rows; }
       s.crow[c] = base;
-      for (int k = 0; k < rows; k++) { s.rmeta[base + k] = c | (k << 9) | (3 << 12) | RM_INEQ; s.omap[base + k] = orow + k; }
+      s.cscr[c] = (double)orow;            // collision scratch is free again: contact's first row in MuJoCo's ordering
       orow += rows;
     }
-    for (int k = 0; k < 6; k++) { s.rmeta[k] = (k / 3) | ((k % 3) << 9); s.omap[k] = k; }
-    s.rmeta[6] = (1 << 12); s.omap[6] = 6;
     s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU;
   }
   __syncwarp();
+  if (lane < 7) { s.rmeta[lane] = lane < 6 ? ((lane / 3) | ((lane % 3) << 9)) : (1 << 12); s.omap[lane] = lane; }
+  for (int w = lane; w < s.ncon * 6; w += 32) {
+    int c = w / 6, k = w % 6;
+    if (k < 2 * (MDL.pair[s.cpair[c]].dim - 1)) {
+      int r = s.crow[c] + k;
+      s.rmeta[r] = c | (k << 9) | (3 << 12) | RM_INEQ;
+      s.omap[r] = (int)s.cscr[c] + k;
+    }
+  }
+  __syncwarp();     // cscr aliases the first pool rows, which the equality fill below overwrites
   if (lim) {
     int u = __popc(bal & ((1u << lane) - 1));
     int r = s.nR + s.nC + s.nF + u;
@@ -891,35 +899,40 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     }
     s.pool[6 * SR + j] = v;
   }
-  // contact Jacobian rows: items (contact, dof)
+  // contact Jacobian rows: items (contact, dof), enumerated per block type so that only owned columns are visited
   const int ncon = s.ncon;
-  for (int w = lane; w < ncon * NV; w += 32) {
-    int c = w / NV, j = w % NV;
-    const PairParam& pp = MDL.pair[s.cpair[c]];
-    if (pp.ptype == 0 && j >= NH) continue;
-    if (pp.ptype == 1 && j < NH) continue;
-    int b1 = MDL.d.geom_body[pp.g1], b2 = MDL.d.geom_body[pp.g2];
-    const double* pt = s.cpos + c * 3;
-    const double* f = s.cframe + c * 9;
-    double l1[3], r1[3], l2[3], r2[3];
-    jac_col(s, m, b1, j, pt, l1, r1);
-    jac_col(s, m, b2, j, pt, l2, r2);
-    double dl[3] = {l2[0] - l1[0], l2[1] - l1[1], l2[2] - l1[2]}, dr[3] = {r2[0] - r1[0], r2[1] - r1[1], r2[2] - r1[2]};
-    double Jn = dot3(f, dl), Jt1 = dot3(f + 3, dl), Jt2 = dot3(f + 6, dl), Jr = dot3(f, dr);
-    int r0 = s.crow[c];
-    double* p; int st;
-    if (pp.ptype == 0) { p = row_r(s, r0) + j; st = SR; }
-    else if (pp.ptype == 1) { p = row_c(s, r0) + (j - NH); st = SC; }
-    else { p = row_f(s, r0) + j; st = SF; }
-    double mu = pp.friction[0];
-    p[0] = Jn + mu * Jt1;
-    p[st] = Jn + (-mu) * Jt1;
-    p[2 * st] = Jn + mu * Jt2;
-    p[3 * st] = Jn + (-mu) * Jt2;
-    if (pp.dim == 4) {
-      double mt = pp.friction[1];
-      p[4 * st] = Jn + mt * Jr;
-      p[5 * st] = Jn + (-mt) * Jr;
+  const int nRc_ = s.nR - 7;
+#pragma unroll 1
+  for (int pt = 0; pt < 3; pt++) {
+    if ((pt == 0 && nRc_ == 0) || (pt == 1 && s.nC == 0) || (pt == 2 && s.nF == 0)) continue;
+    const int ncol = pt == 0 ? NH : pt == 1 ? 6 : NV, j0 = pt == 1 ? NH : 0;
+    for (int w = lane; w < ncon * ncol; w += 32) {
+      int c = w / ncol, j = j0 + w % ncol;
+      const PairParam& pp = MDL.pair[s.cpair[c]];
+      if (pp.ptype != pt) continue;
+      int b1 = MDL.d.geom_body[pp.g1], b2 = MDL.d.geom_body[pp.g2];
+      const double* pt3 = s.cpos + c * 3;
+      const double* f = s.cframe + c * 9;
+      double l1[3], r1[3], l2[3], r2[3];
+      jac_col(s, m, b1, j, pt3, l1, r1);
+      jac_col(s, m, b2, j, pt3, l2, r2);
+      double dl[3] = {l2[0] - l1[0], l2[1] - l1[1], l2[2] - l1[2]}, dr[3] = {r2[0] - r1[0], r2[1] - r1[1], r2[2] - r1[2]};
+      double Jn = dot3(f, dl), Jt1 = dot3(f + 3, dl), Jt2 = dot3(f + 6, dl), Jr = dot3(f, dr);
+      int r0 = s.crow[c];
+      double* p; int st;
+      if (pt == 0) { p = row_r(s, r0) + j; st = SR; }
+      else if (pt == 1) { p = row_c(s, r0) + (j - NH); st = SC; }
+      else { p = row_f(s, r0) + j; st = SF; }
+      double mu = pp.friction[0];
+      p[0] = Jn + mu * Jt1;
+      p[st] = Jn + (-mu) * Jt1;
+      p[2 * st] = Jn + mu * Jt2;
+      p[3 * st] = Jn + (-mu) * Jt2;
+      if (pp.dim == 4) {
+        double mt = pp.friction[1];
+        p[4 * st] = Jn + mt * Jr;
+        p[5 * st] = Jn + (-mt) * Jr;
+      }
     }
   }
   __syncwarp();
