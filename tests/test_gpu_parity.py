@@ -504,3 +504,31 @@ def test_bad_simulation_guard_resets_the_env():
     assert bool(torch.isfinite(st["qpos"]).all()) and bool(torch.isfinite(st["qvel"]).all()) and bool(torch.isfinite(obs["observation"]).all())
     assert env.stats().cpu().numpy()[5] == 2
     env.close()
+
+
+def test_make_registry_ids_and_reference_goal_autoreset():
+    from mycobotgym_b200.vector_env import make
+
+    for env_id, obs_dim, adim, rdtype in [("MyCobotPickAndPlace-Sparse-joint-v0", 25, 7, torch.float32),
+                                          ("MyCobotReach-Dense-joint-v0", 10, 7, torch.float64),
+                                          ("MyCobotPickAndPlace-RewardShaping-joint-v0", 25, 7, torch.float64),
+                                          ("MyCobotFetchReach-Sparse-IK-v0", 10, 4, torch.float32)]:
+        env = make(env_id, num_envs=4)
+        obs, info = env.reset(seed=0)
+        assert obs["observation"].shape == (4, obs_dim) and info == {} and env.action_dim == adim
+        obs, rew, term, trunc, inf = env.step(torch.zeros(4, adim))
+        assert rew.dtype == rdtype and rew.shape == (4,) and term.dtype == torch.bool and "is_success" in inf
+        env.close()
+    with pytest.raises(NotImplementedError):
+        make("MyCobotReach-Dense-mocap-v0", num_envs=1)
+    # auto-reset with the reference's (host-side, seeded) sampling protocol: goals change at the TimeLimit, state restarts
+    env = make("MyCobotPickAndPlace-Sparse-joint-v0", num_envs=3, goal_source="reference", max_episode_steps=3)
+    random.seed(5)
+    obs, _ = env.reset(seed=5)
+    g0 = obs["desired_goal"].clone()
+    for t in range(3):
+        obs, rew, term, trunc, inf = env.step(torch.zeros(3, 7))
+    assert bool(trunc.all()) and bool(inf["_final_observation"].all())
+    assert not torch.equal(obs["desired_goal"], g0) and bool((env.get_state()["elapsed"] == 0).all())
+    assert not torch.equal(inf["final_observation"], obs["observation"])
+    env.close()
