@@ -187,16 +187,27 @@ BUILTIN_DEFAULTS = {
 }
 
 
-def _load_xml(path):
+def _load_xml(path, _top=True):
     root = ET.parse(path).getroot()
     base = os.path.dirname(path)
     out = ET.Element("mujoco")
     for child in list(root):
         if child.tag == "include":
-            inc = _load_xml(os.path.join(base, child.get("file")))
+            inc = _load_xml(os.path.join(base, child.get("file")), _top=False)
             out.extend(list(inc))
         else:
             out.append(child)
+    if _top:
+        # MuJoCo merges repeated top-level sections (worldbody, equality, actuator, ...) in document order
+        merged = ET.Element("mujoco")
+        seen = {}
+        for child in list(out):
+            if child.tag in ("worldbody", "equality", "actuator", "contact", "tendon", "keyframe", "asset") and child.tag in seen:
+                seen[child.tag].extend(list(child))
+            else:
+                seen.setdefault(child.tag, child)
+                merged.append(child)
+        return merged
     return out
 
 
@@ -313,11 +324,12 @@ def compile_mjcf(xml_path, log=None):
     def add_body(el, parent, childclass):
         bid = len(bodies)
         if el is None:  # world
-            b = dict(name="world", parent=0, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]))
+            b = dict(name="world", parent=0, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]), mocap=False)
             children = root.find("worldbody")
         else:
             childclass = el.get("childclass", childclass)
-            b = dict(name=el.get("name"), parent=parent, pos=_vec(el.get("pos", "0 0 0")), quat=_orient(el))
+            b = dict(name=el.get("name"), parent=parent, pos=_vec(el.get("pos", "0 0 0")), quat=_orient(el),
+                     mocap=_bool(el.get("mocap", "false")))
             children = el
         b.update(jntadr=-1, jntnum=0, inertial=None, geom_ids=[])
         bodies.append(b)
@@ -464,6 +476,16 @@ def compile_mjcf(xml_path, log=None):
     m["body_mass"] = np.array([b["mass"] for b in bodies])
     m["body_inertia"] = np.array([b["inertia"] for b in bodies])
     m["body_subtreemass"] = subtreemass
+    mocapid, nmocap = [], 0
+    for b in bodies:
+        if b["mocap"]:
+            assert b["jntnum"] == 0 and b["parent"] == 0, "mocap bodies are static children of the world"
+            mocapid.append(nmocap)
+            nmocap += 1
+        else:
+            mocapid.append(-1)
+    m["nmocap"] = nmocap
+    m["body_mocapid"] = np.array(mocapid, dtype=np.int32)
     m["jnt_names"] = [j["name"] for j in joints]
     m["jnt_type"] = np.array([j["type"] for j in joints], dtype=np.int32)
     m["jnt_qposadr"] = np.array([j["qposadr"] for j in joints], dtype=np.int32)
@@ -501,7 +523,7 @@ def compile_mjcf(xml_path, log=None):
     m["qpos0"] = qpos0
 
     # ---- collision geoms: primitives only (plane, box); mesh hulls are a documented gap
-    cg = [g for g in geoms if g["type"] in (GEOM_TYPES["plane"], GEOM_TYPES["box"])]
+    cg = [g for g in geoms if g["type"] in (GEOM_TYPES["plane"], GEOM_TYPES["box"]) and (g["contype"] or g["conaffinity"])]
     ndropped = len(geoms) - len(cg)
     log.append(f"{ndropped} mesh geoms not emitted as collision geoms (convex-hull narrowphase is out of round-1 scope)")
     m["ngeom"] = len(cg)
@@ -562,8 +584,14 @@ def compile_mjcf(xml_path, log=None):
         for e in eqn:
             a = dict(BUILTIN_DEFAULTS["equality"])
             a.update(e.attrib)
-            d = np.zeros(7)
-            if e.tag == "connect":
+            d = np.zeros(11)
+            if e.tag == "weld":
+                d[0:3] = _vec(a.get("anchor", "0 0 0"))
+                d[3:10] = _vec(a.get("relpose", "0 1 0 0 0 0 0"))
+                d[10] = float(a.get("torquescale", "1"))
+                eqs.append(dict(type=EQ_WELD, o1=name2body[a["body1"]], o2=name2body[a["body2"]], data=d,
+                                solref=_vec(a["solref"]), solimp=_vec(a["solimp"], 5, [0.9, 0.95, 0.001, 0.5, 2])))
+            elif e.tag == "connect":
                 d[:3] = _vec(a["anchor"])
                 eqs.append(dict(type=EQ_CONNECT, o1=name2body[a["body1"]], o2=name2body[a["body2"]], data=d,
                                 solref=_vec(a["solref"]), solimp=_vec(a["solimp"], 5, [0.9, 0.95, 0.001, 0.5, 2])))
@@ -577,7 +605,7 @@ def compile_mjcf(xml_path, log=None):
     m["eq_type"] = np.array([e["type"] for e in eqs], dtype=np.int32)
     m["eq_obj1id"] = np.array([e["o1"] for e in eqs], dtype=np.int32)
     m["eq_obj2id"] = np.array([e["o2"] for e in eqs], dtype=np.int32)
-    m["eq_data"] = np.array([e["data"] for e in eqs])
+    m["eq_data"] = np.array([e["data"] for e in eqs]).reshape(len(eqs), 11)
     m["eq_solref"] = np.array([e["solref"] for e in eqs])
     m["eq_solimp"] = np.array([e["solimp"] for e in eqs])
 
@@ -614,11 +642,19 @@ def compile_mjcf(xml_path, log=None):
     kn = root.find("keyframe")
     if kn is not None:
         for k in kn.findall("key"):
-            keys.append(dict(qpos=_vec(k.get("qpos")), qvel=_vec(k.get("qvel")), ctrl=_vec(k.get("ctrl"))))
+            keys.append(dict(qpos=_vec(k.get("qpos")), qvel=_vec(k.get("qvel")),
+                             ctrl=_vec(k.get("ctrl")) if k.get("ctrl") else np.zeros(len(acts)),
+                             mpos=_vec(k.get("mpos")) if k.get("mpos") else None,
+                             mquat=_vec(k.get("mquat")) if k.get("mquat") else None))
     m["nkey"] = len(keys)
     m["key_qpos"] = np.array([k["qpos"] for k in keys]).reshape(len(keys), nq)
     m["key_qvel"] = np.array([k["qvel"] for k in keys]).reshape(len(keys), nv)
     m["key_ctrl"] = np.array([k["ctrl"] for k in keys]).reshape(len(keys), len(acts))
+    mb = [i for i, b in enumerate(bodies) if b["mocap"]]
+    m["key_mpos"] = np.array([k["mpos"] if k["mpos"] is not None else np.concatenate([bodies[i]["pos"] for i in mb] or [np.zeros(0)])
+                              for k in keys]).reshape(len(keys), 3 * nmocap)
+    m["key_mquat"] = np.array([k["mquat"] if k["mquat"] is not None else np.concatenate([bodies[i]["quat"] for i in mb] or [np.zeros(0)])
+                               for k in keys]).reshape(len(keys), 4 * nmocap)
 
     set_const(m)
     m["compile_log"] = list(log)
@@ -715,6 +751,16 @@ def set_const(m):
             b1, b2 = m["eq_obj1id"][e], m["eq_obj2id"][e]
             g = xpos[b1] + xmat[b1] @ m["eq_data"][e, :3]
             m["eq_data"][e, 3:6] = xmat[b2].T @ (g - xpos[b2])
+        elif m["eq_type"][e] == EQ_WELD:
+            # engine_setconst.c: anchor (data[0:3]) is in body2's frame; data[3:6] = the same point in body1's frame;
+            # data[6:10] = orientation of body2 relative to body1 at qpos0, unless the user gave a quaternion
+            b1, b2 = m["eq_obj1id"][e], m["eq_obj2id"][e]
+            if np.all(m["eq_data"][e, 6:10] == 0):
+                g = xpos[b2] + xmat[b2] @ m["eq_data"][e, 0:3]
+                m["eq_data"][e, 3:6] = xmat[b1].T @ (g - xpos[b1])
+                m["eq_data"][e, 6:10] = quat_mul(quat_conj(xquat[b1]), xquat[b2])
+            else:
+                m["eq_data"][e, 6:10] /= np.linalg.norm(m["eq_data"][e, 6:10])
     M = mass_matrix_numpy(m, fk)
     Minv = np.linalg.inv(M)
     nv = m["nv"]
@@ -856,7 +902,8 @@ def diff_flatmodels(a, b, rtol=1e-9):
 
 
 ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
-COMPILED_JOINT = os.path.join(ASSET_DIR, "mycobot280_joint.json")
+COMPILED_JOINT = os.path.join(ASSET_DIR, "mycobot280_joint.json")     # mycobot280.xml (joint and IK controllers)
+COMPILED_MOCAP = os.path.join(ASSET_DIR, "mycobot280_mocap.json")     # mycobot280_mocap.xml (mocap controller)
 
 
 def load_compiled(path=COMPILED_JOINT):

@@ -45,10 +45,10 @@ enum { EFC_EQUALITY = 0, EFC_LIMIT = 1, EFC_CONTACT = 2 };
 
 typedef struct {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, neq, nexclude, nM;
-  int iterations, ls_iterations, disable_cube; int pad_;
+  int iterations, ls_iterations, disable_cube, nmocap;
   double timestep, tolerance, ls_tolerance, impratio, meaninertia;
   double gravity[3];
-  const int *body_parentid, *body_rootid, *body_weldid, *body_jntnum, *body_jntadr, *body_dofnum, *body_dofadr;
+  const int *body_parentid, *body_rootid, *body_weldid, *body_jntnum, *body_jntadr, *body_dofnum, *body_dofadr, *body_mocapid;
   const double *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_subtreemass, *body_invweight0;
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const double *jnt_pos, *jnt_axis, *jnt_range, *jnt_margin, *jnt_solref, *jnt_solimp;
@@ -74,6 +74,7 @@ typedef struct {
 typedef struct {
   /* state */
   double qpos[MAXQ], qvel[MAXV], ctrl[MAXU], qacc_warmstart[MAXV], time;
+  double mocap_pos[3], mocap_quat[4];   /* one mocap body at most (robot0:mocap, mocap.xml:3) */
   /* kinematics */
   double xpos[MAXBODY * 3], xquat[MAXBODY * 4], xmat[MAXBODY * 9], xipos[MAXBODY * 3], ximat[MAXBODY * 9];
   double xanchor[MAXJNT * 3], xaxis[MAXJNT * 3];
@@ -214,9 +215,12 @@ void o_kinematics(const omodel* m, odata* d) {
       memcpy(d->xanchor + 3 * ja, xp, 3 * sizeof(double));
       rotvecquat(d->xaxis + 3 * ja, m->jnt_axis + 3 * ja, xq);
     } else {
-      mulmatvec3(xp, d->xmat + 9 * pid, m->body_pos + 3 * i);
+      const double* bpos = m->body_pos + 3 * i;
+      const double* bquat = m->body_quat + 4 * i;
+      if (m->body_mocapid[i] >= 0) { normalize4(d->mocap_quat); bpos = d->mocap_pos; bquat = d->mocap_quat; }   /* mj_kinematics: mocap pose */
+      mulmatvec3(xp, d->xmat + 9 * pid, bpos);
       for (int k = 0; k < 3; k++) xp[k] += d->xpos[3 * pid + k];
-      mulquat(xq, d->xquat + 4 * pid, m->body_quat + 4 * i);
+      mulquat(xq, d->xquat + 4 * pid, bquat);
       for (int j = ja; j < ja + jn; j++) {
         double vec[3], qloc[4];
         int qa = m->jnt_qposadr[j];
@@ -654,7 +658,7 @@ void o_make_constraint(const omodel* m, odata* d) {
   d->nefc = 0;
   /* equality (mj_instantiateEquality) */
   for (int e = 0; e < m->neq; e++) {
-    const double* data = m->eq_data + 7 * e;
+    const double* data = m->eq_data + 11 * e;
     int o1 = m->eq_obj1id[e], o2 = m->eq_obj2id[e];
     if (m->eq_type[e] == EQ_CONNECT) {
       double p1[3], p2[3];
@@ -667,6 +671,42 @@ void o_make_constraint(const omodel* m, odata* d) {
         for (int c = 0; c < nv; c++) jac[c] = jp1[r * nv + c] - jp2[r * nv + c];
         int row = add_row(d, nv, jac, p1[r] - p2[r], 0, EFC_EQUALITY, e);
         d->efc_diagApprox[row] = m->body_invweight0[2 * o1] + m->body_invweight0[2 * o2];
+      }
+    } else if (m->eq_type[e] == EQ_WELD) {
+      /* mj_instantiateEquality, mjEQ_WELD (2.3.x): data = anchor in body2 (3), anchor in body1 (3), relpose quat (4), torquescale */
+      double p1[3], p2[3], quat[4], quat1[4], quat2[4], cpos[6];
+      const double torquescale = data[10];
+      mulmatvec3(p1, d->xmat + 9 * o1, data + 3);
+      mulmatvec3(p2, d->xmat + 9 * o2, data);
+      for (int k = 0; k < 3; k++) { p1[k] += d->xpos[3 * o1 + k]; p2[k] += d->xpos[3 * o2 + k]; cpos[k] = p1[k] - p2[k]; }
+      o_jac(m, d, jp1, jr1, p1, o1);
+      o_jac(m, d, jp2, jr2, p2, o2);
+      mulquat(quat, d->xquat + 4 * o1, data + 6);                        /* q1 * relpose */
+      quat1[0] = d->xquat[4 * o2]; quat1[1] = -d->xquat[4 * o2 + 1]; quat1[2] = -d->xquat[4 * o2 + 2]; quat1[3] = -d->xquat[4 * o2 + 3];
+      mulquat(quat2, quat1, quat);                                       /* neg(q2) * q1 * relpose */
+      for (int k = 0; k < 3; k++) cpos[3 + k] = torquescale * quat2[1 + k];
+      double tran = m->body_invweight0[2 * o1] + m->body_invweight0[2 * o2];
+      double rot = m->body_invweight0[2 * o1 + 1] + m->body_invweight0[2 * o2 + 1];
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < nv; c++) jac[c] = jp1[r * nv + c] - jp2[r * nv + c];
+        int row = add_row(d, nv, jac, cpos[r], 0, EFC_EQUALITY, e);
+        d->efc_diagApprox[row] = tran;
+      }
+      /* rotational rows: 0.5 * neg(q2) * (jacr1 - jacr2)_col * q1 * relpose, axis part, times torquescale */
+      double Jrot[3 * MAXV];
+      for (int c = 0; c < nv; c++) {
+        double ax[3] = {jr1[c] - jr2[c], jr1[nv + c] - jr2[nv + c], jr1[2 * nv + c] - jr2[2 * nv + c]};
+        double qa[4] = {-quat1[1] * ax[0] - quat1[2] * ax[1] - quat1[3] * ax[2],
+                        quat1[0] * ax[0] + quat1[2] * ax[2] - quat1[3] * ax[1],
+                        quat1[0] * ax[1] + quat1[3] * ax[0] - quat1[1] * ax[2],
+                        quat1[0] * ax[2] + quat1[1] * ax[1] - quat1[2] * ax[0]};   /* mju_mulQuatAxis(neg(q2), axis) */
+        double q3[4];
+        mulquat(q3, qa, quat);
+        for (int r = 0; r < 3; r++) Jrot[r * nv + c] = 0.5 * q3[1 + r] * torquescale;
+      }
+      for (int r = 0; r < 3; r++) {
+        int row = add_row(d, nv, Jrot + r * nv, cpos[3 + r], 0, EFC_EQUALITY, e);
+        d->efc_diagApprox[row] = rot;
       }
     } else if (m->eq_type[e] == EQ_JOINT) {
       int q1 = m->jnt_qposadr[o1], q2 = m->jnt_qposadr[o2];
@@ -1163,7 +1203,7 @@ int o_maxefc(void) { return MAXEFC; }
 
 /* field accessors so the Python side never has to mirror the odata layout */
 #define ACC(name, type) type* o_##name(odata* d) { return d->name; }
-ACC(qpos, double) ACC(qvel, double) ACC(ctrl, double) ACC(qacc_warmstart, double) ACC(qacc, double)
+ACC(mocap_pos, double) ACC(mocap_quat, double) ACC(qpos, double) ACC(qvel, double) ACC(ctrl, double) ACC(qacc_warmstart, double) ACC(qacc, double)
 ACC(xpos, double) ACC(xquat, double) ACC(xmat, double) ACC(xipos, double) ACC(site_xpos, double) ACC(site_xmat, double)
 ACC(geom_xpos, double) ACC(geom_xmat, double)
 ACC(subtree_com, double) ACC(cdof, double) ACC(cinert, double) ACC(Mfull, double) ACC(qfrc_bias, double) ACC(qfrc_smooth, double)

@@ -18,10 +18,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmjc_oracle.so")
 
 _INT_SCALARS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "neq", "nexclude", "nM",
-                "iterations", "ls_iterations", "disable_cube", "pad_"]
+                "iterations", "ls_iterations", "disable_cube", "nmocap"]
 _DBL_SCALARS = ["timestep", "tolerance", "ls_tolerance", "impratio", "meaninertia"]
 _PTRS = [
-    ("i", ["body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr"]),
+    ("i", ["body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_mocapid"]),
     ("d", ["body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_subtreemass", "body_invweight0"]),
     ("i", ["jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited"]),
     ("d", ["jnt_pos", "jnt_axis", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp"]),
@@ -70,7 +70,7 @@ def lib():
         _lib.o_sizeof_data.restype = C.c_int
         _lib.o_sizeof_model.restype = C.c_int
         assert _lib.o_sizeof_model() == C.sizeof(OModel), (_lib.o_sizeof_model(), C.sizeof(OModel))
-        for name in ["qpos", "qvel", "ctrl", "qacc_warmstart", "qacc", "xpos", "xquat", "xmat", "xipos", "site_xpos", "site_xmat",
+        for name in ["mocap_pos", "mocap_quat", "qpos", "qvel", "ctrl", "qacc_warmstart", "qacc", "xpos", "xquat", "xmat", "xipos", "site_xpos", "site_xmat",
                      "geom_xpos", "geom_xmat", "subtree_com", "cdof", "cinert", "Mfull", "qfrc_bias", "qfrc_smooth", "qacc_smooth",
                      "qfrc_constraint", "qfrc_actuator", "qfrc_passive", "actuator_force", "efc_J", "efc_pos", "efc_D", "efc_R",
                      "efc_aref", "efc_force", "efc_diagApprox", "efc_KBIP"]:
@@ -88,7 +88,7 @@ class OracleSim:
         self._keep = []
         om = OModel()
         for n in _INT_SCALARS:
-            if n in ("nexclude", "disable_cube", "pad_"):
+            if n in ("nexclude", "disable_cube"):
                 continue
             setattr(om, n, int(flat[n]))
         om.nexclude = int(flat["exclude"].shape[0])
@@ -107,11 +107,19 @@ class OracleSim:
         self.buf = C.create_string_buffer(self.L.o_sizeof_data())
         self.d = C.cast(self.buf, C.c_void_p)
         self.qpos[:] = flat["qpos0"]
+        if self.flat["nmocap"]:
+            mb = list(flat["body_mocapid"]).index(0)
+            self.mocap_pos[:] = flat["body_pos"][mb]
+            self.mocap_quat[:] = flat["body_quat"][mb]
+        else:
+            self.mocap_quat[:] = [1, 0, 0, 0]
 
     def _arr(self, name, n, dtype=np.float64):
         p = getattr(self.L, "o_" + name)(self.d)
         return np.ctypeslib.as_array(p, shape=(n,))
 
+    mocap_pos = property(lambda s: s._arr("mocap_pos", 3))
+    mocap_quat = property(lambda s: s._arr("mocap_quat", 4))
     qpos = property(lambda s: s._arr("qpos", s.nq))
     qvel = property(lambda s: s._arr("qvel", s.nv))
     ctrl = property(lambda s: s._arr("ctrl", s.nu))
@@ -321,7 +329,8 @@ class OracleEnv:
                  control_steps=5):
         self.flat = flat
         self.controller_type, self.fetch_env, self.control_steps = controller_type, fetch_env, control_steps
-        assert controller_type in ("joint", "IK") and not (fetch_env and controller_type == "joint")
+        assert controller_type in ("joint", "IK", "mocap") and not (fetch_env and controller_type == "joint")
+        assert (controller_type == "mocap") == bool(flat["nmocap"]), "the mocap controller needs the mocap model variant (mycobot280_mocap.xml)"
         self.has_object, self.block_gripper = has_object, block_gripper
         self.target_in_the_air, self.distance_threshold = target_in_the_air, distance_threshold
         self.reward_type, self.frame_skip, self.max_episode_steps = reward_type, frame_skip, max_episode_steps
@@ -338,6 +347,9 @@ class OracleEnv:
             self.sim.qpos[:] = flat["key_qpos"][0]
             self.sim.qvel[:] = flat["key_qvel"][0]
             self.sim.ctrl[:] = flat["key_ctrl"][0]
+            if flat["nmocap"]:
+                self.sim.mocap_pos[:] = flat["key_mpos"][0]
+                self.sim.mocap_quat[:] = flat["key_mquat"][0]
         self.sim.forward()
         self.initial_gripper_xpos = self.sim.site_xpos[self.site_eef].copy()
         self.height_offset = float(self.sim.site_xpos[self.site_obj][2])
@@ -457,6 +469,19 @@ class OracleEnv:
                 ctrl_action[:6] = s.ctrl[:6] + delta[:6]
                 s.ctrl[:] = ctrl_action
                 s.step(self.frame_skip)
+        elif self.controller_type == "mocap":   # mycobot.py:172-189 + gymnasium_robotics mocap_set_action / reset_mocap2body_xpos
+            tcp = self.flat["body_names"].index("gripper_tcp")
+            mocap_action = np.zeros(7)
+            mocap_action[:3] = action[:3] * np.float32(0.1)                       # float32 product
+            grip_tcp_quat = s.xquat[tcp].copy()                                   # stale frame, like every site / body pose here
+            mocap_action[3:7] = np.array([0.5, -0.5, -0.5, 0.5]) if self.fetch_env else action[3:7]
+            mocap_action[3:7] -= grip_tcp_quat
+            s.mocap_pos[:] = s.xpos[tcp]                                          # reset_mocap2body_xpos
+            s.mocap_quat[:] = s.xquat[tcp]
+            s.mocap_pos[:] = s.mocap_pos + mocap_action[:3]
+            s.mocap_quat[:] = s.mocap_quat + mocap_action[3:7]
+            s.ctrl[-1] = 0.5 + np.float64(action[-1]) * 0.5
+            s.step(self.frame_skip)
         else:
             s.ctrl[:] = action.astype(np.float64)  # do_simulation: ctrl[:] = action (absolute; mycobot.py:192-193)
             s.step(self.frame_skip)

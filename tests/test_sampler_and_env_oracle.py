@@ -160,3 +160,31 @@ def test_ik_controller_on_the_oracle(flat):
     full = np.linalg.lstsq(np.concatenate((jp, jr)).T @ np.concatenate((jp, jr)) + 0.3 * np.eye(18), np.concatenate((jp, jr)).T @ err, rcond=-1)[0]
     np.testing.assert_allclose(full[:6], np.linalg.solve(J6.T @ J6 + 0.3 * np.eye(6), J6.T @ err), atol=1e-14)
     assert np.abs(full[6:]).max() < 1e-16
+
+
+def test_mocap_controller_on_the_oracle():
+    # mycobot.py:172-189: the mocap body is placed at the (stale) tool pose + 0.1 * action and a weld drags the arm there
+    from mycobotgym_b200 import mjcf
+
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP)
+    assert (fm.nbody, fm.nu, fm.neq, fm.nmocap) == (26, 1, 4, 1) and list(fm.eq_type) == [1, 0, 0, 2]
+    np.testing.assert_allclose(fm.eq_data[0, 6:10], [np.sqrt(0.5), 0, 0, np.sqrt(0.5)], atol=1e-12)   # tool frame vs mocap frame at qpos0
+    for fetch in (False, True):
+        env = OracleEnv(fm, has_object=True, controller_type="mocap", fetch_env=fetch)
+        random.seed(0)
+        o, _ = env.reset(seed=0)
+        assert env.sim.nefc >= 13                       # weld (6) + 2 connects (6) + joint coupling (1)
+        g0 = o["observation"][:3].copy()
+        a = np.zeros(4 if fetch else 8, dtype=np.float32)
+        a[0] = 1.0
+        if not fetch:
+            a[3:7] = env.sim.xquat[fm.body_names.index("gripper_tcp")]
+        for _ in range(5):
+            o, r, te, tr, info = env.step(a)
+        moved = o["observation"][:3] - g0
+        assert 0.2 < moved[0] < 0.6 and abs(moved[1]) < 0.05        # 5 x 0.1 m commanded along x
+        assert abs(np.linalg.norm(env.sim.mocap_quat) - 1) < 1e-12 and abs(env.sim.ctrl[0] - 0.5) < 1e-15
+    if True:
+        env = OracleEnv(fm, has_object=True, controller_type="mocap", fetch_env=True)
+        np.testing.assert_allclose(env.sim.mocap_pos, [-0.05154491, 0.01053502, 0.3448586], atol=1e-12)   # mycobot280_mocap.xml:8
+        assert abs(env.height_offset - 0.209981) < 1e-9
