@@ -33,6 +33,8 @@ WORKLOADS = {
     "pick": (dict(has_object=True, reward_type="sparse"), 16384, 1.25e6),
     # IK controller (the reference's default): 5 x (6x6 DLS solve + 20 substeps) per env-step
     "ik": (dict(has_object=True, reward_type="sparse", controller_type="IK"), 16384, 5 * 1.25e6),
+    # mocap controller on the mocap model variant: a 6-row weld drags the arm (13 equality rows instead of 7)
+    "mocap": (dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml"), 16384, 1.45e6),
 }
 METRIC = "env-steps/sec (pick-and-place, 16K envs/GPU) at 1/2/4/8 B200 vs CPU MuJoCo"
 UNIT = "env-steps/s"
@@ -43,8 +45,9 @@ def _cpu_worker(job):
     from mycobotgym_b200 import mjcf
     from oracle.oracle import OracleEnv
 
-    flat = mjcf.load_compiled()
     kw, _, _ = WORKLOADS[workload]
+    flat = mjcf.load_compiled(mjcf.COMPILED_MOCAP if kw.get("controller_type") == "mocap" else mjcf.COMPILED_JOINT)
+    adim = 8 if kw.get("controller_type") == "mocap" else 7
     okw = dict(has_object=kw.get("has_object", True), block_gripper=kw.get("block_gripper", False),
                target_in_the_air=kw.get("target_in_the_air", True), reward_type=kw.get("reward_type", "sparse"),
                controller_type=kw.get("controller_type", "joint"))
@@ -52,12 +55,12 @@ def _cpu_worker(job):
     rng = np.random.default_rng(tid)
     for e in envs:
         e.reset(seed=tid)
-    envs[0].step(np.zeros(7, dtype=np.float32))
+    envs[0].step(np.zeros(adim, dtype=np.float32))
     t0 = time.perf_counter()
     n = 0
     for _ in range(steps):
         for e in envs:
-            a = rng.uniform(-1, 1, 7).astype(np.float32)
+            a = rng.uniform(-1, 1, adim).astype(np.float32)
             o, r, te, tr, info = e.step(a)
             if te or tr:
                 e.reset()
@@ -234,14 +237,14 @@ def run_ours(args):
         per_gpu_rate = value / world
         achieved = per_gpu_rate * flop_per_step / 1e12
         st = stats.cpu().numpy()
-        state_bytes = 2 * 72 * 8 + 28 + (env.obs_dim + 6) * 8 + rbytes + 3
+        state_bytes = 2 * 80 * 8 + 28 + (env.obs_dim + 6) * 8 + rbytes + 3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, {kw.get('controller_type', 'joint')} controller, "
                                    f"{100 if kw.get('controller_type') == 'IK' else 20} substeps/step, uniform random actions "
-                                   f"U[-1,1]^7 float32, 50-step TimeLimit (episode clocks staggered), auto-reset with on-device goal resampling",
+                                   f"U[-1,1]^{env.action_dim} float32, 50-step TimeLimit (episode clocks staggered), auto-reset with on-device goal resampling",
                        "envs_per_gpu": n, "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -36,7 +36,7 @@ extern "C" {
 #define MCB_MAXPAIR 12
 #define MCB_OBS_OBJECT 25
 #define MCB_OBS_REACH 10
-#define MCB_STATE_STRIDE 72 /* doubles per env in the resident state record: qpos19 qvel18 ctrl7 warm18 goal3 qprev6 pad1 */
+#define MCB_STATE_STRIDE 80 /* doubles per env in the resident state record: qpos19 qvel18 ctrl7 warm18 goal3 qprev6 mocap7 pad2 */
 
 /* Flattened, reduced model (host memory; copied to the device by mcb_model_create).
  * Replaces the compiled mjModel the reference builds in MujocoEnv.__init__ (mycobot.py:69-75). */
@@ -115,6 +115,20 @@ typedef struct mcb_model_desc {
   double key_height_offset;
   double key_qpos[MCB_NQ];
   double key_ctrl[MCB_NU];
+  /* mocap variant (mycobot280_mocap.xml): one mocap body welded to gripper_tcp (mocap.xml:16-20); nu = 1 there */
+  int32_t nu;                    /* actuators in use: 7 (joint variant) or 1 (mocap variant: the finger actuator) */
+  int32_t has_weld;
+  int32_t weld_body2;            /* jointed body carrying gripper_tcp */
+  int32_t reserved0_;
+  double Tquat[MCB_NB][4];       /* Tmat as a quaternion (body orientation chain for the weld's orientation error) */
+  double weld_anchor1[3];        /* anchor in the mocap body's frame (eq_data[3:6]) */
+  double weld_anchor2[3];        /* anchor in weld_body2's frame (gripper_tcp offset + eq_data[0:3]) */
+  double weld_relquat[4];        /* orientation of body2 relative to the mocap body at qpos0 (eq_data[6:10]) */
+  double weld_torquescale;
+  double weld_diag[2];           /* body_invweight0 sums: translational, rotational */
+  double weld_solref[2], weld_solimp[5];
+  double mocap_pos0[3], mocap_quat0[4];       /* mocap pose from the XML (mocap.xml:3) */
+  double key_mocap_pos[3], key_mocap_quat[4]; /* ... and from keyframe 0 for fetch envs (mycobot280_mocap.xml:8-9) */
 } mcb_model_desc;
 
 /* Task configuration == the reference constructor kwargs (mycobot.py:30-46) + TimeLimit (__init__.py:34). */
@@ -127,7 +141,8 @@ typedef struct mcb_task_cfg {
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
   int32_t nefc_max;            /* 0 (default): two-tier layout (48-row common case + 128-row fallback launch); 128: fallback layout only */
-  int32_t controller_type;     /* 0 joint (action 7), 1 IK (action 7, or 4 with fetch_env); mycobot.py:36,134-170,190-193 */
+  int32_t controller_type;     /* 0 joint (action 7), 1 IK (7, or 4 with fetch_env), 2 mocap (8, or 4 with fetch_env; needs the mocap
+                                  model variant); mycobot.py:36,90-103,134-193 */
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
   int32_t control_steps;       /* IK: DLS solves per env-step, each followed by frame_skip substeps (5; mycobot.py:35,162) */
   int32_t reserved_;
@@ -151,7 +166,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
 int32_t mcb_batch_destroy(mcb_batch* b);
 int32_t mcb_batch_num_envs(const mcb_batch* b);
 int32_t mcb_batch_obs_dim(const mcb_batch* b);
-int32_t mcb_batch_action_dim(const mcb_batch* b);   /* 7, or 4 for the fetch IK variant (mycobot.py:90-97) */
+int32_t mcb_batch_action_dim(const mcb_batch* b);   /* 7 (joint, IK), 8 (mocap), 4 (fetch IK / fetch mocap); mycobot.py:90-103 */
 
 /* replaces MyCobotEnv.reset / reset_model / _sample_goal (mycobot.py:207-243,506-514).
  * mask: uint8[N] or NULL (= all).  obj_xy: double[N,2] or NULL (device sampler).  goals: double[N,3] or NULL.
@@ -177,12 +192,13 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
  * qacc_warmstart[N,18] goal[N,3] elapsed int32[N]; any pointer may be NULL.  qprev[N,6] = the arm joint
  * positions the reference's *stale* site poses belong to (data.site_xpos is one substep old after mj_step; the IK
  * controller reads it at the start of the next step, mycobot.py:136,151).  Setting qpos without qprev marks the
- * frames fresh (qprev := qpos), which is the state after reset / mj_forward. */
+ * frames fresh (qprev := qpos), which is the state after reset / mj_forward.  mocap[N,7] = data.mocap_pos | mocap_quat
+ * (mocap variant; it persists across resets like in the reference, mycobot.py:207-236 never touches it). */
 int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* qacc_warmstart, double* goal,
-                      int32_t* elapsed, double* qprev, void* stream);
+                      int32_t* elapsed, double* qprev, double* mocap, void* stream);
 int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl,
                       const double* qacc_warmstart, const double* goal, const int32_t* elapsed, const double* qprev,
-                      void* stream);
+                      const double* mocap, void* stream);
 
 /* replaces mujoco.mj_forward on every env (mycobot.py:213,229,306); refreshes qacc_warmstart; optional obs out */
 int32_t mcb_forward(mcb_batch* b, double* obs, double* achieved_goal, double* desired_goal, void* stream);

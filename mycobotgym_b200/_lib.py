@@ -73,8 +73,8 @@ def load():
     L.mcb_reset.argtypes = [vp] + [vp] * 7
     L.mcb_step.argtypes = [vp] + [vp] * 10
     L.mcb_step_host.argtypes = [vp] + [vp] * 10
-    L.mcb_get_state.argtypes = [vp] + [vp] * 8
-    L.mcb_set_state.argtypes = [vp] + [vp] * 8
+    L.mcb_get_state.argtypes = [vp] + [vp] * 9
+    L.mcb_set_state.argtypes = [vp] + [vp] * 9
     L.mcb_forward.argtypes = [vp] + [vp] * 4
     L.mcb_compute_reward.argtypes = [vp, vp, i64, dbl, i32, vp, vp]
     L.mcb_stats.argtypes = [vp, vp, i32, vp]

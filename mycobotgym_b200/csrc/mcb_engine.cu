@@ -126,7 +126,9 @@ struct EnvS {
   double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
   double anchors[12];
   double qprev[6];   // arm qpos the frames in shared memory were computed from (the reference's stale site poses)
-  double ik[14];     // IK controller: target position (3), target quaternion (4), pose error (6)
+  double ik[14];     // IK controller: target position (3), target quaternion (4), pose error (6); mocap variant: weld residual (6)
+  double mocap[8];   // mocap variant: data.mocap_pos (3) | data.mocap_quat (4)
+  double quat5[4];   // mocap variant: orientation quaternion of the body carrying gripper_tcp (composed like mj_kinematics)
   union {
     struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
     struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
@@ -134,7 +136,7 @@ struct EnvS {
   };
   double cdist[MAXC], cpos[MAXC * 3], cframe[MAXC * 9];
   int cpair[MAXC], crow[MAXC];
-  int rmeta[NROW];   // bits 0-7 index (eq / contact / dof), 8 sign, 9-11 sub-row, 12-13 kind (0 connect 1 joint-eq 2 limit 3 contact), 16 inequality
+  int rmeta[NROW];   // bits 0-7 index (eq / contact / dof), 8 sign, 9-11 sub-row, 12-14 kind (0 connect 1 joint-eq 2 limit 3 contact 4 weld), 16 inequality
   int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
   int nR, nC, nF, nU, nefc, ncon, overflow, iters;
 };
@@ -231,6 +233,36 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
         else v = s.xpos[p * 3 + r] + s.xmat[p * 9 + 3 * r] * t[0] + s.xmat[p * 9 + 3 * r + 1] * t[1] + s.xmat[p * 9 + 3 * r + 2] * t[2];
         s.xpos[b * 3 + r] = v;
       }
+    }
+    __syncwarp();
+  }
+  if (MDL.d.has_weld) {
+    if (lane == 0) {
+      // mj_kinematics normalises data.mocap_quat in place; body quaternions are composed along the chain
+      double* mq = s.mocap + 3;
+      double n = sqrt(mq[0] * mq[0] + mq[1] * mq[1] + mq[2] * mq[2] + mq[3] * mq[3]);
+      if (n < MINVAL) { mq[0] = 1; mq[1] = mq[2] = mq[3] = 0; } else { mq[0] /= n; mq[1] /= n; mq[2] /= n; mq[3] /= n; }
+      int chain[NB], nc = 0;
+      for (int b = MDL.d.weld_body2; b >= 0; b = MDL.d.parent[b]) chain[nc++] = b;
+      double q[4] = {1, 0, 0, 0};
+      for (int k = nc - 1; k >= 0; k--) {
+        int b = chain[k];
+        const double* tq = MDL.d.Tquat[b];
+        double t[4] = {q[0] * tq[0] - q[1] * tq[1] - q[2] * tq[2] - q[3] * tq[3], q[0] * tq[1] + q[1] * tq[0] + q[2] * tq[3] - q[3] * tq[2],
+                       q[0] * tq[2] - q[1] * tq[3] + q[2] * tq[0] + q[3] * tq[1], q[0] * tq[3] + q[1] * tq[2] - q[2] * tq[1] + q[3] * tq[0]};
+        double ang = s.qpos[b] - MDL.d.qpos0[b], sn, cs;
+        sincos(0.5 * ang, &sn, &cs);
+        const double* ax = MDL.d.axis[b];
+        double r[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
+        if (ang == 0) { r[0] = 1; r[1] = r[2] = r[3] = 0; }
+        q[0] = t[0] * r[0] - t[1] * r[1] - t[2] * r[2] - t[3] * r[3];
+        q[1] = t[0] * r[1] + t[1] * r[0] + t[2] * r[3] - t[3] * r[2];
+        q[2] = t[0] * r[2] - t[1] * r[3] + t[2] * r[0] + t[3] * r[1];
+        q[3] = t[0] * r[3] + t[1] * r[2] - t[2] * r[1] + t[3] * r[0];
+        double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        q[0] /= nq; q[1] /= nq; q[2] /= nq; q[3] /= nq;
+      }
+      s.quat5[0] = q[0]; s.quat5[1] = q[1]; s.quat5[2] = q[2]; s.quat5[3] = q[3];
     }
     __syncwarp();
   }
@@ -836,7 +868,8 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       int rows = 2 * (pp.dim - 1);
       if (pp.ptype == 0) nRc += rows; else if (pp.ptype == 1) nC += rows; else nF += rows;
     }
-    int nR = 7 + nRc;
+    const int ne0 = MDL.d.has_weld ? 13 : 7;
+    int nR = ne0 + nRc;
     bool fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
     if (!fits) {
       // drop contacts from the end until it fits (the small layout aborts the env instead, see the kernel)
@@ -850,7 +883,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       }
       s.ncon = nc;
     }
-    int r0 = 7, r1 = nR, r2 = nR + nC, orow = 7 + nU;
+    int r0 = ne0, r1 = nR, r2 = nR + nC, orow = ne0 + nU;
     for (int c = 0; c < nc; c++) {
       const PairParam& pp = MDL.pair[s.cpair[c]];
       int rows = 2 * (pp.dim - 1), base;
@@ -862,7 +895,9 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU;
   }
   __syncwarp();
-  if (lane < 7) { s.rmeta[lane] = lane < 6 ? ((lane / 3) | ((lane % 3) << 9)) : (1 << 12); s.omap[lane] = lane; }
+  const int ne0 = MDL.d.has_weld ? 13 : 7, eq0 = ne0 - 7;      // equality rows: [weld (6)] connect (3 + 3) joint coupling (1)
+  if (lane < 7) { s.rmeta[eq0 + lane] = lane < 6 ? ((lane / 3) | ((lane % 3) << 9)) : (1 << 12); s.omap[eq0 + lane] = eq0 + lane; }
+  if (lane < eq0) { s.rmeta[lane] = (lane << 9) | (4 << 12); s.omap[lane] = lane; }
   for (int w = lane; w < s.ncon * 6; w += 32) {
     int c = w / 6, k = w % 6;
     if (k < 2 * (MDL.pair[s.cpair[c]].dim - 1)) {
@@ -876,7 +911,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     int u = __popc(bal & ((1u << lane) - 1));
     int r = s.nR + s.nC + s.nF + u;
     s.rmeta[r] = lane | (neg << 8) | (2 << 12) | RM_INEQ;
-    s.omap[r] = 7 + u;
+    s.omap[r] = ne0 + u;
   }
   // equality Jacobian rows (robot block): item = (connect e, dof j) -> its three rows
   for (int w = lane; w < 2 * NH; w += 32) {
@@ -884,9 +919,47 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     double l1[3], l2[3], rt[3];
     jac_col(s, m, MDL.d.con_body1[e], j, s.anchors + (2 * e) * 3, l1, rt);
     jac_col(s, m, MDL.d.con_body2[e], j, s.anchors + (2 * e + 1) * 3, l2, rt);
-    s.pool[(3 * e) * SR + j] = l1[0] - l2[0];
-    s.pool[(3 * e + 1) * SR + j] = l1[1] - l2[1];
-    s.pool[(3 * e + 2) * SR + j] = l1[2] - l2[2];
+    s.pool[(eq0 + 3 * e) * SR + j] = l1[0] - l2[0];
+    s.pool[(eq0 + 3 * e + 1) * SR + j] = l1[1] - l2[1];
+    s.pool[(eq0 + 3 * e + 2) * SR + j] = l1[2] - l2[2];
+  }
+  if (eq0) {
+    // weld between the (static) mocap body and gripper_tcp (mj_instantiateEquality, mjEQ_WELD): residual in s.ik[0..5]
+    const int b2 = MDL.d.weld_body2;
+    const double* mq = s.mocap + 3;
+    const double* rq = MDL.d.weld_relquat;
+    double quat[4] = {mq[0] * rq[0] - mq[1] * rq[1] - mq[2] * rq[2] - mq[3] * rq[3], mq[0] * rq[1] + mq[1] * rq[0] + mq[2] * rq[3] - mq[3] * rq[2],
+                      mq[0] * rq[2] - mq[1] * rq[3] + mq[2] * rq[0] + mq[3] * rq[1], mq[0] * rq[3] + mq[1] * rq[2] - mq[2] * rq[1] + mq[3] * rq[0]};
+    const double n2[4] = {s.quat5[0], -s.quat5[1], -s.quat5[2], -s.quat5[3]};      // neg(q2)
+    const double ts = MDL.d.weld_torquescale;
+    double p2[3];
+    {
+      const double* R = s.xmat + b2 * 9;
+      const double* a2 = MDL.d.weld_anchor2;
+#pragma unroll
+      for (int r = 0; r < 3; r++) p2[r] = s.xpos[b2 * 3 + r] + R[3 * r] * a2[0] + R[3 * r + 1] * a2[1] + R[3 * r + 2] * a2[2];
+    }
+    if (lane == 0) {
+      double Rm[9];
+      quat2mat(Rm, mq);
+      const double* a1 = MDL.d.weld_anchor1;
+      for (int r = 0; r < 3; r++) s.ik[r] = (s.mocap[r] + Rm[3 * r] * a1[0] + Rm[3 * r + 1] * a1[1] + Rm[3 * r + 2] * a1[2]) - p2[r];
+      double e[4] = {n2[0] * quat[0] - n2[1] * quat[1] - n2[2] * quat[2] - n2[3] * quat[3], n2[0] * quat[1] + n2[1] * quat[0] + n2[2] * quat[3] - n2[3] * quat[2],
+                     n2[0] * quat[2] - n2[1] * quat[3] + n2[2] * quat[0] + n2[3] * quat[1], n2[0] * quat[3] + n2[1] * quat[2] - n2[2] * quat[1] + n2[3] * quat[0]};
+      for (int r = 0; r < 3; r++) s.ik[3 + r] = ts * e[1 + r];
+    }
+    if (lane < NH) {
+      const int j = lane;
+      double lin[3], rot[3];
+      jac_col(s, m, b2, j, p2, lin, rot);
+      double ax[3] = {-rot[0], -rot[1], -rot[2]};                                      // jacr(mocap) - jacr(tcp), the mocap body is static
+      double qa[4] = {-n2[1] * ax[0] - n2[2] * ax[1] - n2[3] * ax[2], n2[0] * ax[0] + n2[2] * ax[2] - n2[3] * ax[1],
+                      n2[0] * ax[1] + n2[3] * ax[0] - n2[1] * ax[2], n2[0] * ax[2] + n2[1] * ax[1] - n2[2] * ax[0]};   // mju_mulQuatAxis
+      double q3[4] = {qa[0] * quat[0] - qa[1] * quat[1] - qa[2] * quat[2] - qa[3] * quat[3], qa[0] * quat[1] + qa[1] * quat[0] + qa[2] * quat[3] - qa[3] * quat[2],
+                      qa[0] * quat[2] - qa[1] * quat[3] + qa[2] * quat[0] + qa[3] * quat[1], qa[0] * quat[3] + qa[1] * quat[2] - qa[2] * quat[1] + qa[3] * quat[0]};
+      s.pool[0 * SR + j] = -lin[0]; s.pool[1 * SR + j] = -lin[1]; s.pool[2 * SR + j] = -lin[2];
+      s.pool[3 * SR + j] = 0.5 * q3[1] * ts; s.pool[4 * SR + j] = 0.5 * q3[2] * ts; s.pool[5 * SR + j] = 0.5 * q3[3] * ts;
+    }
   }
   if (lane < NH) {
     int j = lane;
@@ -897,11 +970,11 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       const double* pc = MDL.d.jeq_polycoef;
       v = -(pc[1] + 2 * pc[2] * dif + 3 * pc[3] * dif * dif + 4 * pc[4] * dif * dif * dif);
     }
-    s.pool[6 * SR + j] = v;
+    s.pool[(eq0 + 6) * SR + j] = v;
   }
   // contact Jacobian rows: items (contact, dof), enumerated per block type so that only owned columns are visited
   const int ncon = s.ncon;
-  const int nRc_ = s.nR - 7;
+  const int nRc_ = s.nR - ne0;
 #pragma unroll 1
   for (int pt = 0; pt < 3; pt++) {
     if ((pt == 0 && nRc_ == 0) || (pt == 1 && s.nC == 0) || (pt == 2 && s.nF == 0)) continue;
@@ -939,7 +1012,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   // per-row regularisation and reference acceleration (mj_makeImpedance, mj_referenceConstraint)
   const int nefc = s.nefc;
   for (int r = lane; r < nefc; r += 32) {
-    int meta = s.rmeta[r], kind = (meta >> 12) & 3, idx = meta & 0xff, sub = (meta >> 9) & 7;
+    int meta = s.rmeta[r], kind = (meta >> 12) & 7, idx = meta & 0xff, sub = (meta >> 9) & 7;
     const double *solref, *solimp;
     double pos, diag, pyr = 0;
     if (kind == 0) {
@@ -951,6 +1024,9 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       const double* pc = MDL.d.jeq_polycoef;
       pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
       solref = MDL.d.jeq_solref; solimp = MDL.d.jeq_solimp; diag = MDL.d.jeq_diag;
+    } else if (kind == 4) {
+      pos = s.ik[sub];
+      solref = MDL.d.weld_solref; solimp = MDL.d.weld_solimp; diag = MDL.d.weld_diag[sub < 3 ? 0 : 1];
     } else if (kind == 2) {
       double v = s.qpos[idx];
       pos = (meta & 0x100) ? MDL.d.jnt_range[idx][1] - v : v - MDL.d.jnt_range[idx][0];
@@ -1053,7 +1129,7 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
 template <class S>
 __device__ void actuation_smooth(S& s, const DevModel* __restrict__ m, int lane, int nva) {
   double force = 0;
-  if (lane < NU) {
+  if (lane < MDL.d.nu) {
     const double* mom = MDL.d.act_moment[lane];
     double len = 0, vel = 0;
     for (int i = 0; i < NH; i++) { double c = mom[i]; if (c != 0) { len += c * s.qpos[i]; vel += c * s.qvel[i]; } }
@@ -1524,6 +1600,7 @@ __device__ void load_state(S& s, const double* __restrict__ st, int lane) {
     else if (w < 62) s.warm[w - 44] = v;
     else if (w < 65) s.goal[w - 62] = v;
     else if (w < 71) s.qprev[w - 65] = v;
+    else if (w < 78) s.mocap[w - 71] = v;
   }
   __syncwarp();
 }
@@ -1537,6 +1614,7 @@ __device__ void store_state(const S& s, double* __restrict__ st, int lane) {
     else if (w < 62) v = s.warm[w - 44];
     else if (w < 65) v = s.goal[w - 62];
     else if (w < 71) v = s.qprev[w - 65];
+    else if (w < 78) v = s.mocap[w - 71];
     st[w] = v;
   }
 }
@@ -1764,7 +1842,7 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
     for (int w = lane; w < NB * 3; w += 32) s.xpos[w] = 0;
     for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
     if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; s.search[lane] = 0; s.Mv[lane] = 0; }
-    if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
+    if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = MDL.d.has_weld ? 13 : 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
     __syncwarp();
     unsigned long long ctr = 0;
     if (valid) { load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane); ctr = a.rng_ctr[env]; }
@@ -1789,19 +1867,46 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
       }
       substeps = 1;
     } else {
-      const bool ik = cfg.controller_type == 1;
-      const int adim = (ik && cfg.fetch_env) ? 4 : NU;
-      float act[NU];
+      const bool ik = cfg.controller_type == 1, mocap = cfg.controller_type == 2;
+      const int adim = cfg.fetch_env ? 4 : (mocap ? 8 : NU);
+      float act[8];
 #pragma unroll
-      for (int k = 0; k < NU; k++) act[k] = 0.0f;
+      for (int k = 0; k < 8; k++) act[k] = 0.0f;
       if (ok) {
         // action = clip(action, -1, 1) in float32 (mycobot.py:133)
 #pragma unroll
-        for (int k = 0; k < NU; k++) if (k < adim) act[k] = fminf(1.0f, fmaxf(-1.0f, a.actions[(size_t)env * adim + k]));
+        for (int k = 0; k < 8; k++) if (k < adim) act[k] = fminf(1.0f, fmaxf(-1.0f, a.actions[(size_t)env * adim + k]));
       }
       double grip_ctrl = 0;
       int nblocks = 1;
-      if (!ik) {
+      if (mocap) {
+        // mocap controller (mycobot.py:172-189 + mocap_set_action / reset_mocap2body_xpos): the mocap body goes to the
+        // (stale) gripper_tcp pose plus the action deltas; the weld then drags the arm during the 20 substeps
+        if (ok) {
+          double qsave = lane < 6 ? s.qpos[lane] : 0.0;
+          if (lane < 6) s.qpos[lane] = s.qprev[lane];
+          __syncwarp();
+          fk(s, m, lane, NB - 1);
+          if (lane < 6) s.qpos[lane] = qsave;
+          __syncwarp();
+          if (lane == 0) {
+            double tcp[3];
+            const int b2 = MDL.d.weld_body2;
+            const double* R = s.xmat + b2 * 9;
+            const double* a2 = MDL.d.weld_anchor2;
+            for (int r = 0; r < 3; r++) tcp[r] = s.xpos[b2 * 3 + r] + R[3 * r] * a2[0] + R[3 * r + 1] * a2[1] + R[3 * r + 2] * a2[2];
+            for (int k = 0; k < 3; k++) s.mocap[k] = tcp[k] + (double)(act[k] * 0.1f);       // float32 product, float64 sum
+            const double fq[4] = {0.5, -0.5, -0.5, 0.5};
+            for (int k = 0; k < 4; k++) {
+              double tq = s.quat5[k];
+              double want = cfg.fetch_env ? fq[k] : (double)act[3 + k];
+              s.mocap[3 + k] = tq + (want - tq);                                             // mocap_quat + (action - tcp_quat)
+            }
+            float ag = cfg.fetch_env ? act[3] : act[7];
+            s.ctrl[MDL.d.nu - 1] = 0.5 + (double)ag * 0.5;
+          }
+        }
+      } else if (!ik) {
         // joint controller: ctrl = action widened to double (mycobot.py:192-193 -> MujocoEnv.do_simulation)
         if (ok && lane < NU) {
           float v = 0.0f;
@@ -1824,7 +1929,7 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         }
         float ag = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NU; k++) if (k == adim - 1) ag = act[k];
+        for (int k = 0; k < 8; k++) if (k == adim - 1) ag = act[k];
         grip_ctrl = 0.5 + (double)ag * 0.5;          // actuation_center + action[-1] * actuation_range (mycobot.py:158-160)
         nblocks = cfg.control_steps;
       }
@@ -1949,11 +2054,15 @@ __global__ void init_state_kernel(double* state, int* elapsed, double* ep_return
   for (int k = 0; k < NQ; k++) st[k] = q0[k];
   for (int k = 0; k < NU; k++) st[37 + k] = c0[k];
   for (int k = 0; k < 6; k++) st[65 + k] = q0[k];
+  const double* mp = fetch ? m->d.key_mocap_pos : m->d.mocap_pos0;
+  const double* mq = fetch ? m->d.key_mocap_quat : m->d.mocap_quat0;
+  for (int k = 0; k < 3; k++) st[71 + k] = mp[k];
+  for (int k = 0; k < 4; k++) st[74 + k] = mq[k];
   elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
 }
 
 // gather / scatter between the resident state record and caller arrays
-__global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int* el, double* qprev, int write) {
+__global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int* el, double* qprev, double* mocap, int write) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
@@ -1965,6 +2074,7 @@ __global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos
     if (goal) for (int k = 0; k < 3; k++) st[62 + k] = goal[(size_t)i * 3 + k];
     if (el) elapsed[i] = el[i];
     if (qprev) for (int k = 0; k < 6; k++) st[65 + k] = qprev[(size_t)i * 6 + k];
+    if (mocap) for (int k = 0; k < 7; k++) st[71 + k] = mocap[(size_t)i * 7 + k];
   } else {
     if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = st[k];
     if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = st[19 + k];
@@ -1973,6 +2083,7 @@ __global__ void state_io_kernel(double* state, int* elapsed, int n, double* qpos
     if (goal) for (int k = 0; k < 3; k++) goal[(size_t)i * 3 + k] = st[62 + k];
     if (el) el[i] = elapsed[i];
     if (qprev) for (int k = 0; k < 6; k++) qprev[(size_t)i * 6 + k] = st[65 + k];
+    if (mocap) for (int k = 0; k < 7; k++) mocap[(size_t)i * 7 + k] = st[71 + k];
   }
 }
 
@@ -2117,7 +2228,8 @@ int32_t mcb_model_destroy(mcb_model* m) {
 
 int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out) {
   if (!m || !cfg || !out || n_envs <= 0) return fail("mcb_batch_create: bad argument");
-  if (cfg->controller_type < 0 || cfg->controller_type > 1) return fail("mcb_batch_create: controller_type must be 0 (joint) or 1 (IK)");
+  if (cfg->controller_type < 0 || cfg->controller_type > 2) return fail("mcb_batch_create: controller_type must be 0 (joint), 1 (IK) or 2 (mocap)");
+  if ((cfg->controller_type == 2) != (m->host.d.has_weld != 0)) return fail("mcb_batch_create: the mocap controller needs the mocap model variant, the other controllers the joint variant");
   if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
   if (cfg->controller_type == 1 && (cfg->control_steps < 1 || cfg->control_steps > 50)) return fail("mcb_batch_create: control_steps out of range");
   if (cfg->reward_type < 0 || cfg->reward_type > 2 || (cfg->reward_type == 2 && !cfg->has_object)) return fail("mcb_batch_create: reward_type must be 0, 1 or 2 (2 needs has_object)");
@@ -2165,7 +2277,7 @@ int32_t mcb_batch_destroy(mcb_batch* b) {
 }
 int32_t mcb_batch_num_envs(const mcb_batch* b) { return b ? b->n_envs : -1; }
 int32_t mcb_batch_obs_dim(const mcb_batch* b) { return b ? b->obs_dim : -1; }
-int32_t mcb_batch_action_dim(const mcb_batch* b) { return b ? ((b->cfg.controller_type == 1 && b->cfg.fetch_env) ? 4 : NU) : -1; }
+int32_t mcb_batch_action_dim(const mcb_batch* b) { return b ? (b->cfg.fetch_env ? 4 : (b->cfg.controller_type == 2 ? 8 : NU)) : -1; }
 
 int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals, double* obs, double* ag, double* dg, void* stream) {
   if (!b) return fail("mcb_reset: null batch");
@@ -2204,17 +2316,17 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
   return total;
 }
 
-int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int32_t* elapsed, double* qprev, void* stream) {
+int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, double* warm, double* goal, int32_t* elapsed, double* qprev, double* mocap, void* stream) {
   if (!b) return fail("mcb_get_state: null batch");
-  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, qprev, 0);
+  state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, qprev, mocap, 0);
   CK(cudaGetLastError());
   return 0;
 }
 int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const double* goal,
-                      const int32_t* elapsed, const double* qprev, void* stream) {
+                      const int32_t* elapsed, const double* qprev, const double* mocap, void* stream) {
   if (!b) return fail("mcb_set_state: null batch");
   state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, (double*)qpos, (double*)qvel, (double*)ctrl,
-                                                                             (double*)warm, (double*)goal, (int*)elapsed, (double*)qprev, 1);
+                                                                             (double*)warm, (double*)goal, (int*)elapsed, (double*)qprev, (double*)mocap, 1);
   CK(cudaGetLastError());
   return 0;
 }

@@ -50,6 +50,10 @@ class ModelDesc(C.Structure):
         ("impratio", _d), ("iterations", _i), ("ls_iterations", _i),
         ("initial_gripper_xpos", _d * 3), ("height_offset", _d), ("init_qpos", _d * NQ), ("init_ctrl", _d * NU),
         ("key_initial_gripper_xpos", _d * 3), ("key_height_offset", _d), ("key_qpos", _d * NQ), ("key_ctrl", _d * NU),
+        ("nu", _i), ("has_weld", _i), ("weld_body2", _i), ("reserved0_", _i),
+        ("Tquat", _d * 4 * NB), ("weld_anchor1", _d * 3), ("weld_anchor2", _d * 3), ("weld_relquat", _d * 4),
+        ("weld_torquescale", _d), ("weld_diag", _d * 2), ("weld_solref", _d * 2), ("weld_solimp", _d * 5),
+        ("mocap_pos0", _d * 3), ("mocap_quat0", _d * 4), ("key_mocap_pos", _d * 3), ("key_mocap_quat", _d * 4),
     ]
 
 
@@ -83,7 +87,7 @@ def _rel_pose(m, body, anc):
 
 def reduce_model(m) -> ModelDesc:
     nbody = int(m["nbody"])
-    assert int(m["nv"]) == NV and int(m["nq"]) == NQ and int(m["nu"]) == NU and int(m["njnt"]) == NB
+    assert int(m["nv"]) == NV and int(m["nq"]) == NQ and int(m["nu"]) in (1, NU) and int(m["njnt"]) == NB
     jointed = [b for b in range(nbody) if m["body_jntnum"][b] > 0]
     assert len(jointed) == NB
     jidx = {b: k for k, b in enumerate(jointed)}
@@ -107,6 +111,7 @@ def reduce_model(m) -> ModelDesc:
             pos, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
         _set(d.Tpos[k], pos)
         _set(d.Tmat[k], quat2mat(quat))
+        _set(d.Tquat[k], quat)
         _set(d.axis[k], m["jnt_axis"][m["body_jntadr"][b]])
     _set(d.parent, parent)
     _set(d.level, level)
@@ -174,8 +179,27 @@ def reduce_model(m) -> ModelDesc:
     assert nh == NHINGE
 
     ci = 0
+    d.has_weld = 0
+    _set(d.mocap_quat0, [1, 0, 0, 0]); _set(d.key_mocap_quat, [1, 0, 0, 0]); _set(d.weld_relquat, [1, 0, 0, 0])
     for e in range(int(m["neq"])):
-        if m["eq_type"][e] == mjcf.EQ_CONNECT:
+        if m["eq_type"][e] == mjcf.EQ_WELD:
+            # the mocap variant's weld (mocap.xml:16-20): body1 = mocap body (static), body2 = gripper_tcp; it must be the first equality
+            b1, b2 = int(m["eq_obj1id"][e]), int(m["eq_obj2id"][e])
+            assert e == 0 and m["body_mocapid"][b1] == 0 and d.has_weld == 0
+            w2 = int(m["body_weldid"][b2])
+            p2, q2 = _rel_pose(m, b2, w2)
+            assert abs(abs(q2[0]) - 1) < 1e-12, "gripper_tcp must share its jointed body's orientation"
+            d.has_weld, d.weld_body2 = 1, jidx[w2]
+            _set(d.weld_anchor1, m["eq_data"][e, 3:6])
+            _set(d.weld_anchor2, p2 + quat2mat(q2) @ m["eq_data"][e, 0:3])
+            _set(d.weld_relquat, m["eq_data"][e, 6:10])
+            d.weld_torquescale = float(m["eq_data"][e, 10])
+            _set(d.weld_diag, m["body_invweight0"][b1] + m["body_invweight0"][b2])
+            _set(d.weld_solref, m["eq_solref"][e])
+            _set(d.weld_solimp, m["eq_solimp"][e])
+            _set(d.mocap_pos0, m["body_pos"][b1]); _set(d.mocap_quat0, m["body_quat"][b1])
+            _set(d.key_mocap_pos, m["key_mpos"][0][:3]); _set(d.key_mocap_quat, m["key_mquat"][0][:4])
+        elif m["eq_type"][e] == mjcf.EQ_CONNECT:
             b1, b2 = int(m["eq_obj1id"][e]), int(m["eq_obj2id"][e])
             assert b1 in jidx and b2 in jidx
             d.con_body1[ci], d.con_body2[ci] = jidx[b1], jidx[b2]
@@ -192,7 +216,7 @@ def reduce_model(m) -> ModelDesc:
             d.jeq_diag = m["dof_invweight0"][d1] + m["dof_invweight0"][d2]
             _set(d.jeq_solref, m["eq_solref"][e])
             _set(d.jeq_solimp, m["eq_solimp"][e])
-    assert ci == 2 and list(m["eq_type"]) == [mjcf.EQ_CONNECT, mjcf.EQ_CONNECT, mjcf.EQ_JOINT]
+    assert ci == 2 and [t for t in m["eq_type"] if t != mjcf.EQ_WELD] == [mjcf.EQ_CONNECT, mjcf.EQ_CONNECT, mjcf.EQ_JOINT]
 
     assert int(m["ngeom"]) == NGEOM
     for g in range(NGEOM):
@@ -249,13 +273,22 @@ def reduce_model(m) -> ModelDesc:
     assert m["site_bodyid"][s_t] == 0
     _set(d.target0_pos, m["site_pos"][s_t])
 
-    _set(d.act_moment, m["actuator_moment"])
-    _set(d.act_gain, m["actuator_gain"])
-    _set(d.act_bias, m["actuator_biasprm"])
-    _set(d.act_ctrlrange, m["actuator_ctrlrange"])
-    _set(d.act_forcerange, m["actuator_forcerange"])
-    _set(d.act_ctrllimited, m["actuator_ctrllimited"])
-    _set(d.act_forcelimited, m["actuator_forcelimited"])
+    nu = int(m["nu"])
+    d.nu = nu
+
+    def padu(a, width=None):
+        a = np.asarray(a, dtype=np.float64)
+        out = np.zeros((NU,) + a.shape[1:])
+        out[:nu] = a
+        return out
+
+    _set(d.act_moment, padu(m["actuator_moment"]))
+    _set(d.act_gain, padu(m["actuator_gain"]))
+    _set(d.act_bias, padu(m["actuator_biasprm"]))
+    _set(d.act_ctrlrange, padu(m["actuator_ctrlrange"]))
+    _set(d.act_forcerange, padu(m["actuator_forcerange"]))
+    _set(d.act_ctrllimited, padu(m["actuator_ctrllimited"]).astype(np.int32))
+    _set(d.act_forcelimited, padu(m["actuator_forcelimited"]).astype(np.int32))
     d.timestep, d.tolerance, d.ls_tolerance = float(m["timestep"]), float(m["tolerance"]), float(m["ls_tolerance"])
     _set(d.gravity, m["gravity"])
     d.meaninertia, d.impratio = float(m["stat_meaninertia"]), float(m["impratio"])
@@ -267,6 +300,8 @@ def reduce_model(m) -> ModelDesc:
     d.height_offset = float((xpos[ob] + xmat[ob] @ m["site_pos"][s_obj])[2])
     _set(d.init_qpos, m["qpos0"])
     _set(d.init_ctrl, np.zeros(NU))
+    if d.has_weld:
+        pass  # fetch keyframe forward uses the keyframe's mocap pose; FK of the robot does not depend on it
     # fetch envs: mj_resetDataKeyframe(0) then forward (mycobot.py:451-472)
     kq = m["key_qpos"][0].copy()
     kq[15:19] /= np.linalg.norm(kq[15:19])
@@ -274,5 +309,5 @@ def reduce_model(m) -> ModelDesc:
     _set(d.key_initial_gripper_xpos, fkk[0][seb] + fkk[2][seb] @ m["site_pos"][s_eef])
     d.key_height_offset = float((fkk[0][ob] + fkk[2][ob] @ m["site_pos"][s_obj])[2])
     _set(d.key_qpos, m["key_qpos"][0])
-    _set(d.key_ctrl, m["key_ctrl"][0])
+    _set(d.key_ctrl, padu(m["key_ctrl"][0]))
     return d

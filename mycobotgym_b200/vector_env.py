@@ -7,8 +7,9 @@ attrs `goal`, `distance_threshold`, `reward_type`) for `num_envs` environments a
 and task logic runs in the CUDA library behind include/mycobot_b200.h; torch only owns the device
 buffers and the stream.  TimeLimit(50) (mycobotgym/__init__.py:34) is folded into the kernel.
 
-Built controllers: joint (`...-joint-v0`) and IK incl. the Fetch variants (`...-IK-v0`, `MyCobotFetch...-IK-v0`);
-mocap ids and the image envs (`-v1`) raise NotImplementedError (SURVEY.md section 8f "next" rows).
+Built controllers: joint (`...-joint-v0`), IK (`...-IK-v0`) and mocap (`...-mocap-v0`, on the mocap model
+variant), each incl. its Fetch variant where the reference registers one; the image envs (`-v1`) raise
+NotImplementedError (out of scope).
 """
 from __future__ import annotations
 
@@ -133,15 +134,18 @@ class ReferenceGoalSampler:
 _MODEL_CACHE = {}
 
 
-def _device_model(device_index):
-    if device_index not in _MODEL_CACHE:
+def _device_model(device_index, variant="joint"):
+    """One device copy per (GPU, model variant): mycobot280.xml serves the joint and IK controllers,
+    mycobot280_mocap.xml (mocap body + weld, one actuator) the mocap controller."""
+    key = (device_index, variant)
+    if key not in _MODEL_CACHE:
         L = _lib.load()
-        flat = mjcf.load_compiled()
+        flat = mjcf.load_compiled(mjcf.COMPILED_MOCAP if variant == "mocap" else mjcf.COMPILED_JOINT)
         desc = flatten.reduce_model(flat)
         h = C.c_void_p()
         _lib.check(L.mcb_model_create(C.byref(desc), device_index, C.byref(h)))
-        _MODEL_CACHE[device_index] = (h, desc, flat)
-    return _MODEL_CACHE[device_index]
+        _MODEL_CACHE[key] = (h, desc, flat)
+    return _MODEL_CACHE[key]
 
 
 def _ptr(t):
@@ -156,16 +160,17 @@ class MyCobotVectorEnv:
                  distance_threshold=0.01, initial_qpos=None, fetch_env=False, reward_type="sparse", frame_skip=20,
                  max_episode_steps=50, device="cuda:0", seed=0, auto_reset=True, goal_source="device", nefc_max=0,
                  **kwargs):
-        if controller_type not in ("joint", "IK"):
-            raise NotImplementedError(f"controller_type={controller_type!r}: the joint and IK controllers are built; mocap is a 'next' row (SURVEY 8f)")
+        if controller_type not in ("joint", "IK", "mocap"):
+            raise ValueError(f"unknown controller_type {controller_type!r}")
         if fetch_env and controller_type == "joint":
             raise AssertionError("Joint controller not supported for Fetch env")        # mycobot.py:96
         if reward_type not in ("sparse", "dense", "reward_shaping"):
             raise ValueError(f"unknown reward_type {reward_type!r}")
         if reward_type == "reward_shaping" and not has_object:
             raise NotImplementedError("reward_shaping on the reach env needs the hidden cube simulated (it is frozen here, DESIGN.md)")
-        if "mocap" in model_path:
-            raise NotImplementedError("mocap model variant is a 'next' row")
+        if ("mocap" in model_path) != (controller_type == "mocap"):
+            raise ValueError("the mocap controller needs mycobot280_mocap.xml and the joint/IK controllers mycobot280.xml "
+                             "(the reference would fail on data.mocap_pos / on the missing actuators)")
         if goal_source not in ("device", "reference"):
             raise ValueError("goal_source must be 'device' or 'reference'")
         if not torch.cuda.is_available():
@@ -182,12 +187,12 @@ class MyCobotVectorEnv:
         self._L = _lib.load()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._dev_index = dev_index
-        self._model, self._desc, self._flat = _device_model(dev_index)
+        self._model, self._desc, self._flat = _device_model(dev_index, "mocap" if controller_type == "mocap" else "joint")
         cfg = flatten.TaskCfg(
             has_object=int(has_object), block_gripper=int(block_gripper), target_in_the_air=int(target_in_the_air),
             reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,
             frame_skip=self.frame_skip, auto_reset=int(self.auto_reset and goal_source == "device"), nefc_max=int(nefc_max),
-            controller_type=0 if controller_type == "joint" else 1, fetch_env=int(bool(fetch_env)), control_steps=int(control_steps),
+            controller_type={"joint": 0, "IK": 1, "mocap": 2}[controller_type], fetch_env=int(bool(fetch_env)), control_steps=int(control_steps),
             reserved_=0, distance_threshold=self.distance_threshold)
         self._cfg = cfg
         with torch.cuda.device(dev_index):
@@ -195,7 +200,7 @@ class MyCobotVectorEnv:
             _lib.check(self._L.mcb_batch_create(self._model, self.num_envs, C.byref(cfg), int(seed), C.byref(h)))
         self._batch = h
         self.obs_dim = self._L.mcb_batch_obs_dim(h)
-        self.action_dim = self._L.mcb_batch_action_dim(h)          # 7, or 4 for the fetch IK variant (mycobot.py:90-97)
+        self.action_dim = self._L.mcb_batch_action_dim(h)          # 7 (joint, IK), 8 (mocap), 4 (fetch variants) (mycobot.py:90-97)
         N, dev = self.num_envs, self.device
         f64 = torch.float64
         self._obs = torch.zeros(N, self.obs_dim, dtype=f64, device=dev)
@@ -301,13 +306,14 @@ class MyCobotVectorEnv:
         st = dict(qpos=torch.empty(N, 19, dtype=torch.float64, device=dev), qvel=torch.empty(N, 18, dtype=torch.float64, device=dev),
                   ctrl=torch.empty(N, 7, dtype=torch.float64, device=dev), qacc_warmstart=torch.empty(N, 18, dtype=torch.float64, device=dev),
                   goal=torch.empty(N, 3, dtype=torch.float64, device=dev), elapsed=torch.empty(N, dtype=torch.int32, device=dev),
-                  qprev=torch.empty(N, 6, dtype=torch.float64, device=dev))
+                  qprev=torch.empty(N, 6, dtype=torch.float64, device=dev), mocap=torch.empty(N, 7, dtype=torch.float64, device=dev))
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_get_state(self._batch, _ptr(st["qpos"]), _ptr(st["qvel"]), _ptr(st["ctrl"]),
-                                            _ptr(st["qacc_warmstart"]), _ptr(st["goal"]), _ptr(st["elapsed"]), _ptr(st["qprev"]), self._stream()))
+                                            _ptr(st["qacc_warmstart"]), _ptr(st["goal"]), _ptr(st["elapsed"]), _ptr(st["qprev"]),
+                                            _ptr(st["mocap"]), self._stream()))
         return st
 
-    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None, qprev=None):
+    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None, qprev=None, mocap=None):
         def prep(x, shape, dt):
             if x is None:
                 return None
@@ -318,7 +324,7 @@ class MyCobotVectorEnv:
         N = self.num_envs
         ts = [prep(qpos, (N, 19), torch.float64), prep(qvel, (N, 18), torch.float64), prep(ctrl, (N, 7), torch.float64),
               prep(qacc_warmstart, (N, 18), torch.float64), prep(goal, (N, 3), torch.float64), prep(elapsed, (N,), torch.int32),
-              prep(qprev, (N, 6), torch.float64)]
+              prep(qprev, (N, 6), torch.float64), prep(mocap, (N, 7), torch.float64)]
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_set_state(self._batch, *[_ptr(t) for t in ts], self._stream()))
             torch.cuda.current_stream(self.device).synchronize()

@@ -57,8 +57,10 @@ def test_registry_matches_reference_registration():
 
 
 def test_unbuilt_rows_fail_loudly():
-    for kwargs in (dict(controller_type="mocap"), dict(reward_type="reward_shaping", has_object=False)):
-        with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):
+        vector_env.MyCobotVectorEnv(num_envs=1, reward_type="reward_shaping", has_object=False)
+    for kwargs in (dict(controller_type="mocap"), dict(model_path="./assets/mycobot280_mocap.xml"), dict(controller_type="osc")):
+        with pytest.raises(ValueError):                      # controller and model variant must agree
             vector_env.MyCobotVectorEnv(num_envs=1, **kwargs)
     with pytest.raises(AssertionError):                      # mycobot.py:96
         vector_env.MyCobotVectorEnv(num_envs=1, fetch_env=True, controller_type="joint")

@@ -480,6 +480,76 @@ def test_ik_controller_matches_oracle(flat, fetch_env, has_object):
     env.close()
 
 
+@pytest.mark.parametrize("fetch_env,has_object", [(False, True), (True, True), (False, False)])
+def test_mocap_controller_matches_oracle(fetch_env, has_object):
+    # mocap controller on the mocap model variant (mycobot.py:172-189, mycobot280_mocap.xml): the mocap body is
+    # placed at the STALE gripper_tcp pose + action and a weld equality (6 rows ahead of the connects) drags the arm there.
+    # Single-step comparisons with the oracle re-synchronised before each step, as for the IK controller.
+    from mycobotgym_b200 import mjcf
+    from oracle.oracle import OracleEnv
+
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP)
+    n, adim = 6, (4 if fetch_env else 8)
+    kw = dict(has_object=has_object, reward_type="dense", controller_type="mocap", fetch_env=fetch_env)
+    env = _env(num_envs=n, model_path="./assets/mycobot280_mocap.xml", auto_reset=False, goal_source="reference", **kw)
+    assert env.action_dim == adim and env.single_action_space.shape == (adim,)
+    oes = [OracleEnv(fm, **kw) for _ in range(n)]
+    ftight = mjcf_tight(fm)
+    oes_tight = [OracleEnv(ftight, **kw) for _ in range(n)]
+    random.seed(21)
+    xy, goals = [], []
+    for i, oe in enumerate(oes):
+        oe.reset(seed=200 + i)
+        xy.append(oe.sim.qpos[12:14].copy()); goals.append(oe.goal.copy())
+        oes_tight[i].goal = oe.goal.copy()
+    obs, _ = env.reset(object_xy=np.array(xy) if has_object else None, goals=np.array(goals))
+    assert abs(env.height_offset - oes[0].height_offset) < 1e-12
+    np.testing.assert_allclose(env.initial_gripper_xpos, oes[0].initial_gripper_xpos, atol=1e-12)
+    st0 = env.get_state()
+    np.testing.assert_allclose(st0["mocap"][0].cpu().numpy(), np.concatenate((oes[0].sim.mocap_pos, oes[0].sim.mocap_quat)), atol=1e-15)
+    np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), oes[0]._get_obs()["observation"], atol=1e-9)
+    rng = np.random.default_rng(22)
+    nq = 19 if has_object else 12
+    tcp = fm["body_names"].index("gripper_tcp")
+
+    def sync(oe, st, i):
+        q_stale = st["qpos"][i].copy()
+        q_stale[:6] = st["qprev"][i]
+        oe.sim.set_state(q_stale, st["qvel"][i], st["ctrl"][i, :1], st["qacc_warmstart"][i])
+        oe.sim.kinematics()                                   # stale gripper_tcp pose, as the reference holds it
+        oe.sim.qpos[:] = st["qpos"][i]
+        oe.sim.mocap_pos[:] = st["mocap"][i, :3]
+        oe.sim.mocap_quat[:] = st["mocap"][i, 3:]
+
+    for t in range(4):
+        st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+        for i in range(n):
+            sync(oes[i], st, i)
+            sync(oes_tight[i], st, i)
+            oes_tight[i].sim.qvel[:6] *= 1 + 2.2e-16
+        assert t == 0 or np.abs(st["qprev"] - st["qpos"][:, :6]).max() > 1e-6
+        acts = rng.uniform(-1, 1, (n, adim)).astype(np.float32)
+        if not fetch_env:
+            # orientation commands near the current tool orientation for half the envs, arbitrary for the rest
+            for i in range(0, n, 2):
+                acts[i, 3:7] = (oes[i].sim.xquat[tcp] + 0.1 * rng.uniform(-1, 1, 4)).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
+        after = env.get_state()
+        for i, oe in enumerate(oes):
+            o, r, te, tr, inf = oe.step(acts[i])
+            oes_tight[i].step(acts[i])
+            sens = np.abs(oes_tight[i].sim.qpos[:nq] - oe.sim.qpos[:nq]).max()
+            tol = min(max(1e-7, 100 * sens), 1e-4)
+            np.testing.assert_allclose(after["mocap"][i].cpu().numpy(), np.concatenate((oe.sim.mocap_pos, oe.sim.mocap_quat)), atol=1e-13,
+                                       err_msg=f"mocap pose step {t} env {i}")
+            np.testing.assert_allclose(after["qpos"][i, :nq].cpu().numpy(), oe.sim.qpos[:nq], atol=tol, rtol=0, err_msg=f"step {t} env {i}")
+            assert abs(float(after["ctrl"][i, 0]) - oe.sim.ctrl[0]) == 0.0
+            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol * 10, rtol=0)
+            assert abs(float(rew[i]) - float(r)) < tol * 10 and bool(term[i]) == te
+    assert np.abs(after["qpos"][:, :6].cpu().numpy() - st0["qpos"][:, :6].cpu().numpy()).max() > 0.05     # the weld really moved the arm
+    env.close()
+
+
 def mjcf_tight(flat):
     from mycobotgym_b200 import mjcf
 
@@ -512,7 +582,9 @@ def test_make_registry_ids_and_reference_goal_autoreset():
     for env_id, obs_dim, adim, rdtype in [("MyCobotPickAndPlace-Sparse-joint-v0", 25, 7, torch.float32),
                                           ("MyCobotReach-Dense-joint-v0", 10, 7, torch.float64),
                                           ("MyCobotPickAndPlace-RewardShaping-joint-v0", 25, 7, torch.float64),
-                                          ("MyCobotFetchReach-Sparse-IK-v0", 10, 4, torch.float32)]:
+                                          ("MyCobotFetchReach-Sparse-IK-v0", 10, 4, torch.float32),
+                                          ("MyCobotReach-Dense-mocap-v0", 10, 8, torch.float64),
+                                          ("MyCobotFetchPickAndPlace-Sparse-mocap-v0", 25, 4, torch.float32)]:
         env = make(env_id, num_envs=4)
         obs, info = env.reset(seed=0)
         assert obs["observation"].shape == (4, obs_dim) and info == {} and env.action_dim == adim
@@ -520,7 +592,7 @@ def test_make_registry_ids_and_reference_goal_autoreset():
         assert rew.dtype == rdtype and rew.shape == (4,) and term.dtype == torch.bool and "is_success" in inf
         env.close()
     with pytest.raises(NotImplementedError):
-        make("MyCobotReach-Dense-mocap-v0", num_envs=1)
+        make("MyCobotReach-Dense-joint-v1", num_envs=1)           # image envs are out of scope
     # auto-reset with the reference's (host-side, seeded) sampling protocol: goals change at the TimeLimit, state restarts
     env = make("MyCobotPickAndPlace-Sparse-joint-v0", num_envs=3, goal_source="reference", max_episode_steps=3)
     random.seed(5)
