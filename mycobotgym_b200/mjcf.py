@@ -809,8 +809,9 @@ def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco,
         return mujoco.mj_id2name(mjm, objtype, i) or ""
 
     m["body_names"] = [name(mujoco.mjtObj.mjOBJ_BODY, i) for i in range(nbody)]
-    for k in ("body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr"):
+    for k in ("body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_mocapid"):
         m[k] = np.array(getattr(mjm, k), dtype=np.int32)
+    m["nmocap"] = int(mjm.nmocap)
     for k in ("body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_subtreemass"):
         m[k] = np.array(getattr(mjm, k), dtype=np.float64)
     m["body_invweight0"] = np.array(mjm.body_invweight0, dtype=np.float64).reshape(nbody, 2)
@@ -825,7 +826,8 @@ def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco,
         m[k] = np.array(getattr(mjm, k), dtype=np.float64)
     m["nM"] = int(mjm.nM)
     m["qpos0"] = np.array(mjm.qpos0, dtype=np.float64)
-    keep = [g for g in range(mjm.ngeom) if mjm.geom_type[g] in (GEOM_TYPES["plane"], GEOM_TYPES["box"])]
+    keep = [g for g in range(mjm.ngeom) if mjm.geom_type[g] in (GEOM_TYPES["plane"], GEOM_TYPES["box"])
+            and (mjm.geom_contype[g] or mjm.geom_conaffinity[g])]
     m["ngeom"] = len(keep)
     m["geom_names"] = [name(mujoco.mjtObj.mjOBJ_GEOM, g) for g in keep]
     for k, dt in (("geom_type", np.int32), ("geom_bodyid", np.int32), ("geom_contype", np.int32), ("geom_conaffinity", np.int32),
@@ -850,7 +852,7 @@ def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco,
     m["eq_type"] = np.array([{int(mujoco.mjtEq.mjEQ_CONNECT): EQ_CONNECT, int(mujoco.mjtEq.mjEQ_WELD): EQ_WELD,
                               int(mujoco.mjtEq.mjEQ_JOINT): EQ_JOINT}[int(t)] for t in mjm.eq_type], dtype=np.int32)
     m["eq_obj1id"], m["eq_obj2id"] = np.array(mjm.eq_obj1id, dtype=np.int32), np.array(mjm.eq_obj2id, dtype=np.int32)
-    m["eq_data"] = np.array(mjm.eq_data, dtype=np.float64)[:, :7]
+    m["eq_data"] = np.array(mjm.eq_data, dtype=np.float64)[:, :11]
     m["eq_solref"], m["eq_solimp"] = np.array(mjm.eq_solref, dtype=np.float64), np.array(mjm.eq_solimp, dtype=np.float64)
     nu = mjm.nu
     m["nu"] = int(nu)
@@ -874,6 +876,8 @@ def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco,
     m["key_qpos"] = np.array(mjm.key_qpos, dtype=np.float64).reshape(mjm.nkey, nq)
     m["key_qvel"] = np.array(mjm.key_qvel, dtype=np.float64).reshape(mjm.nkey, nv)
     m["key_ctrl"] = np.array(mjm.key_ctrl, dtype=np.float64).reshape(mjm.nkey, nu)
+    m["key_mpos"] = np.array(mjm.key_mpos, dtype=np.float64).reshape(mjm.nkey, 3 * mjm.nmocap)
+    m["key_mquat"] = np.array(mjm.key_mquat, dtype=np.float64).reshape(mjm.nkey, 4 * mjm.nmocap)
     m["stat_meaninertia"] = float(mjm.stat.meaninertia)
     m["M0"] = mass_matrix_numpy(m, fk_numpy(m, m["qpos0"]))
     m["compile_log"] = ["filled from a live mujoco.MjModel; mesh geoms dropped from collision"]
