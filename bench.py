@@ -40,6 +40,49 @@ METRIC = "env-steps/sec (pick-and-place, 16K envs/GPU) at 1/2/4/8 B200 vs CPU Mu
 UNIT = "env-steps/s"
 
 
+def her_relabel_leg(env, acts, dev, flush):
+    """SURVEY 8d config 3 "timed separately": HER relabelling (train.py:93-97, n_sampled_goal=4) of a batch of 4 * N
+    transitions out of a device-resident replay ring filled by 52 rollout steps.  HBM-bound gather; reported against
+    MEASURED_PEAKS.json's copy bandwidth.  Algorithmic bytes per sample: rows read + rows written."""
+    import torch
+
+    from mycobotgym_b200.her import DeviceHerReplayBuffer
+
+    n, T = env.num_envs, 64
+    buf = DeviceHerReplayBuffer(T * n, env, seed=7)
+    obs = {k: v.clone() for k, v in env._obs_dict().items()}
+    for t in range(52):
+        a = acts[t % acts.shape[0]]
+        out = env.step(a)
+        buf.add_step(obs, a, out)
+        obs = {k: v.clone() for k, v in out[0].items()}
+    B = 4 * n
+    for _ in range(3):
+        buf.sample(B)
+    reps = 10
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for r in range(reps):
+        flush.zero_()
+        ev[r][0].record()
+        buf.sample(B)
+        ev[r][1].record()
+    torch.cuda.synchronize()
+    assert buf.failed_samples() == 0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / reps
+    od, ad = env.obs_dim, env.action_dim
+    bytes_per_sample = 2 * ((2 * od + 9) * 8 + ad * 4 + 4) + 2 + 8 + 4      # rows read + rows written, flags + episode table, dones out
+    peak = None
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    gbs = B * bytes_per_sample / (ms * 1e-3) / 1e9
+    buf.close()
+    return {"batch": B, "ms": ms, "samples_per_s": B / (ms * 1e-3), "bytes_per_sample": bytes_per_sample, "achieved_GBps": gbs,
+            "peak_GBps": peak, "frac": (gbs / peak) if peak else None, "ring": f"{T} steps x {n} envs, 52 filled",
+            "note": "mcb_her_sample: future-strategy relabel + compute_reward, one warp per sample; 1 kernel + 1 memset per call"}
+
+
 def _cpu_worker(job):
     workload, tid, envs_per_worker, steps = job
     from mycobotgym_b200 import mjcf
@@ -228,6 +271,10 @@ def run_ours(args):
     rbytes = 4 if kw["reward_type"] == "sparse" else 8
     h2d, d2h = n * env.action_dim * 4, n * ((env.obs_dim + 6) * 8 + rbytes + 3)
 
+    her = None
+    if rank == 0 and world == 1 and kw["reward_type"] in ("sparse", "dense") and not args.no_her:
+        her = her_relabel_leg(env, acts, dev, flush)
+
     if rank == 0:
         L = _lib.load()
         import ctypes as C
@@ -261,6 +308,7 @@ def run_ours(args):
             "episode_stats": {"episodes": st[0], "successes": st[1], "return_sum": st[2], "length_sum": st[3], "env_steps": st[4],
                               "row_overflows": st[5], "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
             "wall_s_timed_region": t_wall,
+            "her_relabel": her,
         }
         print(json.dumps(line), flush=True)
     env.close()
@@ -276,6 +324,7 @@ def main():
     ap.add_argument("--workload", default="pick", choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-her", action="store_true", help="skip the separately timed HER relabel leg")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-port timing leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -224,6 +224,32 @@ int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the m
 int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out); /* DFMA micro-kernel, CUDA-event timed */
 int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, float* ms_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device-resident HER replay ("future" strategy) -- replaces stable_baselines3.HerReplayBuffer as
+ * mycobotgym/scripts/train.py:89-97 configures it (n_sampled_goal=4, goal_selection_strategy="future"), including its
+ * env.compute_reward call on relabelled goals (mycobot.py:289-295).  All array arguments are device pointers.
+ * Semantics follow stable_baselines3==2.0.0a0 her_replay_buffer.py: per stored transition ep_start / ep_length,
+ * only transitions of complete episodes are sampled, the first int((1 - 1/(n_sampled_goal+1)) * batch) samples get
+ * desired_goal := next_achieved_goal of a transition drawn uniformly from [current, episode end) and a recomputed
+ * reward (float32), dones are returned as done * (1 - timeout). */
+typedef struct mcb_her mcb_her;
+int32_t mcb_her_create(int32_t n_envs, int32_t buffer_steps, int32_t obs_dim, int32_t action_dim, int32_t n_sampled_goal,
+                       int32_t reward_type, double distance_threshold, uint64_t seed, mcb_her** out);
+void mcb_her_destroy(mcb_her* h);
+/* HerReplayBuffer.add: one transition per env, [N, .] rows; rewards float32 (rewards_f64 = 0) or float64 (1) */
+int32_t mcb_her_add(mcb_her* h, const double* obs, const double* achieved_goal, const double* desired_goal, const double* next_obs,
+                    const double* next_achieved_goal, const float* actions, const void* rewards, int32_t rewards_f64,
+                    const uint8_t* terminated, const uint8_t* truncated, void* stream);
+int64_t mcb_her_size(const mcb_her* h);                       /* stored transitions (all envs) */
+/* debugging / tests: copies of the episode table [T, N] (device) and the number of sampleable transitions (host) */
+int32_t mcb_her_episode_table(mcb_her* h, int32_t* ep_start, int32_t* ep_length, int64_t* n_valid_host, void* stream);
+/* HerReplayBuffer.sample(batch_size).  inj_index [batch] (flat t * N + env) and inj_future [batch] (index inside the
+ * episode) replace the device RNG draws when non-null (parity tests).  index_out [batch, 2] (optional) receives the
+ * sampled flat index and the relabel source (or -1).  *fail_count (device int) counts samples that found no complete episode. */
+int32_t mcb_her_sample(mcb_her* h, int32_t batch_size, const int64_t* inj_index, const int32_t* inj_future, double* obs, double* achieved_goal,
+                       double* desired_goal, double* next_obs, double* next_achieved_goal, float* actions, float* rewards, float* dones,
+                       int64_t* index_out, int32_t* fail_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

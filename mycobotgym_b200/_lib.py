@@ -25,7 +25,8 @@ EXPORTS = [
     "mcb_model_destroy", "mcb_batch_create", "mcb_batch_destroy", "mcb_batch_num_envs", "mcb_batch_obs_dim", "mcb_batch_action_dim",
     "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
     "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
-    "mcb_time_step_kernel",
+    "mcb_time_step_kernel", "mcb_her_create", "mcb_her_destroy", "mcb_her_add", "mcb_her_size", "mcb_her_episode_table",
+    "mcb_her_sample",
 ]
 
 
@@ -81,6 +82,14 @@ def load():
     L.mcb_debug_forward.argtypes = [vp, i32, i32, vp, i32, vp]
     L.mcb_last_step_launches.argtypes = [vp]
     L.mcb_fp64_peak_probe.argtypes = [i32, i32, C.POINTER(dbl)]
+    L.mcb_her_create.argtypes = [i32, i32, i32, i32, i32, i32, dbl, u64, C.POINTER(vp)]
+    L.mcb_her_destroy.argtypes = [vp]
+    L.mcb_her_destroy.restype = None
+    L.mcb_her_add.argtypes = [vp] + [vp] * 7 + [i32, vp, vp, vp]
+    L.mcb_her_size.argtypes = [vp]
+    L.mcb_her_size.restype = i64
+    L.mcb_her_episode_table.argtypes = [vp, vp, vp, C.POINTER(i64), vp]
+    L.mcb_her_sample.argtypes = [vp, i32] + [vp] * 13
     assert L.mcb_model_desc_size() == C.sizeof(ModelDesc), (L.mcb_model_desc_size(), C.sizeof(ModelDesc))
     assert L.mcb_task_cfg_size() == C.sizeof(TaskCfg), (L.mcb_task_cfg_size(), C.sizeof(TaskCfg))
     _lib = L

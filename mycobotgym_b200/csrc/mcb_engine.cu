@@ -2427,3 +2427,5 @@ int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, f
 }
 
 }  // extern "C"
+
+#include "mcb_her.cuh"
