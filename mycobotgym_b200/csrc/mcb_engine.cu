@@ -362,13 +362,34 @@ __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba
   __syncwarp();
 }
 
-// chol_solve_blk<N0, N, DADD>(): Cholesky A = L L' of the diagonal block rows/cols [N0, N0+N) of a packed symmetric
-// matrix (src -> dst, may alias) AND the solution of A x = b, in one pass.  Lane i owns row i in registers;
-// finished rows are broadcast through dst.  Lane 31 carries the right-hand side (read from the shared vector
-// `bsrc`) as an extra row, so the forward substitution costs nothing extra; its entries go to the lanes through
-// the shared scratch `ytmp`; the back substitution is a branch-free shuffle chain.  DADD: `dadd` is added to the
-// lane's diagonal entry first (Euler: h * damping).  Lanes outside the block return 0.
-// Fully unrolled: every shared-memory offset is an immediate, no index arithmetic or selects in the inner loops.
+// fast_rcp(): 1 / d for d >= MINVAL without the library routine's special-case branches: MUFU seed (about 20 bits)
+// and two Newton steps (error about 1 ulp; the factorisation does not need a correctly rounded quotient).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+
+// 64-bit shuffle as two explicit 32-bit shuffles (the generic double overload left register swaps behind)
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __shfl_sync(FULLMASK, __double2loint(v), src);
+  int hi = __shfl_sync(FULLMASK, __double2hiint(v), src);
+  return __hiloint2double(hi, lo);
+}
+
+// chol_solve_blk<N0, N, DADD>(): factorisation A = L D L' (unit lower L) of the diagonal block rows/cols [N0, N0+N) of
+// a packed symmetric matrix (src -> dst, may alias) AND the solution of A x = b, in one pass.  Lane i owns row i in
+// registers as the UNSCALED entries u_ik = l_ik d_k, so a column step is one dot product with the scaled row j of L
+// (broadcast from shared memory), one shuffle of the pivot, one reciprocal and one multiply; finished entries
+// l_ij = u_ij / d_j go to dst (strict lower triangle; the diagonal slot receives 1).  Lane 31 carries the right-hand
+// side (read from the shared vector `bsrc`) as an extra row, so the forward substitution AND the scaling by D^-1 cost
+// nothing extra; its entries reach the lanes through the shared scratch `ytmp`; the back substitution with the unit
+// triangle is a shuffle + fma chain without divisions.  DADD: `dadd` is added to the lane's diagonal entry first
+// (Euler: h * damping).  Pivots below MINVAL are clamped (mju_cholFactor's mindiag).  Lanes outside the block return 0.
+// Fully unrolled: every shared-memory offset is an immediate, no index arithmetic in the inner loops.
 template <int N0, int N, bool DADD>
 __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, const double* bsrc, double* ytmp, double dadd, int lane) {
   const int i = lane;
@@ -376,37 +397,35 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, co
   const bool rhs = (i == 31);
   const int ro = i * (i + 1) / 2 + N0;
   const double* base = rhs ? bsrc + N0 : src + ro;      // lane 31 loads b, the others their matrix row
+  double* wbase = rhs ? ytmp + N0 : dst + ro;           // ... and stores D^-1 L^-1 b, the others their row of L
+  const int ieff = (mine || rhs) ? i : -1;              // entry (i, N0 + k) exists for this lane iff ieff >= N0 + k
   double row[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
-    double v = (rhs || (mine && N0 + k <= i)) ? base[k] : 0.0;
+    double v = (ieff >= N0 + k) ? base[k] : 0.0;
     if (DADD) v += (N0 + k == i) ? dadd : 0.0;     // (a separate "row[i - N0] += dadd" would index row[] dynamically => local memory)
     row[k] = v;
   }
-  double myinv = 0.0;
 #pragma unroll
   for (int j = 0; j < N; j++) {
     const double* rj = dst + TRI(N0 + j, N0);
     double s0 = row[j], s1 = 0.0;
 #pragma unroll
     for (int k = 0; k < j; k++) { if (k & 1) s1 -= row[k] * rj[k]; else s0 -= row[k] * rj[k]; }
-    double sv = s0 + s1;
-    if (i == N0 + j && sv < MINVAL) sv = MINVAL;     // rank-deficiency guard on the pivot (mju_cholFactor's mindiag)
-    double sjj = __shfl_sync(FULLMASK, sv, N0 + j);
-    double inv = rsqrt(sjj);
-    double l = sv * inv;                               // pivot lane: sqrt(sjj); lane 31: entry j of L^-1 b
-    row[j] = l;
-    if (mine && i >= N0 + j) dst[ro + j] = l;
-    if (rhs) ytmp[N0 + j] = l;
-    if (i == N0 + j) myinv = inv;
+    const double sv = s0 + s1;
+    row[j] = sv;
+    double d = shfl_d(sv, N0 + j);
+    d = (d < MINVAL) ? MINVAL : d;                      // (fmax() drags NaN handling along)
+    const double l = sv * fast_rcp(d);
+    if (ieff >= N0 + j) wbase[j] = l;
     __syncwarp();
   }
   double x = mine ? ytmp[i] : 0.0;
 #pragma unroll
-  for (int k = N0 + N - 1; k >= N0; k--) {
-    double xk = __shfl_sync(FULLMASK, x * myinv, k);
-    double lk = (i < k && i >= N0) ? dst[TRI(k, 0) + i] : 0.0;
-    x = (i == k) ? xk : fma(-lk, xk, x);
+  for (int k = N0 + N - 1; k > N0; k--) {
+    const double xk = shfl_d(x, k);
+    const double lk = (i < k && i >= N0) ? dst[TRI(k, 0) + i] : 0.0;
+    x = fma(-lk, xk, x);
   }
   return x;
 }

@@ -77,3 +77,25 @@ print(f"\n== top {topn} source lines by samples")
 for ln, (s, ie) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:topn]:
     text = src[ln - 1].strip()[:110] if ln else "?"
     print(f"  L{ln}: {100 * s / tot_s:5.2f}% smp {100 * ie / tot_i:5.2f}% ins | {text}")
+
+# ---- opcode-class mix per device function (instructions executed) ----
+CLASSES = [("fp64", r"^(DFMA|DMUL|DADD|DSETP|DMNMX)"), ("lds", r"^LDS"), ("sts", r"^STS"), ("ldst_other", r"^(LD|ST|ATOM|RED)"),
+           ("branch", r"^(BRA|BSSY|BSYNC|BREAK|CALL|RET|EXIT|WARPSYNC|BAR|JMP)"), ("setp", r"^(ISETP|FSETP|PLOP3|PSETP)"),
+           ("imad", r"^IMAD"), ("shfl", r"^(SHFL|VOTE|MATCH|REDUX)"), ("mufu", r"^MUFU"),
+           ("int_other", r"^(LOP3|VIADD|IADD3|LEA|SHF|SEL|FSEL|MOV|UMOV|CS2R|PRMT|BREV|FLO|ULEA|S2UR|S2R|UIADD|ULOP|USHF|UIMAD|R2UR|POPC|VIADDMNMX|IABS|I2F|F2I|I2FP|F2F|NOP)")]
+mix = {}
+for k in range(n):
+    r = data[k]
+    ie = float(r[ci["Instructions Executed"]] or 0)
+    m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[ci["Source"]])
+    op = m.group(2) if m else "?"
+    cls = next((c for c, pat in CLASSES if re.match(pat, op)), "other")
+    d = mix.setdefault(func_of(lines[k]), {})
+    d[cls] = d.get(cls, 0.0) + ie
+names = [c for c, _ in CLASSES] + ["other"]
+print("\n== opcode-class mix per device function (% of ALL executed warp instructions)")
+print("  " + " " * 24 + "".join(f"{c:>11s}" for c in names) + "      total")
+for f, d in sorted(mix.items(), key=lambda kv: -sum(kv[1].values()))[:24]:
+    print(f"  {f:24s}" + "".join(f"{100 * d.get(c, 0) / tot_i:10.2f}%" for c in names) + f"{100 * sum(d.values()) / tot_i:10.2f}%")
+allc = {c: sum(d.get(c, 0) for d in mix.values()) for c in names}
+print(f"  {'ALL':24s}" + "".join(f"{100 * allc[c] / tot_i:10.2f}%" for c in names))
