@@ -142,6 +142,24 @@ struct EnvS {
 };
 
 // ------------------------------------------------------------------------------------------------
+// fast_rcp(): 1 / d for d >= MINVAL without the library routine's special-case branches: MUFU seed (about 20 bits)
+// and two Newton steps (error about 1 ulp; the factorisation does not need a correctly rounded quotient).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+
+// 64-bit shuffle as two explicit 32-bit shuffles (the generic double overload left register swaps behind)
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __shfl_sync(FULLMASK, __double2loint(v), src);
+  int hi = __shfl_sync(FULLMASK, __double2hiint(v), src);
+  return __hiloint2double(hi, lo);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
@@ -362,24 +380,6 @@ __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba
   __syncwarp();
 }
 
-// fast_rcp(): 1 / d for d >= MINVAL without the library routine's special-case branches: MUFU seed (about 20 bits)
-// and two Newton steps (error about 1 ulp; the factorisation does not need a correctly rounded quotient).
-__device__ __forceinline__ double fast_rcp(double d) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  return fma(y, e, y);
-}
-
-// 64-bit shuffle as two explicit 32-bit shuffles (the generic double overload left register swaps behind)
-__device__ __forceinline__ double shfl_d(double v, int src) {
-  int lo = __shfl_sync(FULLMASK, __double2loint(v), src);
-  int hi = __shfl_sync(FULLMASK, __double2hiint(v), src);
-  return __hiloint2double(hi, lo);
-}
-
 // chol_solve_blk<N0, N, DADD>(): factorisation A = L D L' (unit lower L) of the diagonal block rows/cols [N0, N0+N) of
 // a packed symmetric matrix (src -> dst, may alias) AND the solution of A x = b, in one pass.  Lane i owns row i in
 // registers as the UNSCALED entries u_ik = l_ik d_k, so a column step is one dot product with the scaled row j of L
@@ -442,7 +442,7 @@ __device__ __forceinline__ double factor_solve(const double* src, double* dst, c
 template <bool DADD>
 __device__ __forceinline__ double factor_solve_M(const double* M, double* dst, const double* bsrc, double* ytmp, double dadd, int lane, int nva) {
   double x = chol_solve_blk<0, 12, DADD>(M, dst, bsrc, ytmp, dadd, lane);
-  if (lane >= NH && lane < nva) x = bsrc[lane] / (M[TRI(lane, 0) + lane] + dadd);
+  if (lane >= NH && lane < nva) x = bsrc[lane] * fast_rcp(M[TRI(lane, 0) + lane] + dadd);
   return x;
 }
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
@@ -500,13 +500,13 @@ __device__ __forceinline__ void emit_contact(S& s, int idx, int pair, double dis
   f[0] = nrm[0]; f[1] = nrm[1]; f[2] = nrm[2];
   // mju_makeFrame
   double nn = sqrt(dot3(f, f));
-  if (nn < MINVAL) { f[0] = 1; f[1] = f[2] = 0; } else { f[0] /= nn; f[1] /= nn; f[2] /= nn; }
+  if (nn < MINVAL) { f[0] = 1; f[1] = f[2] = 0; } else { const double in = fast_rcp(nn); f[0] *= in; f[1] *= in; f[2] *= in; }
   f[3] = f[4] = f[5] = 0;
   if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
   double t = dot3(f, f + 3);
   f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
   nn = sqrt(dot3(f + 3, f + 3));
-  if (nn < MINVAL) { f[3] = 1; f[4] = f[5] = 0; } else { f[3] /= nn; f[4] /= nn; f[5] /= nn; }
+  if (nn < MINVAL) { f[3] = 1; f[4] = f[5] = 0; } else { const double in = fast_rcp(nn); f[3] *= in; f[4] *= in; f[5] *= in; }
   cross3(f + 6, f, f + 3);
 #pragma unroll
   for (int k = 0; k < 9; k++) s.cframe[idx * 9 + k] = f[k];
@@ -592,7 +592,7 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
       cross3(Lx, cs + CS_A + 3 * i, cs + CS_B + 3 * j);
       double l = sqrt(dot3(Lx, Lx));
       if (l >= 1e-6) {
-        for (int k = 0; k < 3; k++) Lx[k] /= l;
+        { const double il = fast_rcp(l); for (int k = 0; k < 3; k++) Lx[k] *= il; }   // (x / l with x == 0 takes div.rn.f64's slow path)
         t = dot3(d, Lx);
         double ra = 0, rb = 0;
         for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(cs + CS_A + 3 * k, Lx)); rb += s2[k] * fabs(dot3(cs + CS_B + 3 * k, Lx)); }
@@ -1481,7 +1481,7 @@ __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lan
   else if (lane == 15 && nva > NH) {
     double ax[3] = {s.qvel[15], s.qvel[16], s.qvel[17]};
     double n = sqrt(dot3(ax, ax));
-    if (n < MINVAL) { ax[0] = 1; ax[1] = ax[2] = 0; } else { ax[0] /= n; ax[1] /= n; ax[2] /= n; }
+    if (n < MINVAL) { ax[0] = 1; ax[1] = ax[2] = 0; } else { const double in = fast_rcp(n); ax[0] *= in; ax[1] *= in; ax[2] *= in; }
     double ang = h * n;
     double qr[4];
     if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
@@ -1489,7 +1489,7 @@ __device__ __noinline__ void euler(S& s, const DevModel* __restrict__ m, int lan
     double* q = s.qpos + 15;
     double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     double a[4];
-    if (nq < MINVAL) { a[0] = 1; a[1] = a[2] = a[3] = 0; } else { a[0] = q[0] / nq; a[1] = q[1] / nq; a[2] = q[2] / nq; a[3] = q[3] / nq; }
+    if (nq < MINVAL) { a[0] = 1; a[1] = a[2] = a[3] = 0; } else { const double in = fast_rcp(nq); a[0] = q[0] * in; a[1] = q[1] * in; a[2] = q[2] * in; a[3] = q[3] * in; }
     q[0] = a[0] * qr[0] - a[1] * qr[1] - a[2] * qr[2] - a[3] * qr[3];
     q[1] = a[0] * qr[1] + a[1] * qr[0] + a[2] * qr[3] - a[3] * qr[2];
     q[2] = a[0] * qr[2] - a[1] * qr[3] + a[2] * qr[0] + a[3] * qr[1];
