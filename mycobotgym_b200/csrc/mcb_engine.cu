@@ -154,6 +154,11 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // 64-bit shuffle as two explicit 32-bit shuffles (the generic double overload left register swaps behind)
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  int lo = __shfl_xor_sync(FULLMASK, __double2loint(v), m);
+  int hi = __shfl_xor_sync(FULLMASK, __double2hiint(v), m);
+  return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ double shfl_d(double v, int src) {
   int lo = __shfl_sync(FULLMASK, __double2loint(v), src);
   int hi = __shfl_sync(FULLMASK, __double2hiint(v), src);
@@ -202,10 +207,13 @@ __device__ __forceinline__ void quat2mat(double* m, const double* q) {
 }
 
 
+// kinematic tree of the reduced model (flatten.reduce_model): arm 0..5, gripper sub-chains 6->7, 8->9, 10, 11 under body 5,
+// free cube 12.  fk() is written against this table; mcb_model_create checks the descriptor against it.
+static const int kTreeParent[NB] = {-1, 0, 1, 2, 3, 4, 5, 6, 5, 8, 5, 5, -1};
+
 // ------------------------------------------------------------------------------------------------
 // fk(): body frames of the 13 jointed bodies.  Lane b builds the local transform of body b
-// (Tmat * Rot(axis, q)); the chain is then composed level by level with lanes spread over the
-// 9 + 3 matrix / vector elements of every body on the level.
+// (Tmat * Rot(axis, q)); the chain is then composed along the tree with matrix rows held in registers.
 template <class S>
 __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
   if (lane < NH) {
@@ -231,29 +239,42 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
     s.xpos[CUBE * 3] = s.qpos[12]; s.xpos[CUBE * 3 + 1] = s.qpos[13]; s.xpos[CUBE * 3 + 2] = s.qpos[14];
   }
   __syncwarp();
-  for (int L = 0; L < MDL.nlevel; L++) {
-    int s0 = MDL.level_start[L], n = (MDL.level_start[L + 1] - s0) * 12;
-    for (int w = lane; w < n; w += 32) {
-      int b = MDL.level_body[s0 + w / 12], e = w % 12;
-      if (b == CUBE) continue;
-      int p = MDL.d.parent[b];
-      if (e < 9) {
-        int r = e / 3, c = e % 3;
-        double v;
-        if (p < 0) v = s.lR[b * 9 + e];
-        else v = s.xmat[p * 9 + 3 * r] * s.lR[b * 9 + c] + s.xmat[p * 9 + 3 * r + 1] * s.lR[b * 9 + 3 + c] + s.xmat[p * 9 + 3 * r + 2] * s.lR[b * 9 + 6 + c];
-        s.xmat[b * 9 + e] = v;
-      } else {
-        int r = e - 9;
-        const double* t = MDL.d.Tpos[b];
-        double v;
-        if (p < 0) v = t[r];
-        else v = s.xpos[p * 3 + r] + s.xmat[p * 9 + 3 * r] * t[0] + s.xmat[p * 9 + 3 * r + 1] * t[1] + s.xmat[p * 9 + 3 * r + 2] * t[2];
-        s.xpos[b * 3 + r] = v;
-      }
+  // Chain composition with the tree topology compiled in (kTreeParent; mcb_model_create refuses any other tree): lane
+  // 3 g + r carries row r of the accumulated rotation and component r of the position in registers, so the six serial
+  // arm levels need no shared-memory round trip and no barrier; the four lane groups g recompute the arm redundantly and
+  // then branch to the gripper sub-chains 6->7, 8->9, 10, 11.  Every shared-memory offset of the arm is an immediate.
+  if (lane < 12) {
+    const int g = lane / 3, r = lane - 3 * g;
+    double X0 = s.lR[3 * r], X1 = s.lR[3 * r + 1], X2 = s.lR[3 * r + 2], P = MDL.d.Tpos[0][r];
+    if (g == 0) { s.xmat[3 * r] = X0; s.xmat[3 * r + 1] = X1; s.xmat[3 * r + 2] = X2; s.xpos[r] = P; }
+#pragma unroll
+    for (int b = 1; b <= 5; b++) {
+      const double* L = s.lR + b * 9;
+      const double* t = MDL.d.Tpos[b];
+      P = P + X0 * t[0] + X1 * t[1] + X2 * t[2];
+      const double n0 = X0 * L[0] + X1 * L[3] + X2 * L[6], n1 = X0 * L[1] + X1 * L[4] + X2 * L[7], n2 = X0 * L[2] + X1 * L[5] + X2 * L[8];
+      X0 = n0; X1 = n1; X2 = n2;
+      if (g == 0) { s.xmat[b * 9 + 3 * r] = X0; s.xmat[b * 9 + 3 * r + 1] = X1; s.xmat[b * 9 + 3 * r + 2] = X2; s.xpos[b * 3 + r] = P; }
     }
-    __syncwarp();
+    {
+      const int b = g < 2 ? 6 + 2 * g : 8 + g;        // 6, 8, 10, 11: the children of body 5
+      const double* L = s.lR + b * 9;
+      const double* t = MDL.d.Tpos[b];
+      P = P + X0 * t[0] + X1 * t[1] + X2 * t[2];
+      const double n0 = X0 * L[0] + X1 * L[3] + X2 * L[6], n1 = X0 * L[1] + X1 * L[4] + X2 * L[7], n2 = X0 * L[2] + X1 * L[5] + X2 * L[8];
+      X0 = n0; X1 = n1; X2 = n2;
+      s.xmat[b * 9 + 3 * r] = X0; s.xmat[b * 9 + 3 * r + 1] = X1; s.xmat[b * 9 + 3 * r + 2] = X2; s.xpos[b * 3 + r] = P;
+    }
+    if (g < 2) {
+      const int b = 7 + 2 * g;                        // 7 (child of 6), 9 (child of 8)
+      const double* L = s.lR + b * 9;
+      const double* t = MDL.d.Tpos[b];
+      P = P + X0 * t[0] + X1 * t[1] + X2 * t[2];
+      const double n0 = X0 * L[0] + X1 * L[3] + X2 * L[6], n1 = X0 * L[1] + X1 * L[4] + X2 * L[7], n2 = X0 * L[2] + X1 * L[5] + X2 * L[8];
+      s.xmat[b * 9 + 3 * r] = n0; s.xmat[b * 9 + 3 * r + 1] = n1; s.xmat[b * 9 + 3 * r + 2] = n2; s.xpos[b * 3 + r] = P;
+    }
   }
+  __syncwarp();
   if (MDL.d.has_weld) {
     if (lane == 0) {
       // mj_kinematics normalises data.mocap_quat in place; body quaternions are composed along the chain
@@ -353,17 +374,70 @@ __device__ void cinert_cdof(S& s, const DevModel* __restrict__ m, int lane, int 
 }
 
 
+// Tree walks with the topology compiled in (kTreeParent).  Lane layout of a walk over NC <= 8 components per body:
+// group g = lane / 8 follows one gripper sub-chain (g0: 6 -> 7, g1: 8 -> 9, g2: 10, g3: 11), component c = lane % 8;
+// all four groups walk the arm 0..5 redundantly, so a root-to-leaf pass is 8 dependent register updates and needs no
+// barrier; group 0 stores the arm's results.
+// tree_down(): out[b][c] = out[parent][c] + a[b][c] * w[b]   (b = 0..11; root value `root`)
+__device__ __forceinline__ void tree_down(double* out, const double* a, const double* w, double root, int lane) {
+  const int g = lane >> 3, c = lane & 7;
+  if (c < 6) {
+    double v = root;
+#pragma unroll
+    for (int b = 0; b <= 5; b++) {
+      v = fma(a[b * 6 + c], w[b], v);
+      if (g == 0) out[b * 6 + c] = v;
+    }
+    const int b6 = g < 2 ? 6 + 2 * g : 8 + g;
+    v = fma(a[b6 * 6 + c], w[b6], v);
+    out[b6 * 6 + c] = v;
+    if (g < 2) { const int b7 = b6 + 1; v = fma(a[b7 * 6 + c], w[b7], v); out[b7 * 6 + c] = v; }
+  }
+}
+// tree_up(): out[b][c] = in[b][c] + sum over the children's out   (b = 11..0)
+__device__ __forceinline__ void tree_up(double* out, const double* in, int lane) {
+  const int g = lane >> 3, c = lane & 7;
+  const int cc = c < 6 ? c : 0;
+  const int b6 = g < 2 ? 6 + 2 * g : 8 + g;
+  double v = 0;
+  if (g < 2) { v = in[(b6 + 1) * 6 + cc]; if (c < 6) out[(b6 + 1) * 6 + c] = v; }
+  v += in[b6 * 6 + cc];
+  if (c < 6) out[b6 * 6 + c] = v;
+  v += shfl_xor_d(v, 8);
+  v += shfl_xor_d(v, 16);                       // all groups: sum over the four children of body 5
+#pragma unroll
+  for (int b = 5; b >= 0; b--) {
+    v += in[b * 6 + cc];
+    if (g == 0 && c < 6) out[b * 6 + c] = v;
+  }
+}
+
 // crb_mass(): composite rigid-body inertias (subtree = contiguous DFS range) and the joint-space inertia M
 // (packed lower triangle; the robot-cube block is structurally zero and never written).
 template <class S>
 __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
-  for (int w = lane; w < nba * 10; w += 32) {
-    int b = w / 10, k = w % 10;
-    int e = b + MDL.d.subtree_size[b];
-    if (e > nba) e = nba;
-    double acc = s.cinert[w];
-    for (int c = b + 1; c < e; c++) acc += s.cinert[c * 10 + k];
-    s.crb[w] = acc;
+  {
+    // subtree sums leaf-to-root: lane 10 g + k, g0: 7 -> 6, g1: 9 -> 8, g2: 10 and 11; then the arm 5..0; lanes 30, 31: cube
+    const int g = lane / 10, k = lane - 10 * g;
+    double v = 0;
+    if (g < 2) {
+      const int b7 = 7 + 2 * g;
+      v = s.cinert[b7 * 10 + k]; s.crb[b7 * 10 + k] = v;
+      v += s.cinert[(b7 - 1) * 10 + k]; s.crb[(b7 - 1) * 10 + k] = v;
+    } else if (g == 2) {
+      const double a = s.cinert[10 * 10 + k], b = s.cinert[11 * 10 + k];
+      s.crb[10 * 10 + k] = a; s.crb[11 * 10 + k] = b;
+      v = a + b;
+    } else if (nba > CUBE) {
+#pragma unroll
+      for (int q = 0; q < 5; q++) s.crb[CUBE * 10 + 5 * k + q] = s.cinert[CUBE * 10 + 5 * k + q];
+    }
+    const double v1 = shfl_d(v, (lane + 10) & 31), v2 = shfl_d(v, (lane + 20) & 31);
+    if (g == 0) {
+      v += v1 + v2;
+#pragma unroll
+      for (int b = 5; b >= 0; b--) { v += s.cinert[b * 10 + k]; s.crb[b * 10 + k] = v; }
+    }
   }
   __syncwarp();
   if (lane < nva) mul_inert_vec(s.buf + lane * 6, s.crb + MDL.d.dof_body[lane] * 10, s.cdof + lane * 6);
@@ -1078,15 +1152,13 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
 // velocity_rne(): cvel, cdof_dot, bias forces (RNE with zero qacc).
 template <class S>
 __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva) {
-  for (int w = lane; w < nba * 6; w += 32) {
-    int b = w / 6, c = w % 6;
-    unsigned mask = MDL.d.ancmask[b];
-    double acc = 0, ac2 = 0;
-    while (mask) {
-      int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof[j * 6 + c] * s.qvel[j];
-      if (mask) { int j2 = __ffs(mask) - 1; mask &= mask - 1; ac2 += s.cdof[j2 * 6 + c] * s.qvel[j2]; }
-    }
-    s.cvel[w] = acc + ac2;
+  tree_down(s.cvel, s.cdof, s.qvel, 0.0, lane);
+  if (nba > CUBE && (lane & 7) >= 6 && lane < 24) {
+    const int c = 2 * (lane >> 3) + (lane & 7) - 6;     // the six idle lanes of groups 0..2 take the cube's six components
+    double acc = 0;
+#pragma unroll
+    for (int j = 12; j < 18; j++) acc = fma(s.cdof[j * 6 + c], s.qvel[j], acc);
+    s.cvel[CUBE * 6 + c] = acc;
   }
   __syncwarp();
   if (lane < nva) {
@@ -1105,15 +1177,16 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
     }
   }
   __syncwarp();
-  for (int w = lane; w < nba * 6; w += 32) {
-    int b = w / 6, c = w % 6;
-    unsigned mask = MDL.d.ancmask[b];
-    double acc = (c >= 3 ? -MDL.d.gravity[c - 3] : 0.0), ac2 = 0;
-    while (mask) {
-      int j = __ffs(mask) - 1; mask &= mask - 1; acc += s.cdof_dot[j * 6 + c] * s.qvel[j];
-      if (mask) { int j2 = __ffs(mask) - 1; mask &= mask - 1; ac2 += s.cdof_dot[j2 * 6 + c] * s.qvel[j2]; }
+  {
+    const int c8 = lane & 7;
+    tree_down(s.cacc, s.cdof_dot, s.qvel, (c8 >= 3 && c8 < 6) ? -MDL.d.gravity[c8 - 3] : 0.0, lane);
+    if (nba > CUBE && c8 >= 6 && lane < 24) {
+      const int c = 2 * (lane >> 3) + c8 - 6;
+      double acc = (c >= 3 ? -MDL.d.gravity[c - 3] : 0.0);
+#pragma unroll
+      for (int j = 12; j < 18; j++) acc = fma(s.cdof_dot[j * 6 + c], s.qvel[j], acc);
+      s.cacc[CUBE * 6 + c] = acc;
     }
-    s.cacc[w] = acc + ac2;
   }
   __syncwarp();
   double f[6];
@@ -1127,14 +1200,8 @@ __device__ void velocity_rne(S& s, const DevModel* __restrict__ m, int lane, int
   __syncwarp();
   if (lane < nba) for (int c = 0; c < 6; c++) s.cacc[lane * 6 + c] = f[c];  // cacc now holds cfrc_body
   __syncwarp();
-  for (int w = lane; w < nba * 6; w += 32) {
-    int b = w / 6, c = w % 6;
-    int e = b + MDL.d.subtree_size[b];
-    if (e > nba) e = nba;
-    double acc = 0;
-    for (int k = e - 1; k >= b; k--) acc += s.cacc[k * 6 + c];
-    s.cvel[w] = acc;  // cvel now holds the subtree-accumulated cfrc
-  }
+  tree_up(s.cvel, s.cacc, lane);    // cvel now holds the subtree-accumulated cfrc
+  if (nba > CUBE && (lane & 7) >= 6 && lane < 24) { const int c = 2 * (lane >> 3) + (lane & 7) - 6; s.cvel[CUBE * 6 + c] = s.cacc[CUBE * 6 + c]; }
   __syncwarp();
   if (lane < nva) {
     const double* a = s.cdof + lane * 6;
@@ -2199,6 +2266,8 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   }
   h.level_start[maxl + 1] = pos;
   // non-zeros of M: (i, j) with j an ancestor dof of i (or i itself)
+  for (int b = 0; b < NB; b++)
+    if (d->parent[b] != kTreeParent[b]) { delete m; return fail("mcb_model_create: the kinematic tree differs from the myCobot 280 tree the kernels are written against (kTreeParent)"); }
   int n = 0;
   for (int i = 0; i < NV; i++) {
     uint32_t mask = d->ancmask[d->dof_body[i]];
