@@ -13,7 +13,7 @@ from .flatten import ModelDesc, TaskCfg
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libmycobot_b200.so")
+LIB_PATH = os.environ.get("MCB_LIB") or os.path.join(PKG_DIR, "libmycobot_b200.so")   # MCB_LIB: tuning experiments only
 SRC = os.path.join(PKG_DIR, "csrc", "mcb_engine.cu")
 HDR = os.path.join(ROOT, "include", "mycobot_b200.h")
 

@@ -167,7 +167,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
   return v;
 }
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -206,6 +206,8 @@ __device__ __forceinline__ void quat2mat(double* m, const double* q) {
   m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
 }
 
+
+#define WPB_SMALL_ 16      // warps (= envs) per CTA of the common-layout launch
 
 // kinematic tree of the reduced model (flatten.reduce_model): arm 0..5, gripper sub-chains 6->7, 8->9, 10, 11 under body 5,
 // free cube 12.  fk() is written against this table; mcb_model_create checks the descriptor against it.
@@ -1509,7 +1511,20 @@ struct Newton {
 // independent warps drifting apart made instruction fetch the top stall (profiles/r01c).  Every path through
 // forward() executes exactly NSYNC_FWD barriers when sync is set.
 #define NSYNC_FWD 6
-#define FSYNC() do { if (sync) __syncthreads(); } while (0)
+// Lockstep groups: LOCKSTEP_WARPS consecutive warps of the CTA share one named barrier (ids 1..), so the CTA runs
+// 16 / LOCKSTEP_WARPS groups that drift against each other (different stages -> different pipes busy at the same time)
+// while the warps inside a group still share instruction-cache lines.
+// Measured (profiles/README.md, r01o): after the kernel shrank to ~10 k instructions per substep, free-running warps
+// (LOCKSTEP_WARPS = 1) beat every lockstep grouping: 16 -> 2.25 M, 8 -> 2.34 M, 4 -> 2.39 M, 2 -> 2.43 M, 1 -> 2.44 M
+// env-steps/s (pick-and-place); when the kernel was ~14 k instructions per substep full lockstep had won by 40 %.
+#ifndef LOCKSTEP_WARPS
+#define LOCKSTEP_WARPS 1
+#endif
+__device__ __forceinline__ void group_sync() {
+  if (LOCKSTEP_WARPS >= WPB_SMALL_) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / LOCKSTEP_WARPS), "r"(32 * LOCKSTEP_WARPS) : "memory");
+}
+#define FSYNC() do { if (sync) group_sync(); } while (0)
 template <class S>
 __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva, bool sync) {
   FSYNC();
@@ -1895,7 +1910,7 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 // The env kernel: one warp per env.  BIG = false is the first launch over all envs, WPB warps per CTA running the
 // substep loop in lockstep; envs whose constraint set overflows the small layout leave every output untouched and
 // enqueue themselves on redo_list, which the BIG = true launch (one warp per CTA, grid-stride over the list) serves.
-#define WPB_SMALL 16
+#define WPB_SMALL WPB_SMALL_
 template <bool BIG>
 __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
   typedef EnvS<BIG> S;
@@ -1913,7 +1928,7 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
   const int nwork = BIG ? *a.redo_count : a.n_envs;
-  const bool lockstep = !BIG;
+  const bool lockstep = !BIG && LOCKSTEP_WARPS > 1;
 
   for (int item0 = blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
     const int item = item0 + wid;
@@ -2024,8 +2039,8 @@ __global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_en
         if (ik && ok) ik_update_ctrl(s, lane, grip_ctrl);
         for (int it = 0; it < cfg.frame_skip; it++) {
           if (ok) ok = forward(s, m, lane, nba, nva, lockstep);
-          else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) __syncthreads(); }
-          if (lockstep) __syncthreads();
+          else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) group_sync(); }
+          if (lockstep) group_sync();
           if (ok) {
             if (lane < 6) s.qprev[lane] = s.qpos[lane];     // the frames now in shared memory belong to this qpos
             euler(s, m, lane, nva);
