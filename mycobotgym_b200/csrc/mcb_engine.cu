@@ -1911,8 +1911,11 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 // substep loop in lockstep; envs whose constraint set overflows the small layout leave every output untouched and
 // enqueue themselves on redo_list, which the BIG = true launch (one warp per CTA, grid-stride over the list) serves.
 #define WPB_SMALL WPB_SMALL_
+#ifndef ENV_LB_THREADS
+#define ENV_LB_THREADS (32 * WPB_SMALL)      // register budget of the common-layout kernel = 65536 / ENV_LB_THREADS (tuning knob)
+#endif
 template <bool BIG>
-__global__ void __launch_bounds__(BIG ? 32 : 32 * WPB_SMALL, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
   typedef EnvS<BIG> S;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpb = BIG ? 1 : WPB_SMALL;
