@@ -43,6 +43,8 @@
 #define NH MCB_NHINGE
 #define NTRI 171        // packed lower triangle of an 18 x 18 matrix
 #define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+#define TRIP(i, j) ((((i) >> 1) * (((i) >> 1) + 1) * 2 + ((i) & 1) * ((i) + 1)) + (j))   // row starts padded to even offsets
+#define NTRIP 180
 #define SR 13           // padded strides of the blocked Jacobian rows (odd => conflict-free lane-per-row reads)
 #define SC 7
 #define SF 19
@@ -122,7 +124,7 @@ struct EnvS {
   enum { NROW = BIG ? 128 : 48, POOL = BIG ? 2432 : 460, MAXC = BIG ? 16 : 8, IS_BIG = BIG };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
   double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
-  double M[NTRI], H[NTRI];
+  double M[NTRI + 1], H[NTRIP];          // H doubles as the factor storage of chol_solve_blk (padded rows, TRIP)
   double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
   double anchors[12];
   double qprev[6];   // arm qpos the frames in shared memory were computed from (the reference's stale site poses)
@@ -140,6 +142,9 @@ struct EnvS {
   int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
   int nR, nC, nF, nU, nefc, ncon, overflow, iters;
 };
+static_assert(offsetof(EnvS<false>, H) % 16 == 0 && offsetof(EnvS<true>, H) % 16 == 0, "factor storage must be 16-byte aligned (128-bit loads)");
+static_assert(sizeof(EnvS<false>) % 16 == 0 && sizeof(EnvS<true>) % 16 == 0, "per-env records must keep 16-byte alignment");
+
 
 // ------------------------------------------------------------------------------------------------
 // fast_rcp(): 1 / d for d >= MINVAL without the library routine's special-case branches: MUFU seed (about 20 bits)
@@ -466,14 +471,16 @@ __device__ void crb_mass(S& s, const DevModel* __restrict__ m, int lane, int nba
 // triangle is a shuffle + fma chain without divisions.  DADD: `dadd` is added to the lane's diagonal entry first
 // (Euler: h * damping).  Pivots below MINVAL are clamped (mju_cholFactor's mindiag).  Lanes outside the block return 0.
 // Fully unrolled: every shared-memory offset is an immediate, no index arithmetic in the inner loops.
+// Factor storage: row i of L starts at an even offset TRIP(i, 0), so a row segment starting at an even column is 16-byte
+// aligned and the dot products read it with 128-bit loads (NTRIP = 180 doubles for 18 rows instead of NTRI = 171).
 template <int N0, int N, bool DADD>
 __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, const double* bsrc, double* ytmp, double dadd, int lane) {
   const int i = lane;
   const bool mine = (i >= N0 && i < N0 + N);
   const bool rhs = (i == 31);
   const int ro = i * (i + 1) / 2 + N0;
-  const double* base = rhs ? bsrc + N0 : src + ro;      // lane 31 loads b, the others their matrix row
-  double* wbase = rhs ? ytmp + N0 : dst + ro;           // ... and stores D^-1 L^-1 b, the others their row of L
+  const double* base = rhs ? bsrc + N0 : src + ro;      // lane 31 loads b, the others their matrix row (packed, TRI)
+  double* wbase = rhs ? ytmp + N0 : dst + TRIP(i, N0);  // ... and stores D^-1 L^-1 b, the others their row of L (padded, TRIP)
   const int ieff = (mine || rhs) ? i : -1;              // entry (i, N0 + k) exists for this lane iff ieff >= N0 + k
   double row[N];
 #pragma unroll
@@ -482,12 +489,14 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, co
     if (DADD) v += (N0 + k == i) ? dadd : 0.0;     // (a separate "row[i - N0] += dadd" would index row[] dynamically => local memory)
     row[k] = v;
   }
+  __syncwarp();                                         // src may alias dst, whose layout differs: every load precedes every store
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    const double* rj = dst + TRI(N0 + j, N0);
+    const double2* rj = reinterpret_cast<const double2*>(dst + TRIP(N0 + j, N0));      // N0 is even => 16-byte aligned
     double s0 = row[j], s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < j; k++) { if (k & 1) s1 -= row[k] * rj[k]; else s0 -= row[k] * rj[k]; }
+    for (int k = 0; k + 1 < j; k += 2) { const double2 l2 = rj[k >> 1]; s0 -= row[k] * l2.x; s1 -= row[k + 1] * l2.y; }
+    if (j & 1) s0 -= row[j - 1] * reinterpret_cast<const double*>(rj)[j - 1];
     const double sv = s0 + s1;
     row[j] = sv;
     double d = shfl_d(sv, N0 + j);
@@ -500,7 +509,7 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, co
 #pragma unroll
   for (int k = N0 + N - 1; k > N0; k--) {
     const double xk = shfl_d(x, k);
-    const double lk = (i < k && i >= N0) ? dst[TRI(k, 0) + i] : 0.0;
+    const double lk = (i < k && i >= N0) ? dst[TRIP(k, 0) + i] : 0.0;
     x = fma(-lk, xk, x);
   }
   return x;
@@ -933,6 +942,30 @@ __device__ __forceinline__ double row_dot(S& s, int r, const double* v) {
   return acc;
 }
 
+// two dot products of constraint row r at once (the row is loaded once)
+template <class S>
+__device__ __forceinline__ void row_dot2(S& s, int r, const double* v, const double* w, double& dv, double& dw) {
+  double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  if (r < s.nR) {
+    const double* p = row_r(s, r);
+#pragma unroll
+    for (int k = 0; k < NH; k += 2) { a0 += p[k] * v[k]; a1 += p[k + 1] * v[k + 1]; b0 += p[k] * w[k]; b1 += p[k + 1] * w[k + 1]; }
+  } else if (r < s.nR + s.nC) {
+    const double* p = row_c(s, r);
+#pragma unroll
+    for (int k = 0; k < 6; k += 2) { a0 += p[k] * v[NH + k]; a1 += p[k + 1] * v[NH + k + 1]; b0 += p[k] * w[NH + k]; b1 += p[k + 1] * w[NH + k + 1]; }
+  } else if (r < s.nR + s.nC + s.nF) {
+    const double* p = row_f(s, r);
+#pragma unroll
+    for (int k = 0; k < NV; k += 2) { a0 += p[k] * v[k]; a1 += p[k + 1] * v[k + 1]; b0 += p[k] * w[k]; b1 += p[k + 1] * w[k + 1]; }
+  } else {
+    int meta = s.rmeta[r];
+    double x = v[meta & 0xff], y = w[meta & 0xff];
+    a0 = (meta & 0x100) ? -x : x; b0 = (meta & 0x100) ? -y : y;
+  }
+  dv = a0 + a1; dw = b0 + b1;
+}
+
 // make_rows(): equality (7 robot rows), pyramidal contact rows by block type, joint-limit unit rows; then R, D
 // and the reference acceleration of every row.  Returns false if the layout's capacity is exceeded.
 template <class S>
@@ -1274,30 +1307,35 @@ struct Newton {
     __syncwarp();
     gauss = warp_sum(g);
     cost = gauss + warp_sum(c);
-    // qfrc_constraint = J' f, by row group
-    if (lane < nva) {
-      double q = 0;
+    // qfrc_constraint = J' f, by row group.  Robot lanes take the robot rows; the cube rows (the longest group: 6 rows per
+    // resting contact) are split over three lanes per cube dof and folded with two shuffles.
+    {
       const int nR = s.nR, nC = s.nC, nF = s.nF, nU = s.nU;
-      double q1 = 0, q2 = 0, q3 = 0;
+      double q = 0, q1 = 0, q2 = 0, q3 = 0;
       if (lane < NH) {
         int r = 0;
         for (; r + 3 < nR; r += 4) { q += s.pool[r * SR + lane] * s.eJv[r]; q1 += s.pool[(r + 1) * SR + lane] * s.eJv[r + 1]; q2 += s.pool[(r + 2) * SR + lane] * s.eJv[r + 2]; q3 += s.pool[(r + 3) * SR + lane] * s.eJv[r + 3]; }
         for (; r < nR; r++) q += s.pool[r * SR + lane] * s.eJv[r];
-      } else {
-        const double* p = s.pool + nR * SR + (lane - NH);
+      } else if (lane < NH + 18 && nva > NH) {
+        const int part = (lane - NH) / 6, d = (lane - NH) - 6 * part;
+        const double* p = s.pool + nR * SR + d;
         const double* f = s.eJv + nR;
-        int r = 0;
-        for (; r + 3 < nC; r += 4) { q += p[r * SC] * f[r]; q1 += p[(r + 1) * SC] * f[r + 1]; q2 += p[(r + 2) * SC] * f[r + 2]; q3 += p[(r + 3) * SC] * f[r + 3]; }
-        for (; r < nC; r++) q += p[r * SC] * f[r];
+        int r = part;
+        for (; r + 9 < nC; r += 12) { q += p[r * SC] * f[r]; q1 += p[(r + 3) * SC] * f[r + 3]; q2 += p[(r + 6) * SC] * f[r + 6]; q3 += p[(r + 9) * SC] * f[r + 9]; }
+        for (; r < nC; r += 3) q += p[r * SC] * f[r];
       }
       q = (q + q1) + (q2 + q3);
-      { const double* p = s.pool + nR * SR + nC * SC + lane; for (int r = 0; r < nF; r++) q += p[r * SF] * s.eJv[nR + nC + r]; }
-      for (int u = 0; u < nU; u++) {
-        int r = nR + nC + nF + u, meta = s.rmeta[r];
-        if ((meta & 0xff) == lane) q += (meta & 0x100) ? -s.eJv[r] : s.eJv[r];
+      const double qa = shfl_d(q, (lane + 6) & 31), qb = shfl_d(q, (lane + 12) & 31);
+      if (lane >= NH && lane < NV) q += qa + qb;
+      if (lane < nva) {
+        { const double* p = s.pool + nR * SR + nC * SC + lane; for (int r = 0; r < nF; r++) q += p[r * SF] * s.eJv[nR + nC + r]; }
+        for (int u = 0; u < nU; u++) {
+          int r = nR + nC + nF + u, meta = s.rmeta[r];
+          if ((meta & 0xff) == lane) q += (meta & 0x100) ? -s.eJv[r] : s.eJv[r];
+        }
+        s.qfrc_con[lane] = q;
+        s.grad[lane] = s.Ma[lane] - s.qfrc_smooth[lane] - q;
       }
-      s.qfrc_con[lane] = q;
-      s.grad[lane] = s.Ma[lane] - s.qfrc_smooth[lane] - q;
     }
     __syncwarp();
   }
@@ -1464,8 +1502,12 @@ struct Newton {
     const double scale = 1.0 / (MDL.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
-    rows_times(s.warm, s.eJaref, true);
-    rows_times(s.qacc_smooth, s.eJv, true);
+    for (int r = lane; r < nefc; r += 32) {
+      double dw, ds;
+      row_dot2(s, r, s.warm, s.qacc_smooth, dw, ds);
+      const double ar = s.earef[r];
+      s.eJaref[r] = dw - ar; s.eJv[r] = ds - ar;
+    }
     double ma = mulM_row(s, lane, nva, s.warm), g = 0;
     if (lane < nva) g = 0.5 * (ma - s.qfrc_smooth[lane]) * (s.warm[lane] - s.qacc_smooth[lane]);
     __syncwarp();
