@@ -145,7 +145,8 @@ typedef struct mcb_task_cfg {
                                   model variant); mycobot.py:36,90-103,134-193 */
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
   int32_t control_steps;       /* IK: DLS solves per env-step, each followed by frame_skip substeps (5; mycobot.py:35,162) */
-  int32_t reserved_;
+  int32_t lockstep_warps;      /* scheduling only, results do not depend on it: warps per lockstep group of the step kernel
+                                * (1 free-running ... 16 whole CTA); 0 = measured per batch by mcb_autotune() at the first mcb_step */
   double distance_threshold;   /* 0.01 */
 } mcb_task_cfg;
 
@@ -218,6 +219,15 @@ int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream);
  * efc_J[nefc*18] in MuJoCo row order (equality, limits, contacts) | efc_aref[nefc] | efc_D[nefc] |
  * (dist, pos3, normal3) * ncon.  cap must be >= 3170.  Returns the number of doubles written. */
 int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out, int32_t cap, void* stream);
+
+/* Picks the lockstep grouping of the step kernel for this batch (cfg.lockstep_warps == 0): rolls the batch 12 steps
+ * ahead (the state right after a reset is not representative), times `steps_per_candidate` (0 -> 4) steps per candidate
+ * from that state, keeps the fastest and restores state, episode clocks, RNG streams and statistics exactly.  `actions`
+ * (device float32 [N, action_dim]) are applied at every tuning step; NULL -> uniform random actions from a private
+ * Philox stream.  Synchronises the stream.  mcb_step calls it once by itself (with NULL); call it explicitly before
+ * capturing mcb_step in a CUDA graph.  Returns the chosen grouping. */
+int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream);
+int32_t mcb_batch_lockstep_warps(const mcb_batch* b);
 
 /* measurement helpers used by bench.py */
 int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */

@@ -96,6 +96,7 @@ enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_RESET = 2 };
 struct StepArgs {
   const DevModel* m;
   int n_envs, mode;
+  int lockstep_warps;        // warps per lockstep group of the common-layout kernel (1 = free-running), see group_sync()
   mcb_task_cfg cfg;
   uint64_t seed;
   double* state;             // [N, 72]
@@ -1553,22 +1554,19 @@ struct Newton {
 // independent warps drifting apart made instruction fetch the top stall (profiles/r01c).  Every path through
 // forward() executes exactly NSYNC_FWD barriers when sync is set.
 #define NSYNC_FWD 6
-// Lockstep groups: LOCKSTEP_WARPS consecutive warps of the CTA share one named barrier (ids 1..), so the CTA runs
-// 16 / LOCKSTEP_WARPS groups that drift against each other (different stages -> different pipes busy at the same time)
-// while the warps inside a group still share instruction-cache lines.
-// Measured (profiles/README.md, r01o): after the kernel shrank to ~10 k instructions per substep, free-running warps
-// (LOCKSTEP_WARPS = 1) beat every lockstep grouping: 16 -> 2.25 M, 8 -> 2.34 M, 4 -> 2.39 M, 2 -> 2.43 M, 1 -> 2.44 M
-// env-steps/s (pick-and-place); when the kernel was ~14 k instructions per substep full lockstep had won by 40 %.
-#ifndef LOCKSTEP_WARPS
-#define LOCKSTEP_WARPS 1
-#endif
-__device__ __forceinline__ void group_sync() {
-  if (LOCKSTEP_WARPS >= WPB_SMALL_) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / LOCKSTEP_WARPS), "r"(32 * LOCKSTEP_WARPS) : "memory");
+// Lockstep groups: `lw` consecutive warps of the CTA share one named barrier (ids 1..), so the CTA runs 16 / lw groups
+// that drift against each other (different stages -> different pipes busy at the same time) while the warps inside a
+// group still share instruction-cache lines.  lw = 1: free-running warps, no barriers.  Which grouping wins depends on
+// the workload's code footprint (profiles/README.md, r01o / r01q): pick-and-place and reach are fastest free-running
+// (2.47 M vs 2.27 M env-steps/s in full lockstep), push and the mocap variant are 2x / 1.4x faster in full lockstep
+// (free-running they stall on instruction fetch, `no_instructions` 38 %).  mcb_autotune() measures and picks per batch.
+__device__ __forceinline__ void group_sync(int lw) {
+  if (lw >= WPB_SMALL_) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / lw), "r"(32 * lw) : "memory");
 }
-#define FSYNC() do { if (sync) group_sync(); } while (0)
+#define FSYNC() do { if (sync) group_sync(sync); } while (0)
 template <class S>
-__device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva, bool sync) {
+__device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva, int sync) {
   FSYNC();
   fk(s, m, lane, nba);
   cinert_cdof(s, m, lane, nba, nva);
@@ -1973,7 +1971,7 @@ __global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_en
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
   const int nwork = BIG ? *a.redo_count : a.n_envs;
-  const bool lockstep = !BIG && LOCKSTEP_WARPS > 1;
+  const int lockstep = (!BIG && a.lockstep_warps > 1) ? a.lockstep_warps : 0;
 
   for (int item0 = blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
     const int item = item0 + wid;
@@ -2084,8 +2082,8 @@ __global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_en
         if (ik && ok) ik_update_ctrl(s, lane, grip_ctrl);
         for (int it = 0; it < cfg.frame_skip; it++) {
           if (ok) ok = forward(s, m, lane, nba, nva, lockstep);
-          else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) group_sync(); }
-          if (lockstep) group_sync();
+          else if (lockstep) { for (int k = 0; k < NSYNC_FWD; k++) group_sync(lockstep); }
+          if (lockstep) group_sync(lockstep);
           if (ok) {
             if (lane < 6) s.qprev[lane] = s.qpos[lane];     // the frames now in shared memory belong to this qpos
             euler(s, m, lane, nva);
@@ -2246,6 +2244,14 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
 }
 
 
+// uniform float32 actions in [-1, 1) for mcb_autotune's roll-ahead (Philox stream of its own)
+__global__ void random_actions_kernel(float* act, int n, uint64_t seed, unsigned step) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long ctr = (unsigned long long)step << 32;
+  act[i] = (float)(2.0 * philox_uniform(seed, (uint32_t)i, ctr) - 1.0);
+}
+
 __global__ void iota_kernel(int* list, int* count, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) list[i] = i;
@@ -2273,6 +2279,7 @@ struct mcb_batch {
   double* state; int* elapsed; double* ep_return; unsigned long long* rng_ctr; double* stats;
   double* debug;
   int last_launches;
+  int lockstep_warps, tuned;
   // staging for the host-buffer entry point
   float* d_actions; double *d_obs, *d_ag, *d_dg, *d_fobs; void* d_reward; uint8_t* d_flags;
   float* h_actions; double *h_obs, *h_ag, *h_dg, *h_fobs; void* h_reward; uint8_t* h_flags;
@@ -2282,6 +2289,7 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   a.m = b->model->dev; a.n_envs = b->n_envs; a.cfg = b->cfg; a.seed = b->seed;
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
   a.redo_count = b->redo_count; a.redo_list = b->redo_list;
+  a.lockstep_warps = b->lockstep_warps;
   if (b->big_only) {
     iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
   } else {
@@ -2376,6 +2384,7 @@ int32_t mcb_model_destroy(mcb_model* m) {
 
 int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out) {
   if (!m || !cfg || !out || n_envs <= 0) return fail("mcb_batch_create: bad argument");
+  { const int lw = cfg->lockstep_warps; if (lw != 0 && lw != 1 && lw != 2 && lw != 4 && lw != 8 && lw != 16) return fail("mcb_batch_create: lockstep_warps must be 0 (auto), 1, 2, 4, 8 or 16"); }
   if (cfg->controller_type < 0 || cfg->controller_type > 2) return fail("mcb_batch_create: controller_type must be 0 (joint), 1 (IK) or 2 (mocap)");
   if ((cfg->controller_type == 2) != (m->host.d.has_weld != 0)) return fail("mcb_batch_create: the mocap controller needs the mocap model variant, the other controllers the joint variant");
   if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
@@ -2411,6 +2420,8 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs, cfg->fetch_env);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
+  b->lockstep_warps = cfg->lockstep_warps ? cfg->lockstep_warps : WPB_SMALL;   // 0: mcb_autotune() decides at the first step
+  b->tuned = cfg->lockstep_warps != 0;
   *out = b;
   return 0;
 }
@@ -2441,7 +2452,87 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, do
   a.mode = MODE_STEP; a.actions = actions; a.obs = obs; a.ag = ag; a.dg = dg; a.reward = reward;
   a.terminated = terminated; a.truncated = truncated; a.success = success; a.final_obs = final_obs;
   b->last_launches = 2;  // small-layout kernel + big-layout fallback kernel
+  if (!b->tuned && !b->big_only) { if (mcb_autotune(b, nullptr, 0, stream) < 0) return -1; }
   return launch(b, a, (cudaStream_t)stream);
+}
+
+int32_t mcb_batch_lockstep_warps(const mcb_batch* b) { return b ? b->lockstep_warps : -1; }
+
+int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream) {
+  if (!b) return fail("mcb_autotune: null batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  b->tuned = 1;
+  if (b->cfg.lockstep_warps != 0 || b->big_only) return b->lockstep_warps;
+  const int K = steps_per_candidate > 0 ? steps_per_candidate : 4;
+  const size_t N = (size_t)b->n_envs;
+  const size_t adim = (size_t)mcb_batch_action_dim(b);
+  // snapshot of everything a step mutates; every candidate replays the same K steps from it and it is restored at the end
+  double *sv_state = nullptr, *sv_ret = nullptr, *sv_stats = nullptr; int* sv_el = nullptr; unsigned long long* sv_ctr = nullptr;
+  void* t_reward = nullptr; uint8_t* t_flags = nullptr; float* t_act = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int best = b->lockstep_warps;
+  float best_ms = 1e30f;
+  bool okay = true;
+#define TCK(call) do { if (okay && (call) != cudaSuccess) okay = false; } while (0)
+  TCK(cudaMalloc(&sv_state, N * MCB_STATE_STRIDE * sizeof(double))); TCK(cudaMalloc(&sv_ret, N * sizeof(double)));
+  TCK(cudaMalloc(&sv_stats, 8 * sizeof(double))); TCK(cudaMalloc(&sv_el, N * sizeof(int))); TCK(cudaMalloc(&sv_ctr, N * sizeof(unsigned long long)));
+  TCK(cudaMalloc(&t_reward, N * sizeof(double))); TCK(cudaMalloc(&t_flags, 3 * N));
+  if (!actions) TCK(cudaMalloc(&t_act, N * adim * sizeof(float)));
+  TCK(cudaEventCreate(&e0)); TCK(cudaEventCreate(&e1));
+  if (okay) {
+    TCK(cudaMemcpyAsync(sv_state, b->state, N * MCB_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(sv_ret, b->ep_return, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(sv_stats, b->stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(sv_el, b->elapsed, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(sv_ctr, b->rng_ctr, N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    auto one_step = [&](int k) {
+      if (!actions) random_actions_kernel<<<(unsigned)((N * adim + 255) / 256), 256, 0, st>>>(t_act, (int)(N * adim), b->seed ^ 0x74756e65ull, (unsigned)k);
+      StepArgs a; memset(&a, 0, sizeof a);
+      a.mode = MODE_STEP; a.actions = actions ? actions : t_act; a.reward = t_reward;
+      a.terminated = t_flags; a.truncated = t_flags + N; a.success = t_flags + 2 * N;
+      if (launch(b, a, st)) okay = false;
+    };
+    // roll ahead (state right after a reset is not representative: nothing moves yet), then snapshot the tuning state
+    double* tn_state = nullptr; double* tn_ret = nullptr; int* tn_el = nullptr; unsigned long long* tn_ctr = nullptr;
+    TCK(cudaMalloc(&tn_state, N * MCB_STATE_STRIDE * sizeof(double))); TCK(cudaMalloc(&tn_ret, N * sizeof(double)));
+    TCK(cudaMalloc(&tn_el, N * sizeof(int))); TCK(cudaMalloc(&tn_ctr, N * sizeof(unsigned long long)));
+    for (int k = 0; k < 12 && okay; k++) one_step(k);
+    TCK(cudaMemcpyAsync(tn_state, b->state, N * MCB_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(tn_ret, b->ep_return, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(tn_el, b->elapsed, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(tn_ctr, b->rng_ctr, N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    const int cand[3] = {WPB_SMALL, 4, 1};
+    for (int c = 0; c < 3 && okay; c++) {
+      b->lockstep_warps = cand[c];
+      TCK(cudaMemcpyAsync(b->state, tn_state, N * MCB_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      TCK(cudaMemcpyAsync(b->ep_return, tn_ret, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      TCK(cudaMemcpyAsync(b->elapsed, tn_el, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      TCK(cudaMemcpyAsync(b->rng_ctr, tn_ctr, N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+      for (int k = 0; k <= K && okay; k++) {          // step 0 is the untimed warm-up of this candidate
+        if (k == 1) TCK(cudaEventRecord(e0, st));
+        one_step(100 + k);
+      }
+      TCK(cudaEventRecord(e1, st));
+      TCK(cudaEventSynchronize(e1));
+      float ms = 0;
+      TCK(cudaEventElapsedTime(&ms, e0, e1));
+      if (okay && ms < best_ms) { best_ms = ms; best = cand[c]; }
+    }
+    TCK(cudaMemcpyAsync(b->state, sv_state, N * MCB_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(b->ep_return, sv_ret, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(b->stats, sv_stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(b->elapsed, sv_el, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaMemcpyAsync(b->rng_ctr, sv_ctr, N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    TCK(cudaStreamSynchronize(st));
+    cudaFree(tn_state); cudaFree(tn_ret); cudaFree(tn_el); cudaFree(tn_ctr);
+  }
+#undef TCK
+  cudaFree(sv_state); cudaFree(sv_ret); cudaFree(sv_stats); cudaFree(sv_el); cudaFree(sv_ctr); cudaFree(t_reward); cudaFree(t_flags); cudaFree(t_act);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  b->lockstep_warps = best;
+  if (!okay) return fail("mcb_autotune: CUDA error while timing the candidates", cudaGetLastError());
+  return best;
 }
 
 int32_t mcb_forward(mcb_batch* b, double* obs, double* ag, double* dg, void* stream) {

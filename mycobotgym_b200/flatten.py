@@ -61,7 +61,7 @@ class TaskCfg(C.Structure):
     _fields_ = [
         ("has_object", _i), ("block_gripper", _i), ("target_in_the_air", _i), ("reward_type", _i),
         ("max_episode_steps", _i), ("frame_skip", _i), ("auto_reset", _i), ("nefc_max", _i),
-        ("controller_type", _i), ("fetch_env", _i), ("control_steps", _i), ("reserved_", _i),
+        ("controller_type", _i), ("fetch_env", _i), ("control_steps", _i), ("lockstep_warps", _i),
         ("distance_threshold", _d),
     ]
 

@@ -159,7 +159,7 @@ class MyCobotVectorEnv:
                  control_steps=5, controller_type="joint", obj_range=0.1, target_in_the_air=True,
                  distance_threshold=0.01, initial_qpos=None, fetch_env=False, reward_type="sparse", frame_skip=20,
                  max_episode_steps=50, device="cuda:0", seed=0, auto_reset=True, goal_source="device", nefc_max=0,
-                 **kwargs):
+                 lockstep_warps=0, **kwargs):
         if controller_type not in ("joint", "IK", "mocap"):
             raise ValueError(f"unknown controller_type {controller_type!r}")
         if fetch_env and controller_type == "joint":
@@ -193,7 +193,7 @@ class MyCobotVectorEnv:
             reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,
             frame_skip=self.frame_skip, auto_reset=int(self.auto_reset and goal_source == "device"), nefc_max=int(nefc_max),
             controller_type={"joint": 0, "IK": 1, "mocap": 2}[controller_type], fetch_env=int(bool(fetch_env)), control_steps=int(control_steps),
-            reserved_=0, distance_threshold=self.distance_threshold)
+            lockstep_warps=int(lockstep_warps), distance_threshold=self.distance_threshold)
         self._cfg = cfg
         with torch.cuda.device(dev_index):
             h = C.c_void_p()
@@ -328,6 +328,17 @@ class MyCobotVectorEnv:
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_set_state(self._batch, *[_ptr(t) for t in ts], self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
+
+    def autotune(self, actions=None, steps_per_candidate=0):
+        """Pick the step kernel's lockstep grouping for this batch now (otherwise the first `step` does it); the state is
+        restored exactly.  Returns the chosen number of warps per group."""
+        a = None if actions is None else torch.as_tensor(actions).to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self._dev_index):
+            return _lib.check(self._L.mcb_autotune(self._batch, _ptr(a), int(steps_per_candidate), self._stream()))
+
+    @property
+    def lockstep_warps(self):
+        return int(self._L.mcb_batch_lockstep_warps(self._batch))
 
     def forward(self):
         """mj_forward on every env (refreshes frames, qacc_warmstart and the observation buffers)."""

@@ -576,6 +576,40 @@ def test_bad_simulation_guard_resets_the_env():
     env.close()
 
 
+def test_autotune_restores_state_and_grouping_is_scheduling_only():
+    # the lockstep grouping of the step kernel (mcb_autotune) must not change a single bit of the results, and tuning must
+    # leave state, episode clocks, RNG streams and statistics exactly as they were
+    n = 96
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.rand(4, n, 7, device="cuda", generator=gen) * 2 - 1
+    runs = []
+    for lw in (1, 4, 16, 0):
+        env = _env(num_envs=n, has_object=True, reward_type="sparse", seed=3, max_episode_steps=3, lockstep_warps=lw)
+        env.reset()
+        if lw == 0:
+            before = {k: v.clone() for k, v in env.get_state().items()}
+            stats0 = env.stats(reset=False).clone()
+            chosen = env.autotune()
+            assert chosen in (1, 4, 16) and env.lockstep_warps == chosen
+            after = env.get_state()
+            for k in before:
+                assert torch.equal(before[k], after[k]), k
+            assert torch.equal(stats0, env.stats(reset=False))
+        else:
+            assert env.lockstep_warps == lw
+        obs = None
+        for t in range(4):                                   # crosses an auto-reset (TimeLimit 3): the RNG streams matter
+            obs, rew, term, trunc, info = env.step(acts[t])
+        st = env.get_state()
+        runs.append((st["qpos"].clone(), st["qvel"].clone(), st["goal"].clone(), obs["observation"].clone(), env.stats().clone()))
+        env.close()
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        _env(num_envs=2, lockstep_warps=3)
+
+
 def test_make_registry_ids_and_reference_goal_autoreset():
     from mycobotgym_b200.vector_env import make
 
