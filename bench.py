@@ -212,7 +212,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     kw, per_gpu, flop_per_step = WORKLOADS[args.workload]
     n = args.envs_per_gpu or per_gpu
-    env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, **kw)
+    env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, lockstep_warps=int(os.environ.get("MCB_LOCKSTEP", "0")), **kw)
     env.reset()
     # steady-state rollout: episode clocks staggered uniformly over the 50-step horizon, so ~2 % of the envs hit the
     # TimeLimit and auto-reset (two extra forward passes + goal / cube resampling) inside every timed step
