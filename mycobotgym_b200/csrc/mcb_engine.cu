@@ -284,30 +284,36 @@ __device__ void fk(S& s, const DevModel* __restrict__ m, int lane, int nba) {
   }
   __syncwarp();
   if (MDL.d.has_weld) {
+    // mocap variant: orientation quaternion of the body carrying gripper_tcp, composed along the arm 0..weld_body2 exactly
+    // like mj_kinematics (parent * body_quat, * axis-angle, normalise).  The half-angle rotations are computed by the
+    // arm lanes in parallel (scratch: s.cinert, written only after fk); lane 0 does the six serial products.
+    double* rq = s.cinert;
+    if (lane <= MDL.d.weld_body2 && lane < 6) {
+      const double ang = s.qpos[lane] - MDL.d.qpos0[lane];
+      double sn, cs;
+      sincos(0.5 * ang, &sn, &cs);
+      const double* ax = MDL.d.axis[lane];
+      if (ang == 0) { cs = 1; sn = 0; }
+      rq[lane * 4] = cs; rq[lane * 4 + 1] = ax[0] * sn; rq[lane * 4 + 2] = ax[1] * sn; rq[lane * 4 + 3] = ax[2] * sn;
+    }
+    __syncwarp();
     if (lane == 0) {
-      // mj_kinematics normalises data.mocap_quat in place; body quaternions are composed along the chain
-      double* mq = s.mocap + 3;
+      double* mq = s.mocap + 3;      // mj_kinematics normalises data.mocap_quat in place
       double n = sqrt(mq[0] * mq[0] + mq[1] * mq[1] + mq[2] * mq[2] + mq[3] * mq[3]);
-      if (n < MINVAL) { mq[0] = 1; mq[1] = mq[2] = mq[3] = 0; } else { mq[0] /= n; mq[1] /= n; mq[2] /= n; mq[3] /= n; }
-      int chain[NB], nc = 0;
-      for (int b = MDL.d.weld_body2; b >= 0; b = MDL.d.parent[b]) chain[nc++] = b;
+      if (n < MINVAL) { mq[0] = 1; mq[1] = mq[2] = mq[3] = 0; } else { const double in = fast_rcp(n); mq[0] *= in; mq[1] *= in; mq[2] *= in; mq[3] *= in; }
       double q[4] = {1, 0, 0, 0};
-      for (int k = nc - 1; k >= 0; k--) {
-        int b = chain[k];
+      const int nb = MDL.d.weld_body2;      // the arm is a chain: body b's parent is b - 1 (kTreeParent)
+      for (int b = 0; b <= nb; b++) {
         const double* tq = MDL.d.Tquat[b];
+        const double* r = rq + b * 4;
         double t[4] = {q[0] * tq[0] - q[1] * tq[1] - q[2] * tq[2] - q[3] * tq[3], q[0] * tq[1] + q[1] * tq[0] + q[2] * tq[3] - q[3] * tq[2],
                        q[0] * tq[2] - q[1] * tq[3] + q[2] * tq[0] + q[3] * tq[1], q[0] * tq[3] + q[1] * tq[2] - q[2] * tq[1] + q[3] * tq[0]};
-        double ang = s.qpos[b] - MDL.d.qpos0[b], sn, cs;
-        sincos(0.5 * ang, &sn, &cs);
-        const double* ax = MDL.d.axis[b];
-        double r[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn};
-        if (ang == 0) { r[0] = 1; r[1] = r[2] = r[3] = 0; }
         q[0] = t[0] * r[0] - t[1] * r[1] - t[2] * r[2] - t[3] * r[3];
         q[1] = t[0] * r[1] + t[1] * r[0] + t[2] * r[3] - t[3] * r[2];
         q[2] = t[0] * r[2] - t[1] * r[3] + t[2] * r[0] + t[3] * r[1];
         q[3] = t[0] * r[3] + t[1] * r[2] - t[2] * r[1] + t[3] * r[0];
-        double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-        q[0] /= nq; q[1] /= nq; q[2] /= nq; q[3] /= nq;
+        const double in = fast_rcp(sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
+        q[0] *= in; q[1] *= in; q[2] *= in; q[3] *= in;
       }
       s.quat5[0] = q[0]; s.quat5[1] = q[1]; s.quat5[2] = q[2]; s.quat5[3] = q[3];
     }
@@ -2336,6 +2342,7 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   // non-zeros of M: (i, j) with j an ancestor dof of i (or i itself)
   for (int b = 0; b < NB; b++)
     if (d->parent[b] != kTreeParent[b]) { delete m; return fail("mcb_model_create: the kinematic tree differs from the myCobot 280 tree the kernels are written against (kTreeParent)"); }
+  if (d->has_weld && (d->weld_body2 < 0 || d->weld_body2 > 5)) { delete m; return fail("mcb_model_create: the weld must attach to an arm body (0..5)"); }
   int n = 0;
   for (int i = 0; i < NV; i++) {
     uint32_t mask = d->ancmask[d->dof_body[i]];
