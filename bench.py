@@ -223,6 +223,11 @@ def run_ours(args):
     gen.manual_seed(1234 + rank)
     acts = torch.rand(K + W, n, env.action_dim, device=dev, generator=gen) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # pre-roll one full episode horizon (untimed, before the W warm-up steps): with staggered clocks every env has then been
+    # reset at a different step, so the timed steps see the steady-state mix of early- and late-episode states (arm near the
+    # cube / table late in an episode costs more: contacts, fallback-layout envs) instead of 16 K freshly reset envs
+    for t in range(args.preroll):
+        env.step(torch.rand(n, env.action_dim, device=dev, generator=gen) * 2 - 1)
     for t in range(W):
         env.step(acts[t])
     env.stats(reset=True)
@@ -242,6 +247,7 @@ def run_ours(args):
         env.step(acts[W + t])
         ev[t][1].record()
     stats = env.stats(reset=False).clone()
+    fallback_envs = env.last_fallback_envs()   # after the timed loop's last launch (synchronises; outside the event intervals)
     all_reduce_stats(stats)                # the path's only collective: 8 doubles, once per rollout
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
@@ -291,7 +297,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, {kw.get('controller_type', 'joint')} controller, "
                                    f"{100 if kw.get('controller_type') == 'IK' else 20} substeps/step, uniform random actions "
-                                   f"U[-1,1]^{env.action_dim} float32, 50-step TimeLimit (episode clocks staggered), auto-reset with on-device goal resampling",
+                                   f"U[-1,1]^{env.action_dim} float32, 50-step TimeLimit (episode clocks staggered, {args.preroll}-step untimed pre-roll), auto-reset with on-device goal resampling",
                        "envs_per_gpu": n, "lockstep_warps": env.lockstep_warps, "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -306,7 +312,7 @@ def run_ours(args):
                          "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
             "cpu_baseline": None if cpu_val is None else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "episode_stats": {"episodes": st[0], "successes": st[1], "return_sum": st[2], "length_sum": st[3], "env_steps": st[4],
-                              "row_overflows": st[5], "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
+                              "row_overflows": st[5], "fallback_envs_last_step": fallback_envs, "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
             "wall_s_timed_region": t_wall,
             "her_relabel": her,
         }
@@ -324,6 +330,7 @@ def main():
     ap.add_argument("--workload", default="pick", choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preroll", type=int, default=50, help="untimed steps before the warm-up (steady-state episode mix)")
     ap.add_argument("--no-her", action="store_true", help="skip the separately timed HER relabel leg")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-port timing leg (profiling runs)")
     args = ap.parse_args()

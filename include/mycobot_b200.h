@@ -228,6 +228,9 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
  * capturing mcb_step in a CUDA graph.  Returns the chosen grouping. */
 int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream);
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b);
+/* how many envs of the most recent launch overflowed the common shared-memory layout and were redone by the fallback
+ * kernel (synchronises the stream; diagnostics for bench.py) */
+int32_t mcb_last_fallback_envs(mcb_batch* b, void* stream);
 
 /* measurement helpers used by bench.py */
 int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */

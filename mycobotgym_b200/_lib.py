@@ -25,7 +25,7 @@ EXPORTS = [
     "mcb_model_destroy", "mcb_batch_create", "mcb_batch_destroy", "mcb_batch_num_envs", "mcb_batch_obs_dim", "mcb_batch_action_dim",
     "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
     "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
-    "mcb_time_step_kernel", "mcb_autotune", "mcb_batch_lockstep_warps", "mcb_her_create", "mcb_her_destroy", "mcb_her_add", "mcb_her_size", "mcb_her_episode_table",
+    "mcb_time_step_kernel", "mcb_autotune", "mcb_batch_lockstep_warps", "mcb_last_fallback_envs", "mcb_her_create", "mcb_her_destroy", "mcb_her_add", "mcb_her_size", "mcb_her_episode_table",
     "mcb_her_sample",
 ]
 
@@ -84,6 +84,7 @@ def load():
     L.mcb_fp64_peak_probe.argtypes = [i32, i32, C.POINTER(dbl)]
     L.mcb_autotune.argtypes = [vp, vp, i32, vp]
     L.mcb_batch_lockstep_warps.argtypes = [vp]
+    L.mcb_last_fallback_envs.argtypes = [vp, vp]
     L.mcb_her_create.argtypes = [i32, i32, i32, i32, i32, i32, dbl, u64, C.POINTER(vp)]
     L.mcb_her_destroy.argtypes = [vp]
     L.mcb_her_destroy.restype = None

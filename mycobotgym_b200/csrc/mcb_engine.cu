@@ -2465,6 +2465,14 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, do
 
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b) { return b ? b->lockstep_warps : -1; }
 
+int32_t mcb_last_fallback_envs(mcb_batch* b, void* stream) {
+  if (!b) return fail("mcb_last_fallback_envs: null batch");
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, b->redo_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
+}
+
 int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream) {
   if (!b) return fail("mcb_autotune: null batch");
   cudaStream_t st = (cudaStream_t)stream;

@@ -340,6 +340,11 @@ class MyCobotVectorEnv:
     def lockstep_warps(self):
         return int(self._L.mcb_batch_lockstep_warps(self._batch))
 
+    def last_fallback_envs(self):
+        """Envs of the most recent launch that needed the fallback shared-memory layout (synchronises)."""
+        with torch.cuda.device(self._dev_index):
+            return _lib.check(self._L.mcb_last_fallback_envs(self._batch, self._stream()))
+
     def forward(self):
         """mj_forward on every env (refreshes frames, qacc_warmstart and the observation buffers)."""
         with torch.cuda.device(self._dev_index):
