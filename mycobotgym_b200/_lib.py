@@ -16,6 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("MCB_LIB") or os.path.join(PKG_DIR, "libmycobot_b200.so")   # MCB_LIB: tuning experiments only
 SRC = os.path.join(PKG_DIR, "csrc", "mcb_engine.cu")
 HDR = os.path.join(ROOT, "include", "mycobot_b200.h")
+DEPS = (SRC, HDR, os.path.join(PKG_DIR, "csrc", "mcb_her.cuh"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=true",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -34,7 +35,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in (SRC, HDR))
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in DEPS)
 
 
 def build(force=False, verbose=False):

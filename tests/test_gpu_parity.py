@@ -203,6 +203,31 @@ def test_against_committed_golden_rollouts(name):
     env.close()
 
 
+@pytest.mark.parametrize("name", ["ik_pick_dense_seed3", "ik_fetch_pick_dense_seed5", "mocap_pick_dense_seed6", "mocap_fetch_pick_dense_seed7"])
+def test_against_committed_controller_golden(name):
+    # IK / mocap fixtures: every step starts from its recorded state (stale-frame configuration qprev and the mocap pose
+    # included).  Bound per step: 1e-7 or 100x the oracle's own recorded sensitivity to a one-ulp velocity perturbation.
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    controller, fetch = str(g["controller"]), bool(g["fetch"])
+    kw = dict(model_path="./assets/mycobot280_mocap.xml") if controller == "mocap" else {}
+    env = _env(num_envs=1, has_object=True, reward_type="dense", controller_type=controller, fetch_env=fetch, auto_reset=False, **kw)
+    nu = 1 if controller == "mocap" else 7
+    for t in range(len(g["actions"])):
+        ctrl = np.zeros((1, 7)); ctrl[0, :nu] = g["ctrl0"][t]
+        env.set_state(qpos=g["qpos0"][t][None], qvel=g["qvel0"][t][None], ctrl=ctrl, qacc_warmstart=g["warm0"][t][None],
+                      goal=g["goal"][None], elapsed=np.zeros(1, dtype=np.int32), qprev=g["qprev0"][t][None], mocap=g["mocap0"][t][None])
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(g["actions"][t][None]))
+        st = env.get_state()
+        tol = min(max(1e-7, 100 * float(g["sens"][t])), 1e-4)
+        np.testing.assert_allclose(st["qpos"][0].cpu().numpy(), g["qpos"][t], atol=tol, rtol=0, err_msg=f"step {t}")
+        np.testing.assert_allclose(st["ctrl"][0, :nu].cpu().numpy(), g["ctrl"][t], atol=tol, rtol=0)
+        np.testing.assert_allclose(st["qprev"][0].cpu().numpy(), g["qprev"][t], atol=tol, rtol=0)
+        np.testing.assert_allclose(st["mocap"][0].cpu().numpy(), g["mocap"][t], atol=1e-12 if controller == "mocap" else 1.0, rtol=0)
+        np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), g["obs"][t], atol=tol * 10, rtol=0)
+        assert abs(float(rew[0]) - float(g["reward"][t])) < tol * 10
+    env.close()
+
+
 def test_reference_seeded_goals_are_bit_exact(flat):
     # goals injected from the reference's seeded sampling protocol (random.seed(k) and reset(seed=k))
     from oracle.oracle import OracleEnv

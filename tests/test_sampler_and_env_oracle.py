@@ -117,6 +117,35 @@ def test_oracle_reproduces_committed_golden(flat, name):
         assert te == bool(g["terminated"][t]) and tr == bool(g["truncated"][t])
 
 
+CTRL_GOLDEN = ["ik_pick_dense_seed3", "ik_fetch_pick_dense_seed5", "mocap_pick_dense_seed6", "mocap_fetch_pick_dense_seed7"]
+
+
+@pytest.mark.parametrize("name", CTRL_GOLDEN)
+def test_oracle_reproduces_controller_golden(flat, name):
+    # IK / mocap controller fixtures (tools/make_golden.py controller_rollout): each step restarts from its recorded state,
+    # stale frames included (kinematics at qprev), so a regression in either controller path of the oracle shows up here
+    from mycobotgym_b200 import mjcf
+
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    controller, fetch = str(g["controller"]), bool(g["fetch"])
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP) if controller == "mocap" else flat
+    env = OracleEnv(fm, has_object=True, reward_type="dense", controller_type=controller, fetch_env=fetch)
+    env.goal = g["goal"].copy()
+    for t in range(len(g["actions"])):
+        q_stale = g["qpos0"][t].copy()
+        q_stale[:6] = g["qprev0"][t]
+        env.sim.set_state(q_stale, g["qvel0"][t], g["ctrl0"][t], g["warm0"][t])
+        env.sim.kinematics()
+        env.sim.qpos[:] = g["qpos0"][t]
+        env.sim.mocap_pos[:], env.sim.mocap_quat[:] = g["mocap0"][t][:3], g["mocap0"][t][3:]
+        o, r, te, tr, info = env.step(g["actions"][t])
+        np.testing.assert_allclose(env.sim.qpos, g["qpos"][t], atol=1e-12)
+        np.testing.assert_allclose(env.sim.ctrl, g["ctrl"][t], atol=1e-12)
+        np.testing.assert_allclose(np.concatenate((env.sim.mocap_pos, env.sim.mocap_quat)), g["mocap"][t], atol=1e-14)
+        np.testing.assert_allclose(o["observation"], g["obs"][t], atol=1e-12)
+        assert float(r) == pytest.approx(float(g["reward"][t]), abs=1e-12)
+
+
 def test_staged_reward_on_the_oracle(flat):
     # mycobot.py:402-448: reach term only while the cube is not held; grasp / lift terms once both finger layers touch it
     env = OracleEnv(flat, has_object=True, reward_type="reward_shaping")

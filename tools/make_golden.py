@@ -49,11 +49,12 @@ def rollout(name, has_object, block_gripper, reward_type, seed, nsteps, perturb)
     print(name, "final qpos[:6]", rec["qpos"][-1][:6])
 
 
-rollout("reach_dense_seed0", False, False, "dense", 0, 6, False)
-rollout("reach_dense_seed1_perturbed", False, False, "dense", 1, 6, True)
-rollout("pick_sparse_seed0", True, False, "sparse", 0, 6, False)
-rollout("pick_sparse_seed4_perturbed", True, False, "sparse", 4, 6, True)
-rollout("push_sparse_seed2", True, True, "sparse", 2, 6, False)
+def joint_rollouts():
+    rollout("reach_dense_seed0", False, False, "dense", 0, 6, False)
+    rollout("reach_dense_seed1_perturbed", False, False, "dense", 1, 6, True)
+    rollout("pick_sparse_seed0", True, False, "sparse", 0, 6, False)
+    rollout("pick_sparse_seed4_perturbed", True, False, "sparse", 4, 6, True)
+    rollout("push_sparse_seed2", True, True, "sparse", 2, 6, False)
 
 
 def grasp():
@@ -95,4 +96,78 @@ def grasp():
     print("grasp ncon", rec["ncon"], "nefc", rec["nefc"])
 
 
-grasp()
+
+def controller_rollout(name, controller, fetch, seed, nsteps=3):
+    """IK / mocap controllers: every step is recorded with the state it starts from, including the arm
+    configuration the reference's stale frames belong to (`qprev`) and data.mocap_pos / mocap_quat, plus the oracle's own
+    sensitivity to a one-ulp perturbation of the arm velocities (the bang-bang actuators make 100 substeps chaotic)."""
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP) if controller == "mocap" else flat
+    tight = mjcf.FlatModel(fm)
+    tight["tolerance"] = 1e-13
+    kw = dict(has_object=True, reward_type="dense", controller_type=controller, fetch_env=fetch)
+    env, env2 = OracleEnv(fm, **kw), OracleEnv(tight, **kw)
+    rng = np.random.default_rng(seed)
+    random.seed(seed)
+    env.reset(seed=seed)
+    adim = 4 if fetch else (8 if controller == "mocap" else 7)
+    tcp = fm["body_names"].index("gripper_tcp") if controller == "mocap" else None
+    last_pre = {}
+
+    def wrap(e, key):
+        orig = e.sim.step
+
+        def step_rec(n):
+            orig(n - 1)
+            last_pre[key] = e.sim.qpos[:6].copy()
+            orig(1)
+        e.sim.step = step_rec
+
+    wrap(env, "a"); wrap(env2, "b")
+    rec = {k: [] for k in ["qpos0", "qvel0", "ctrl0", "warm0", "qprev0", "mocap0", "actions", "qpos", "qvel", "ctrl", "warm", "qprev", "mocap", "obs",
+                           "reward", "sens"]}
+    qprev = env.sim.qpos[:6].copy()                     # frames are fresh after reset
+    for t in range(nsteps):
+        s = env.sim
+        rec["qpos0"].append(s.qpos.copy()); rec["qvel0"].append(s.qvel.copy()); rec["ctrl0"].append(s.ctrl.copy())
+        rec["warm0"].append(s.qacc_warmstart.copy()); rec["qprev0"].append(qprev.copy())
+        rec["mocap0"].append(np.concatenate((s.mocap_pos, s.mocap_quat)))
+        # the perturbed twin starts from the same state with stale frames re-created the same way the tests do it
+        for e, scale in ((env2, 1 + 2.2e-16),):
+            q_stale = s.qpos.copy(); q_stale[:6] = qprev
+            e.sim.set_state(q_stale, s.qvel, s.ctrl, s.qacc_warmstart)
+            e.sim.kinematics()
+            e.sim.qpos[:] = s.qpos
+            e.sim.mocap_pos[:] = s.mocap_pos; e.sim.mocap_quat[:] = s.mocap_quat
+            e.sim.qvel[:6] *= scale
+            e.goal = env.goal.copy()
+        a = rng.uniform(-1, 1, adim).astype(np.float32)
+        if controller == "mocap" and not fetch and t % 2 == 0:
+            a[3:7] = (s.xquat[tcp] + 0.1 * rng.uniform(-1, 1, 4)).astype(np.float32)
+        o, r, te, tr, info = env.step(a)
+        env2.step(a)
+        qprev = last_pre["a"].copy()
+        rec["actions"].append(a); rec["qpos"].append(s.qpos.copy()); rec["qvel"].append(s.qvel.copy()); rec["ctrl"].append(s.ctrl.copy())
+        rec["warm"].append(s.qacc_warmstart.copy()); rec["qprev"].append(qprev.copy())
+        rec["mocap"].append(np.concatenate((s.mocap_pos, s.mocap_quat)))
+        rec["obs"].append(o["observation"]); rec["reward"].append(np.float64(r))
+        rec["sens"].append(np.abs(env2.sim.qpos - s.qpos).max())
+    np.savez(os.path.join(OUT, name + ".npz"), controller=controller, fetch=fetch, goal=env.goal.copy(),
+             **{k: np.asarray(v) for k, v in rec.items()})
+    print(name, "sens", rec["sens"], "final arm", rec["qpos"][-1][:6])
+
+
+def controller_rollouts():
+    controller_rollout("ik_pick_dense_seed3", "IK", False, 3)
+    controller_rollout("ik_fetch_pick_dense_seed5", "IK", True, 5)
+    controller_rollout("mocap_pick_dense_seed6", "mocap", False, 6)
+    controller_rollout("mocap_fetch_pick_dense_seed7", "mocap", True, 7)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"      # all | joint | grasp | controllers
+    if which in ("all", "joint"):
+        joint_rollouts()
+    if which in ("all", "grasp"):
+        grasp()
+    if which in ("all", "controllers"):
+        controller_rollouts()
