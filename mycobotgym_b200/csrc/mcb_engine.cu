@@ -171,7 +171,9 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
+// (noinline here and on mulM_row, and one DADD instantiation of the 12 x 12 factorisation for all three uses: the hot code
+// footprint is what free-running warps pay for in instruction fetch -- profiles/README.md)
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
   return v;
@@ -525,7 +527,7 @@ __device__ __noinline__ double chol_solve_blk(const double* src, double* dst, co
 // b is read from the shared vector bsrc; ytmp is an 18-double shared scratch.
 __device__ __forceinline__ double factor_solve(const double* src, double* dst, const double* bsrc, double* ytmp, int lane, int nva, bool coupled) {
   if (coupled) return chol_solve_blk<0, 18, false>(src, dst, bsrc, ytmp, 0.0, lane);
-  double x = chol_solve_blk<0, 12, false>(src, dst, bsrc, ytmp, 0.0, lane);
+  double x = chol_solve_blk<0, 12, true>(src, dst, bsrc, ytmp, 0.0, lane);
   if (nva > NH) { double xc = chol_solve_blk<12, 6, false>(src, dst, bsrc, ytmp, 0.0, lane); if (lane >= NH) x = xc; }
   return x;
 }
@@ -539,7 +541,7 @@ __device__ __forceinline__ double factor_solve_M(const double* M, double* dst, c
 }
 // y_i = sum_j M_ij v_j for the lane's row (block diagonal: robot lanes see columns 0..11, cube lanes 12..17)
 template <class S>
-__device__ __forceinline__ double mulM_row(const S& s, int lane, int nva, const double* v) {
+__device__ __noinline__ double mulM_row(const S& s, int lane, int nva, const double* v) {
   double acc = 0, a1 = 0, a2 = 0;
   const int ro = lane * (lane + 1) / 2;
   if (lane < NH) {
@@ -1581,7 +1583,7 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
   velocity_rne(s, m, lane, nba, nva);
   FSYNC();
   actuation_smooth(s, m, lane, nva);
-  double qs = factor_solve_M<false>(s.M, s.H, s.qfrc_smooth, s.Mv, 0.0, lane, nva);
+  double qs = factor_solve_M<true>(s.M, s.H, s.qfrc_smooth, s.Mv, 0.0, lane, nva);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
   FSYNC();
