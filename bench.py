@@ -312,7 +312,7 @@ def run_ours(args):
                          "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
             "cpu_baseline": None if cpu_val is None else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "episode_stats": {"episodes": st[0], "successes": st[1], "return_sum": st[2], "length_sum": st[3], "env_steps": st[4],
-                              "row_overflows": st[5], "fallback_envs_last_step": fallback_envs, "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
+                              "row_overflows": st[5], "fallback_envs_last_step": fallback_envs[0], "last_tier_envs_last_step": fallback_envs[1], "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
             "wall_s_timed_region": t_wall,
             "her_relabel": her,
         }

@@ -140,7 +140,8 @@ typedef struct mcb_task_cfg {
   int32_t max_episode_steps;   /* 50 */
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
-  int32_t nefc_max;            /* 0 (default): two-tier layout (48-row common case + 128-row fallback launch); 128: fallback layout only */
+  int32_t nefc_max;            /* 0 (default): tiered shared-memory layouts (48-row common case, 88-row middle tier for contact-rich envs,
+                                * 128-row last tier), one launch each; 88 / 128: start in the middle / last tier (tests) */
   int32_t controller_type;     /* 0 joint (action 7), 1 IK (7, or 4 with fetch_env), 2 mocap (8, or 4 with fetch_env; needs the mocap
                                   model variant); mycobot.py:36,90-103,134-193 */
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
@@ -228,9 +229,10 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
  * capturing mcb_step in a CUDA graph.  Returns the chosen grouping. */
 int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream);
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b);
-/* how many envs of the most recent launch overflowed the common shared-memory layout and were redone by the fallback
- * kernel (synchronises the stream; diagnostics for bench.py) */
-int32_t mcb_last_fallback_envs(mcb_batch* b, void* stream);
+/* how many envs of the most recent step overflowed the common shared-memory layout and were redone by the middle-tier
+ * kernel (return value) and how many of those also overflowed the middle tier (*last_tier_envs, may be NULL).
+ * Synchronises the stream; diagnostics for bench.py. */
+int32_t mcb_last_fallback_envs(mcb_batch* b, int32_t* last_tier_envs, void* stream);
 
 /* measurement helpers used by bench.py */
 int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */

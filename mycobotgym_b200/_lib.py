@@ -85,7 +85,7 @@ def load():
     L.mcb_fp64_peak_probe.argtypes = [i32, i32, C.POINTER(dbl)]
     L.mcb_autotune.argtypes = [vp, vp, i32, vp]
     L.mcb_batch_lockstep_warps.argtypes = [vp]
-    L.mcb_last_fallback_envs.argtypes = [vp, vp]
+    L.mcb_last_fallback_envs.argtypes = [vp, C.POINTER(i32), vp]
     L.mcb_her_create.argtypes = [i32, i32, i32, i32, i32, i32, dbl, u64, C.POINTER(vp)]
     L.mcb_her_destroy.argtypes = [vp]
     L.mcb_her_destroy.restype = None

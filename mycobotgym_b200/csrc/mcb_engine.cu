@@ -97,6 +97,7 @@ struct StepArgs {
   const DevModel* m;
   int n_envs, mode;
   int lockstep_warps;        // warps per lockstep group of the common-layout kernel (1 = free-running), see group_sync()
+  int mid_threshold;         // the middle tier only runs when more envs than this left the common layout (else: straight to the last tier)
   mcb_task_cfg cfg;
   uint64_t seed;
   double* state;             // [N, 72]
@@ -104,8 +105,8 @@ struct StepArgs {
   double* ep_return;         // [N]
   unsigned long long* rng_ctr;  // [N]
   double* stats;             // [8]
-  int* redo_count;           // envs that overflowed the small layout in this launch
-  int* redo_list;            // [N]
+  int* redo_count;           // [2] envs that overflowed tier 0 / tier 1 in this step
+  int* redo_list;            // [2][N]
   const float* actions;      // [N, 7]
   const uint8_t* mask;       // reset
   const double* inj_xy;      // reset
@@ -120,9 +121,12 @@ struct StepArgs {
 // ------------------------------------------------------------------------------------------------
 // per-env shared-memory working set.  BIG = false: the common case; BIG = true: the fallback for envs whose
 // contact set does not fit (grasps, pile-ups).
-template <bool BIG>
+// TIER 0: the common case (16 envs per CTA); TIER 1: contact-rich envs -- a grasp, pushing, the gripper resting on the
+// table (10 envs per CTA); TIER 2: the last resort, one env per CTA, rows beyond its capacity are dropped and counted.
+template <int TIER>
 struct EnvS {
-  enum { NROW = BIG ? 128 : 48, POOL = BIG ? 2432 : 460, MAXC = BIG ? 16 : 8, IS_BIG = BIG };
+  enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : 128, POOL = TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432, MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : 16,
+         IS_BIG = TIER == 2 };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
   double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
   double M[NTRI + 1], H[NTRIP];          // H doubles as the factor storage of chol_solve_blk (padded rows, TRIP)
@@ -143,8 +147,9 @@ struct EnvS {
   int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
   int nR, nC, nF, nU, nefc, ncon, overflow, iters;
 };
-static_assert(offsetof(EnvS<false>, H) % 16 == 0 && offsetof(EnvS<true>, H) % 16 == 0, "factor storage must be 16-byte aligned (128-bit loads)");
-static_assert(sizeof(EnvS<false>) % 16 == 0 && sizeof(EnvS<true>) % 16 == 0, "per-env records must keep 16-byte alignment");
+static_assert(offsetof(EnvS<0>, H) % 16 == 0 && offsetof(EnvS<1>, H) % 16 == 0 && offsetof(EnvS<2>, H) % 16 == 0, "factor storage must be 16-byte aligned (128-bit loads)");
+static_assert(sizeof(EnvS<0>) % 16 == 0 && sizeof(EnvS<1>) % 16 == 0 && sizeof(EnvS<2>) % 16 == 0, "per-env records must keep 16-byte alignment");
+static_assert(MODEL_BYTES + 16 * sizeof(EnvS<0>) <= 232448 && MODEL_BYTES + 10 * sizeof(EnvS<1>) <= 232448, "a CTA must fit the 227 KB of shared memory an SM offers");
 
 
 // ------------------------------------------------------------------------------------------------
@@ -1962,11 +1967,13 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 #ifndef ENV_LB_THREADS
 #define ENV_LB_THREADS (32 * WPB_SMALL)      // register budget of the common-layout kernel = 65536 / ENV_LB_THREADS (tuning knob)
 #endif
-template <bool BIG>
-__global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_env_kernel(const StepArgs a) {
-  typedef EnvS<BIG> S;
+#define WPB_MID 10
+template <int TIER>
+__global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * WPB_MID : 32, TIER == 2 ? 5 : 1) mcb_env_kernel(const StepArgs a) {
+  typedef EnvS<TIER> S;
+  constexpr bool BIG = TIER == 2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int wpb = BIG ? 1 : WPB_SMALL;
+  const int wpb = TIER == 0 ? WPB_SMALL : TIER == 1 ? WPB_MID : 1;
   S& s = *reinterpret_cast<S*>(smem_raw + MODEL_BYTES + (size_t)wid * sizeof(S));
   const DevModel* __restrict__ m = a.m;
   {  // stage the model (global -> shared), once per CTA
@@ -1978,13 +1985,24 @@ __global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_en
   const mcb_task_cfg& cfg = a.cfg;
   const int nba = cfg.has_object ? NB : NB - 1;
   const int nva = cfg.has_object ? NV : NH;
-  const int nwork = BIG ? *a.redo_count : a.n_envs;
-  const int lockstep = (!BIG && a.lockstep_warps > 1) ? a.lockstep_warps : 0;
+  const int nwork = TIER == 0 ? a.n_envs : a.redo_count[TIER - 1];
+  const int* work_list = TIER == 0 ? nullptr : a.redo_list + (size_t)(TIER - 1) * a.n_envs;
+  if (TIER > 0 && nwork == 0) return;
+  if (TIER == 1 && nwork <= a.mid_threshold) {
+    // A tier pass costs the latency of one whole env-step of a single warp whatever the list length, and envs that do not
+    // fit here either pay it twice.  A short list is therefore handed to the last tier as it is: its one-warp CTAs take
+    // it in a single wave.  The middle tier pays off when many envs are in contact at once (a batch of grasps).
+    int* next = a.redo_list + (size_t)a.n_envs;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) next[i] = work_list[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.redo_count[1] = nwork;
+    return;
+  }
+  const int lockstep = (TIER == 0 && a.lockstep_warps > 1) ? a.lockstep_warps : 0;
 
   for (int item0 = blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
     const int item = item0 + wid;
     bool valid = item < nwork;
-    const int env = valid ? (BIG ? a.redo_list[item] : item) : 0;
+    const int env = valid ? (TIER == 0 ? item : work_list[item]) : 0;
     if (valid && a.mode == MODE_RESET && a.mask && !a.mask[env]) valid = false;
 
     // zero what has a static sparsity pattern or is read before it is first written
@@ -2169,9 +2187,9 @@ __global__ void __launch_bounds__(BIG ? 32 : ENV_LB_THREADS, BIG ? 4 : 1) mcb_en
     __syncwarp();
     if (valid) {
       if (!ok) {
-        // small layout overflowed: leave the env untouched for the big-layout launch
+        // this tier's layout overflowed: leave the env untouched for the next tier's launch
         // (observation rows written above are rewritten by it; state, counters and statistics are not yet committed)
-        if (lane == 0) { int k = atomicAdd(a.redo_count, 1); a.redo_list[k] = env; }
+        if (TIER < 2 && lane == 0) { int k = atomicAdd(a.redo_count + TIER, 1); a.redo_list[(size_t)TIER * a.n_envs + k] = env; }
       } else {
         store_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane);
         if (lane == 0) {
@@ -2279,8 +2297,8 @@ struct mcb_model {
 
 struct mcb_batch {
   mcb_model* model;
-  int n_envs, obs_dim, big_only, big_grid;
-  size_t smem_small, smem_big;
+  int n_envs, obs_dim, big_only, mid_only, big_grid, mid_grid;
+  size_t smem_small, smem_mid, smem_big;
   int* redo_count; int* redo_list;
   mcb_task_cfg cfg;
   uint64_t seed;
@@ -2298,15 +2316,17 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
   a.redo_count = b->redo_count; a.redo_list = b->redo_list;
   a.lockstep_warps = b->lockstep_warps;
-  if (b->big_only) {
-    iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
-  } else {
-    CK(cudaMemsetAsync(b->redo_count, 0, sizeof(int), st));
-    mcb_env_kernel<false><<<(b->n_envs + WPB_SMALL - 1) / WPB_SMALL, 32 * WPB_SMALL, b->smem_small, st>>>(a);
-  }
+  a.mid_threshold = b->mid_only ? -1 : b->big_grid;
+  CK(cudaMemsetAsync(b->redo_count, 0, 2 * sizeof(int), st));
+  if (b->big_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list + b->n_envs, b->redo_count + 1, b->n_envs);
+  else if (b->mid_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
+  else mcb_env_kernel<0><<<(b->n_envs + WPB_SMALL - 1) / WPB_SMALL, 32 * WPB_SMALL, b->smem_small, st>>>(a);
   CK(cudaGetLastError());
-  // fallback launch for envs that overflowed the small layout (grid-stride over the device list; usually empty)
-  mcb_env_kernel<true><<<b->big_only ? b->n_envs : b->big_grid, 32, b->smem_big, st>>>(a);
+  // envs that overflowed the common layout (grid-stride over the device list; empty in contact-free workloads) ...
+  if (!b->big_only) mcb_env_kernel<1><<<b->mid_only ? (b->n_envs + WPB_MID - 1) / WPB_MID : b->mid_grid, 32 * WPB_MID, b->smem_mid, st>>>(a);
+  CK(cudaGetLastError());
+  // ... and the few that overflowed the middle one
+  mcb_env_kernel<2><<<b->big_only ? b->n_envs : b->big_grid, 32, b->smem_big, st>>>(a);
   CK(cudaGetLastError());
   return 0;
 }
@@ -2314,9 +2334,10 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
 extern "C" {
 
 const char* mcb_version(void) {
-  static char buf[160];
-  snprintf(buf, sizeof buf, "mycobot_b200 0.3 (sm_100a; shared memory per env: %zu B common layout, %zu B fallback layout; model %zu B; CTA %zu B)",
-           sizeof(EnvS<false>), sizeof(EnvS<true>), (size_t)MODEL_BYTES, (size_t)(MODEL_BYTES + sizeof(EnvS<false>) * WPB_SMALL));
+  static char buf[256];
+  snprintf(buf, sizeof buf, "mycobot_b200 0.4 (sm_100a; shared memory per env: %zu B common layout (16 per CTA), %zu B middle tier (%d per CTA), %zu B last tier; model %zu B; CTAs %zu / %zu / %zu B)",
+           sizeof(EnvS<0>), sizeof(EnvS<1>), WPB_MID, sizeof(EnvS<2>), (size_t)MODEL_BYTES, (size_t)(MODEL_BYTES + sizeof(EnvS<0>) * WPB_SMALL),
+           (size_t)(MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID), (size_t)(MODEL_BYTES + sizeof(EnvS<2>)));
   return buf;
 }
 const char* mcb_last_error(void) { return g_err.c_str(); }
@@ -2404,16 +2425,21 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   memset(b, 0, sizeof *b);
   b->model = m; b->n_envs = n_envs; b->cfg = *cfg; b->seed = seed;
   b->obs_dim = cfg->has_object ? MCB_OBS_OBJECT : MCB_OBS_REACH;
-  if (cfg->nefc_max != 0 && cfg->nefc_max != 48 && cfg->nefc_max != 128) { delete b; return fail("mcb_batch_create: nefc_max must be 0 (two-tier), 48 or 128"); }
+  if (cfg->nefc_max != 0 && cfg->nefc_max != 48 && cfg->nefc_max != 88 && cfg->nefc_max != 128) { delete b; return fail("mcb_batch_create: nefc_max must be 0 (tiered), 48, 88 (start in the middle tier) or 128 (last tier only)"); }
   b->big_only = cfg->nefc_max == 128;
-  b->smem_small = MODEL_BYTES + sizeof(EnvS<false>) * WPB_SMALL;
-  b->smem_big = MODEL_BYTES + sizeof(EnvS<true>);
+  b->mid_only = cfg->nefc_max == 88;
+  b->smem_small = MODEL_BYTES + sizeof(EnvS<0>) * WPB_SMALL;
+  b->smem_mid = MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID;
+  b->smem_big = MODEL_BYTES + sizeof(EnvS<2>);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, m->device));
-  b->big_grid = prop.multiProcessorCount * 4;
-  cudaError_t e = cudaFuncSetAttribute(mcb_env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_small);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  b->big_grid = prop.multiProcessorCount * 5;      // five one-warp CTAs of the last tier are resident per SM (44.5 KB each)
+  b->mid_grid = prop.multiProcessorCount;
+  cudaError_t e = cudaFuncSetAttribute(mcb_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_small);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_mid);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(shared memory)", e); }
   size_t N = (size_t)n_envs;
   CK(cudaMalloc(&b->state, N * MCB_STATE_STRIDE * sizeof(double)));
@@ -2421,9 +2447,9 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   CK(cudaMalloc(&b->ep_return, N * sizeof(double)));
   CK(cudaMalloc(&b->rng_ctr, N * sizeof(unsigned long long)));
   CK(cudaMalloc(&b->stats, 8 * sizeof(double)));
-  CK(cudaMalloc(&b->redo_count, sizeof(int)));
-  CK(cudaMalloc(&b->redo_list, N * sizeof(int)));
-  CK(cudaMemset(b->redo_count, 0, sizeof(int)));
+  CK(cudaMalloc(&b->redo_count, 2 * sizeof(int)));
+  CK(cudaMalloc(&b->redo_list, 2 * N * sizeof(int)));
+  CK(cudaMemset(b->redo_count, 0, 2 * sizeof(int)));
   CK(cudaMalloc(&b->debug, DEBUG_DOUBLES * sizeof(double)));
   CK(cudaMemset(b->stats, 0, 8 * sizeof(double)));
   init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs, cfg->fetch_env);
@@ -2460,26 +2486,27 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, do
   StepArgs a; memset(&a, 0, sizeof a);
   a.mode = MODE_STEP; a.actions = actions; a.obs = obs; a.ag = ag; a.dg = dg; a.reward = reward;
   a.terminated = terminated; a.truncated = truncated; a.success = success; a.final_obs = final_obs;
-  b->last_launches = 2;  // small-layout kernel + big-layout fallback kernel
-  if (!b->tuned && !b->big_only) { if (mcb_autotune(b, nullptr, 0, stream) < 0) return -1; }
+  b->last_launches = 3;  // one kernel per layout tier (the second and third usually find an empty list)
+  if (!b->tuned && !b->big_only && !b->mid_only) { if (mcb_autotune(b, nullptr, 0, stream) < 0) return -1; }
   return launch(b, a, (cudaStream_t)stream);
 }
 
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b) { return b ? b->lockstep_warps : -1; }
 
-int32_t mcb_last_fallback_envs(mcb_batch* b, void* stream) {
+int32_t mcb_last_fallback_envs(mcb_batch* b, int32_t* last_tier_envs, void* stream) {
   if (!b) return fail("mcb_last_fallback_envs: null batch");
-  int n = 0;
-  CK(cudaMemcpyAsync(&n, b->redo_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  int n[2] = {0, 0};
+  CK(cudaMemcpyAsync(n, b->redo_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
-  return n;
+  if (last_tier_envs) *last_tier_envs = n[1];
+  return n[0];
 }
 
 int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream) {
   if (!b) return fail("mcb_autotune: null batch");
   cudaStream_t st = (cudaStream_t)stream;
   b->tuned = 1;
-  if (b->cfg.lockstep_warps != 0 || b->big_only) return b->lockstep_warps;
+  if (b->cfg.lockstep_warps != 0 || b->big_only || b->mid_only) return b->lockstep_warps;
   const int K = steps_per_candidate > 0 ? steps_per_candidate : 4;
   const size_t N = (size_t)b->n_envs;
   const size_t adim = (size_t)mcb_batch_action_dim(b);

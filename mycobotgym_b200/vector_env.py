@@ -341,9 +341,12 @@ class MyCobotVectorEnv:
         return int(self._L.mcb_batch_lockstep_warps(self._batch))
 
     def last_fallback_envs(self):
-        """Envs of the most recent launch that needed the fallback shared-memory layout (synchronises)."""
+        """(envs of the most recent step that left the common shared-memory layout for the middle tier, envs that also
+        left the middle tier for the last one); synchronises."""
+        last = C.c_int32(0)
         with torch.cuda.device(self._dev_index):
-            return _lib.check(self._L.mcb_last_fallback_envs(self._batch, self._stream()))
+            n = _lib.check(self._L.mcb_last_fallback_envs(self._batch, C.byref(last), self._stream()))
+        return n, int(last.value)
 
     def forward(self):
         """mj_forward on every env (refreshes frames, qacc_warmstart and the observation buffers)."""

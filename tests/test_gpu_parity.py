@@ -330,7 +330,7 @@ def test_host_buffer_entry_point_equals_device_entry_point():
         out = e2.step_host(a)
     assert np.array_equal(o1["observation"].cpu().numpy(), out["observation"])
     assert np.array_equal(r1.cpu().numpy(), out["reward"]) and np.array_equal(t1.cpu().numpy(), out["terminated"].astype(bool))
-    assert e1.last_step_launches == 2          # common-layout kernel + fallback-layout kernel
+    assert e1.last_step_launches == 3          # one kernel per layout tier
     e1.close(); e2.close()
 
 
@@ -380,8 +380,9 @@ def test_state_roundtrip_and_ragged_sizes(flat):
         env.close()
 
 
-def test_two_tier_layout_equals_fallback_layout(flat):
-    # the same states through (a) the 48-row common layout with the fallback launch and (b) the 128-row layout only
+def test_tiered_layouts_are_bit_identical(flat):
+    # the same states through (a) the tiered launch (48-row common layout, then 88-row middle tier, then 128-row last tier),
+    # (b) the middle tier only and (c) the last tier only
     n = 64
     qpos, qvel, ctrl = _states(flat, n, 31)
     g = np.load(os.path.join(GOLDEN, "grasp_pick_sparse.npz"))      # a grasp: coupled rows overflow the common layout
@@ -389,16 +390,46 @@ def test_two_tier_layout_equals_fallback_layout(flat):
     acts = np.random.default_rng(32).uniform(-1, 1, (n, 7)).astype(np.float32)
     acts[5] = g["actions"][0]
     outs = []
-    for nefc_max in (0, 128):
+    for nefc_max in (0, 88, 128):
         env = _env(num_envs=n, has_object=True, reward_type="sparse", auto_reset=False, nefc_max=nefc_max)
         env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=np.zeros((n, 18)), goal=np.tile([0.0, 0.0, 0.3], (n, 1)),
                       elapsed=np.zeros(n, dtype=np.int32))
         obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
         st = env.get_state()
+        if nefc_max == 0:
+            assert env.last_fallback_envs() == (1, 1)          # one env left the common layout; a short list goes straight to the last tier
+        outs.append((st["qpos"].cpu().numpy(), st["qvel"].cpu().numpy(), obs["observation"].cpu().numpy(), env.stats().cpu().numpy()))
+        env.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+        assert o[3][4] == n and o[3][5] == 0                    # every env stepped exactly once, nothing dropped
+
+
+def test_many_grasps_take_the_middle_tier():
+    # a batch in which every env holds the cube (what a trained pick-and-place policy looks like): the list is long enough
+    # for the middle tier (> 5 x SM count); results equal the last-tier-only run bit for bit
+    n = 1000
+    g = np.load(os.path.join(GOLDEN, "grasp_pick_sparse.npz"))
+    rep = lambda x: np.repeat(np.asarray(x)[None], n, 0)
+    rng = np.random.default_rng(7)
+    qvel = rep(g["qvel0"]) + 1e-3 * rng.normal(size=(n, 18))
+    acts = np.zeros((n, 7), dtype=np.float32)
+    acts[:, 6] = 0.8
+    acts[:, :6] = rng.uniform(-0.05, 0.05, (n, 6)).astype(np.float32) + g["qpos0"][:6].astype(np.float32)
+    outs = []
+    for nefc_max in (0, 128):
+        env = _env(num_envs=n, has_object=True, reward_type="sparse", auto_reset=False, nefc_max=nefc_max, lockstep_warps=16)
+        env.set_state(qpos=rep(g["qpos0"]), qvel=qvel, ctrl=rep(g["ctrl0"]), qacc_warmstart=rep(g["warm0"]), goal=rep(g["goal"]),
+                      elapsed=np.zeros(n, dtype=np.int32), qprev=rep(g["qpos0"][:6]))
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
+        if nefc_max == 0:
+            left_common, left_middle = env.last_fallback_envs()
+            assert left_common > 900 and left_middle < 50, (left_common, left_middle)
+        st = env.get_state()
         outs.append((st["qpos"].cpu().numpy(), st["qvel"].cpu().numpy(), obs["observation"].cpu().numpy(), env.stats().cpu().numpy()))
         env.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
-    assert outs[0][3][4] == n and outs[0][3][5] == 0            # every env stepped exactly once, nothing dropped
+    assert outs[0][3][4] == n and outs[0][3][5] == 0
 
 
 def test_staged_reward_matches_oracle(flat):
