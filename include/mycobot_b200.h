@@ -210,7 +210,7 @@ int32_t mcb_compute_reward(const double* achieved_goal, const double* goal, int6
                            int32_t reward_type, void* out, void* stream);
 
 /* episode statistics accumulated on device since the last call with reset_after != 0:
- * out[0]=episodes, [1]=successes, [2]=return_sum, [3]=length_sum, [4]=env_steps, [5]=anomalies (constraint rows dropped in the fallback layout + bad-simulation resets),
+ * out[0]=episodes, [1]=successes, [2]=return_sum, [3]=length_sum, [4]=env_steps, [5]=anomalies (constraint rows dropped in the last layout tier + bad-simulation resets),
  * [6]=solver iterations, [7]=substeps.  `out` is a device pointer to 8 doubles. */
 int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream);
 
