@@ -12,7 +12,8 @@ from mycobotgym_b200.vector_env import MyCobotVectorEnv  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 g = np.load(os.path.join(ROOT, "tests", "golden", "grasp_pick_sparse.npz"))
-env = MyCobotVectorEnv(num_envs=n, has_object=True, reward_type="sparse", auto_reset=False, seed=1)
+lw = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+env = MyCobotVectorEnv(num_envs=n, has_object=True, reward_type="sparse", auto_reset=False, seed=1, lockstep_warps=lw)
 env.reset()
 rep = lambda x: np.repeat(x[None], n, 0)
 env.set_state(qpos=rep(g["qpos0"]), qvel=rep(g["qvel0"]), ctrl=rep(g["ctrl0"]), qacc_warmstart=rep(g["warm0"]), goal=rep(g["goal"]),
