@@ -261,7 +261,7 @@ def run_ours(args):
     value = world * n * K / (total_ms * 1e-3)
 
     # e2e: the same step through host buffers (pinned staging inside the C ABI), H2D + D2H inside the timed region
-    a_host = acts[W:].cpu().numpy()
+    a_host = acts[W:].cpu().pin_memory().numpy()      # pinned host actions, as the contract asks
     out = env.step_host(a_host[0])
     torch.cuda.synchronize()
     if world > 1:

@@ -183,9 +183,10 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* achiev
                  void* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* success, double* final_obs,
                  void* stream);
 
-/* Same call with HOST buffers: actions are copied host->device and results device->host inside the call
- * (pinned staging owned by the batch); synchronises `stream` before returning.  This is the call a
- * reference-side VecEnv adapter holding numpy arrays makes. */
+/* Same call with HOST buffers: actions are copied host->device and results device->host inside the call;
+ * synchronises `stream` before returning.  Page-locked caller buffers are the copy targets themselves, pageable ones go
+ * through pinned staging owned by the batch (one extra host memcpy each).  This is the call a reference-side VecEnv
+ * adapter holding numpy arrays makes. */
 int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, double* h_achieved_goal,
                       double* h_desired_goal, void* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
                       uint8_t* h_success, double* h_final_obs /* or NULL */, void* stream);

@@ -2653,25 +2653,32 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
     CK(cudaMallocHost(&b->h_reward, N * sizeof(double)));
     CK(cudaMallocHost(&b->h_flags, N * 3));
   }
-  memcpy(b->h_actions, h_actions, N * ad * sizeof(float));
-  CK(cudaMemcpyAsync(b->d_actions, b->h_actions, N * ad * sizeof(float), cudaMemcpyHostToDevice, st));
+  // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used directly;
+  // pageable ones go through the batch's pinned staging buffers and cost one extra host memcpy each way.
+  auto pinned = [](const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const float* src_actions = h_actions;
+  if (!pinned(h_actions)) { memcpy(b->h_actions, h_actions, N * ad * sizeof(float)); src_actions = b->h_actions; }
+  CK(cudaMemcpyAsync(b->d_actions, src_actions, N * ad * sizeof(float), cudaMemcpyHostToDevice, st));
   if (mcb_step(b, b->d_actions, b->d_obs, b->d_ag, b->d_dg, b->d_reward, b->d_flags, b->d_flags + N, b->d_flags + 2 * N,
                h_final_obs ? b->d_fobs : nullptr, stream)) return -1;
-  if (h_final_obs) CK(cudaMemcpyAsync(b->h_fobs, b->d_fobs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->h_obs, b->d_obs, N * od * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->h_ag, b->d_ag, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->h_dg, b->d_dg, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->h_reward, b->d_reward, N * rbytes, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->h_flags, b->d_flags, N * 3, cudaMemcpyDeviceToHost, st));
+  struct Out { void* user; void* stage; const void* dev; size_t bytes; bool direct; };
+  Out outs[8] = {
+      {h_final_obs, b->h_fobs, b->d_fobs, N * od * sizeof(double), false}, {h_obs, b->h_obs, b->d_obs, N * od * sizeof(double), false},
+      {h_ag, b->h_ag, b->d_ag, N * 3 * sizeof(double), false},            {h_dg, b->h_dg, b->d_dg, N * 3 * sizeof(double), false},
+      {h_reward, b->h_reward, b->d_reward, N * rbytes, false},             {h_term, b->h_flags, b->d_flags, N, false},
+      {h_trunc, b->h_flags + N, b->d_flags + N, N, false},                 {h_succ, b->h_flags + 2 * N, b->d_flags + 2 * N, N, false}};
+  for (Out& o : outs) {
+    if (!o.user) continue;
+    o.direct = pinned(o.user);
+    CK(cudaMemcpyAsync(o.direct ? o.user : o.stage, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
-  if (h_obs) memcpy(h_obs, b->h_obs, N * od * sizeof(double));
-  if (h_final_obs) memcpy(h_final_obs, b->h_fobs, N * od * sizeof(double));
-  if (h_ag) memcpy(h_ag, b->h_ag, N * 3 * sizeof(double));
-  if (h_dg) memcpy(h_dg, b->h_dg, N * 3 * sizeof(double));
-  if (h_reward) memcpy(h_reward, b->h_reward, N * rbytes);
-  if (h_term) memcpy(h_term, b->h_flags, N);
-  if (h_trunc) memcpy(h_trunc, b->h_flags + N, N);
-  if (h_succ) memcpy(h_succ, b->h_flags + 2 * N, N);
+  for (Out& o : outs) if (o.user && !o.direct) memcpy(o.user, o.stage, o.bytes);
   return 0;
 }
 

@@ -388,11 +388,14 @@ class MyCobotVectorEnv:
         assert a.shape == (self.num_envs, self.action_dim)
         N = self.num_envs
         if out is None:
-            out = dict(observation=np.empty((N, self.obs_dim)), achieved_goal=np.empty((N, 3)), desired_goal=np.empty((N, 3)),
-                       reward=np.empty(N, dtype=np.float32 if self.reward_type == "sparse" else np.float64),
-                       terminated=np.empty(N, dtype=np.uint8), truncated=np.empty(N, dtype=np.uint8), is_success=np.empty(N, dtype=np.uint8))
+            # page-locked result buffers (numpy views of pinned torch tensors): the library copies into them directly
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+            out = dict(observation=pin((N, self.obs_dim), torch.float64), achieved_goal=pin((N, 3), torch.float64),
+                       desired_goal=pin((N, 3), torch.float64),
+                       reward=pin((N,), torch.float32 if self.reward_type == "sparse" else torch.float64),
+                       terminated=pin((N,), torch.uint8), truncated=pin((N,), torch.uint8), is_success=pin((N,), torch.uint8))
             if want_final_obs:
-                out["final_observation"] = np.empty((N, self.obs_dim))
+                out["final_observation"] = pin((N, self.obs_dim), torch.float64)
         p = lambda x: x.ctypes.data_as(C.c_void_p)
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_step_host(self._batch, p(a), p(out["observation"]), p(out["achieved_goal"]), p(out["desired_goal"]),

@@ -324,12 +324,19 @@ def test_host_buffer_entry_point_equals_device_entry_point():
     a = np.random.default_rng(3).uniform(-1, 1, (n, 7)).astype(np.float32)
     e1 = _env(num_envs=n, has_object=True, reward_type="sparse", seed=5)
     e2 = _env(num_envs=n, has_object=True, reward_type="sparse", seed=5)
-    e1.reset(); e2.reset()
+    e3 = _env(num_envs=n, has_object=True, reward_type="sparse", seed=5)
+    e1.reset(); e2.reset(); e3.reset()
+    pageable = dict(observation=np.empty((n, 25)), achieved_goal=np.empty((n, 3)), desired_goal=np.empty((n, 3)), reward=np.empty(n, np.float32),
+                    terminated=np.empty(n, np.uint8), truncated=np.empty(n, np.uint8), is_success=np.empty(n, np.uint8))
     for _ in range(3):
         o1, r1, t1, tr1, i1 = e1.step(torch.as_tensor(a))
-        out = e2.step_host(a)
+        out = e2.step_host(a)                              # page-locked result buffers: direct copies
+        out3 = e3.step_host(a, pageable)                   # pageable buffers: through the batch's pinned staging
     assert np.array_equal(o1["observation"].cpu().numpy(), out["observation"])
     assert np.array_equal(r1.cpu().numpy(), out["reward"]) and np.array_equal(t1.cpu().numpy(), out["terminated"].astype(bool))
+    for k in pageable:
+        assert np.array_equal(out[k], out3[k]), k
+    e3.close()
     assert e1.last_step_launches == 3          # one kernel per layout tier
     e1.close(); e2.close()
 
