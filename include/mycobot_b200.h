@@ -238,7 +238,6 @@ int32_t mcb_last_fallback_envs(mcb_batch* b, int32_t* last_tier_envs, void* stre
 /* measurement helpers used by bench.py */
 int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */
 int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out); /* DFMA micro-kernel, CUDA-event timed */
-int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, float* ms_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Device-resident HER replay ("future" strategy) -- replaces stable_baselines3.HerReplayBuffer as

@@ -2711,10 +2711,6 @@ int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out) {
   return 0;
 }
 
-int32_t mcb_time_step_kernel(mcb_batch* b, const float* actions, int32_t reps, float* ms_out, void* stream) {
-  (void)b; (void)actions; (void)reps; (void)ms_out; (void)stream;
-  return fail("mcb_time_step_kernel: not implemented; time mcb_step with CUDA events on the caller's stream");
-}
 
 }  // extern "C"
 
