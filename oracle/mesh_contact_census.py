@@ -10,6 +10,8 @@ U[-1,1]^7 joint targets, 50-step episodes).  Checks per state:
     not in <contact><exclude>).
 Result recorded in DESIGN.md: 0 / 2000 states with a mesh-vs-table/floor/cube contact, 0 / 80 states with a
 mesh-vs-mesh contact (base_link.STL is absent from the reference checkout; it is static and sits on the table).
+With the IK controller (`python oracle/mesh_contact_census.py IK`, random 7-d actions): 0 / 300 states -- the finger-layer
+boxes reach the table first.
 """
 import itertools
 import random
@@ -21,7 +23,7 @@ import numpy as np
 A = "/root/reference/mycobotgym/envs/assets/"
 
 
-def main(episodes=40, mesh_mesh_every=5):
+def main(episodes=40, mesh_mesh_every=5, controller="joint"):
     from scipy.optimize import linprog
     from scipy.spatial import ConvexHull
 
@@ -67,7 +69,7 @@ def main(episodes=40, mesh_mesh_every=5):
         r = linprog(np.zeros(4), A_ub=Aub, b_ub=-np.ones(len(P) + len(Q)), bounds=[(None, None)] * 4, method="highs")
         return r.status != 0
 
-    env = OracleEnv(flat, has_object=True, reward_type="sparse")
+    env = OracleEnv(flat, has_object=True, reward_type="sparse", controller_type=controller)
     rng = np.random.default_rng(0)
     random.seed(0)
     cube_b = names.index("object0")
@@ -90,8 +92,11 @@ def main(episodes=40, mesh_mesh_every=5):
                 mm = any(np.linalg.norm(C[a][0] - C[b][0]) <= C[a][1] + C[b][1] and intersect(W[a], W[b]) for a, b in pairs)
                 n_mm_states += 1
                 n_mm += mm
-    print(f"mesh vs table/floor/cube: {n_prim} / {n_states} states;  mesh vs mesh ({len(pairs)} pairs): {n_mm} / {n_mm_states} states")
+    print(f"[{controller}] mesh vs table/floor/cube: {n_prim} / {n_states} states;  mesh vs mesh ({len(pairs)} pairs): {n_mm} / {n_mm_states} states")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "IK":
+        main(episodes=6, controller="IK")
+    else:
+        main()
