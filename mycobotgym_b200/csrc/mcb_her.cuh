@@ -5,7 +5,7 @@
 // the relabelling gather live in HBM so a rollout of 16 K envs never leaves the device.  Included by mcb_engine.cu.
 //
 // Layout: time-major rings [T][N][.] -- one add() writes N contiguous rows per array (coalesced D2D copies), a sample
-// gathers single rows (obs_dim doubles = 80..200 B, one warp per sample, lanes across the row).  HBM-bound:
+// gathers single rows (obs_dim doubles = 80..200 B; one lane draws one sample, the warp copies its 32 rows).  HBM-bound:
 // (2*obs_dim + 9) doubles + action floats read and written per sample.
 
 struct mcb_her {
@@ -79,12 +79,16 @@ struct HerSampleArgs {
   int* o_fail;
 };
 
-__global__ void __launch_bounds__(256) her_sample_kernel(HerSampleArgs a) {
+// One lane draws one sample (index, and for the virtual ones the relabel source), then the warp copies its 32 rows
+// cooperatively, eight rows in flight at a time: the gather is a stream of independent 200-byte reads from random places of
+// the ring, so memory-level parallelism -- not the copy width -- is what the kernel needs.
+__global__ void __launch_bounds__(128) her_sample_kernel(HerSampleArgs a) {
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= a.batch) return;
+  const int b = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+  const int b0 = b - lane;
+  if (b0 >= a.batch) return;
   int t = 0, env = 0, src = -1;
-  if (lane == 0) {
+  if (b < a.batch) {
     unsigned long long ctr = a.draw0 * 4096ull;
     bool ok = true;
     if (a.inj_index) { t = (int)(a.inj_index[b] / a.N); env = (int)(a.inj_index[b] % a.N); ok = a.ep_length[(size_t)t * a.N + env] > 0; }
@@ -107,30 +111,48 @@ __global__ void __launch_bounds__(256) her_sample_kernel(HerSampleArgs a) {
       else fut = min(el - 1, cur + (int)(philox_uniform(a.seed, (uint32_t)b, ctr) * (el - cur)));      // np.random.randint(cur, el)
       src = (fut + es) % a.T;
     }
+    const size_t row = (size_t)t * a.N + env;
+    // per-sample scalars: goal, reward, done (this lane's own sample)
+    double nag[3], g[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      nag[k] = a.next_ag[row * 3 + k];
+      g[k] = src >= 0 ? a.next_ag[((size_t)src * a.N + env) * 3 + k] : a.dg[row * 3 + k];
+      a.o_ag[(size_t)b * 3 + k] = a.ag[row * 3 + k];
+      a.o_next_ag[(size_t)b * 3 + k] = nag[k];
+      a.o_dg[(size_t)b * 3 + k] = g[k];
+    }
+    float r;
+    if (src >= 0) {
+      // compute_reward(next_achieved_goal, new_goal) (mycobot.py:289-295), stored as float32 like SB3's reward array
+      const double dx = nag[0] - g[0], dy = nag[1] - g[1], dz = nag[2] - g[2];
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      r = a.reward_type == 0 ? -(float)(d > a.thr) : (float)(-d);
+    } else r = a.rewards[row];
+    a.o_rewards[b] = r;
+    a.o_dones[b] = (float)(a.dones[row] * (1 - a.timeouts[row]));
+    if (a.o_index) { a.o_index[2 * (size_t)b] = (int64_t)row; a.o_index[2 * (size_t)b + 1] = src >= 0 ? (int64_t)src * a.N + env : -1; }
   }
-  t = __shfl_sync(FULLMASK, t, 0); env = __shfl_sync(FULLMASK, env, 0); src = __shfl_sync(FULLMASK, src, 0);
-  const size_t row = (size_t)t * a.N + env;
-  for (int k = lane; k < a.od; k += 32) {
-    a.o_obs[(size_t)b * a.od + k] = a.obs[row * a.od + k];
-    a.o_next_obs[(size_t)b * a.od + k] = a.next_obs[row * a.od + k];
-  }
-  for (int k = lane; k < a.ad; k += 32) a.o_actions[(size_t)b * a.ad + k] = a.actions[row * a.ad + k];
-  if (lane < 3) {
-    double nag = a.next_ag[row * 3 + lane];
-    double g = src >= 0 ? a.next_ag[((size_t)src * a.N + env) * 3 + lane] : a.dg[row * 3 + lane];
-    a.o_ag[(size_t)b * 3 + lane] = a.ag[row * 3 + lane];
-    a.o_next_ag[(size_t)b * 3 + lane] = nag;
-    a.o_dg[(size_t)b * 3 + lane] = g;
-    // compute_reward(next_achieved_goal, new_goal) (mycobot.py:289-295), stored as float32 like SB3's reward array
-    double dlt = nag - g, d2 = dlt * dlt;
-    double dx = __shfl_sync(0x7u, d2, 0), dy = __shfl_sync(0x7u, d2, 1), dz = __shfl_sync(0x7u, d2, 2);
-    if (lane == 0) {
-      float r;
-      if (src >= 0) { double d = sqrt(dx + dy + dz); r = a.reward_type == 0 ? -(float)(d > a.thr) : (float)(-d); }
-      else r = a.rewards[row];
-      a.o_rewards[b] = r;
-      a.o_dones[b] = (float)(a.dones[row] * (1 - a.timeouts[row]));
-      if (a.o_index) { a.o_index[2 * (size_t)b] = (int64_t)row; a.o_index[2 * (size_t)b + 1] = src >= 0 ? (int64_t)src * a.N + env : -1; }
+  // cooperative row copies: observation, next observation, action of samples b0 .. b0 + 31
+  const long long myrow = (b < a.batch) ? (long long)t * a.N + env : -1;
+#pragma unroll 1
+  for (int k0 = 0; k0 < 32; k0 += 8) {
+    long long rows[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) rows[u] = __shfl_sync(FULLMASK, myrow, k0 + u);
+    for (int c = lane; c < a.od; c += 32) {
+      double vo[8], vn[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (rows[u] >= 0) { vo[u] = a.obs[(size_t)rows[u] * a.od + c]; vn[u] = a.next_obs[(size_t)rows[u] * a.od + c]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (rows[u] >= 0) { a.o_obs[(size_t)(b0 + k0 + u) * a.od + c] = vo[u]; a.o_next_obs[(size_t)(b0 + k0 + u) * a.od + c] = vn[u]; }
+    }
+    if (lane < a.ad) {
+      float va[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (rows[u] >= 0) va[u] = a.actions[(size_t)rows[u] * a.ad + lane];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (rows[u] >= 0) a.o_actions[(size_t)(b0 + k0 + u) * a.ad + lane] = va[u];
     }
   }
 }
@@ -230,7 +252,7 @@ int32_t mcb_her_sample(mcb_her* h, int32_t batch_size, const int64_t* inj_index,
   a.o_obs = obs; a.o_ag = achieved_goal; a.o_dg = desired_goal; a.o_next_obs = next_obs; a.o_next_ag = next_achieved_goal;
   a.o_actions = actions; a.o_rewards = rewards; a.o_dones = dones; a.o_index = index_out; a.o_fail = fail_count;
   CK(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-  her_sample_kernel<<<(batch_size + 7) / 8, 256, 0, st>>>(a);
+  her_sample_kernel<<<(batch_size + 127) / 128, 128, 0, st>>>(a);
   CK(cudaGetLastError());
   return 0;
 }

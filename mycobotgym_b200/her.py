@@ -92,14 +92,21 @@ class DeviceHerReplayBuffer:
             nag = torch.where(done[:, None], fag, nag)
         self.add(prev_obs, {"observation": nobs, "achieved_goal": nag}, actions, rew, term, trunc)
 
-    def sample(self, batch_size, *, indices=None, future=None, return_indices=False):
+    def alloc_batch(self, batch_size):
+        """Output tensors of one `sample()`; pass them back as `out=` to reuse them (no allocation per gradient step)."""
+        B, dev, f64 = int(batch_size), self.device, torch.float64
+        return dict(obs=torch.empty(B, self.obs_dim, dtype=f64, device=dev), ag=torch.empty(B, 3, dtype=f64, device=dev),
+                    dg=torch.empty(B, 3, dtype=f64, device=dev), nobs=torch.empty(B, self.obs_dim, dtype=f64, device=dev),
+                    nag=torch.empty(B, 3, dtype=f64, device=dev), act=torch.empty(B, self.action_dim, dtype=torch.float32, device=dev),
+                    rew=torch.empty(B, dtype=torch.float32, device=dev), done=torch.empty(B, dtype=torch.float32, device=dev))
+
+    def sample(self, batch_size, *, indices=None, future=None, return_indices=False, out=None):
         """HerReplayBuffer.sample: dict observations / next_observations, actions, rewards [B,1] float32, dones [B,1].
         `indices` (flat step * n_envs + env) and `future` (index inside the episode) inject the random draws."""
-        B, dev, f64 = int(batch_size), self.device, torch.float64
-        out = dict(obs=torch.empty(B, self.obs_dim, dtype=f64, device=dev), ag=torch.empty(B, 3, dtype=f64, device=dev),
-                   dg=torch.empty(B, 3, dtype=f64, device=dev), nobs=torch.empty(B, self.obs_dim, dtype=f64, device=dev),
-                   nag=torch.empty(B, 3, dtype=f64, device=dev), act=torch.empty(B, self.action_dim, dtype=torch.float32, device=dev),
-                   rew=torch.empty(B, dtype=torch.float32, device=dev), done=torch.empty(B, dtype=torch.float32, device=dev))
+        B, dev = int(batch_size), self.device
+        if out is None:
+            out = self.alloc_batch(B)
+        assert out["obs"].shape[0] == B
         idx_out = torch.empty(B, 2, dtype=torch.int64, device=dev) if return_indices else None
         ii = None if indices is None else torch.as_tensor(np.asarray(indices), dtype=torch.int64).to(dev).contiguous()
         ff = None if future is None else torch.as_tensor(np.asarray(future), dtype=torch.int32).to(dev).contiguous()
