@@ -2,31 +2,39 @@
 //
 // One environment per warp; the whole env-step (frame_skip substeps of the MuJoCo-equivalent forward
 // dynamics + semi-implicit Euler, then observation / reward / success / auto-reset) is one kernel launch.
-// An env's working set lives in the warp's slice of shared memory; HBM sees one 576-byte state record read
+// An env's working set lives in the warp's slice of shared memory; HBM sees one 640-byte state record read
 // and written per env-step plus the action and the outputs.  All arithmetic is fp64 on the CUDA cores
 // (DFMA); tensor cores are deliberately unused: the per-env matrices are 18x18 and smaller and the work is a
 // sequence of tree recursions and tiny factorizations, not a dense contraction.
 //
-// Layout decisions that set the speed (profiles/r01_*):
+// Decisions that set the speed (profiles/README.md has the measurement behind each):
 //   * the kernel is latency-bound, so resident envs per SM is the first lever: shared memory per env is
-//     ~14 KB (16 envs/SM) in the common case.  Dead dynamics temporaries and the constraint rows share one
-//     union; matrices are packed lower triangles; the constraint Jacobian is stored BLOCKED by row type
-//     (robot rows: 12 columns, cube rows: 6, coupled rows: 18, joint-limit rows: none);
-//   * capacity is two-tier: the launch uses the small layout (48 rows); an env that needs more (a grasp)
-//     aborts untouched, is queued on a device list and is redone by a second launch with the big layout;
+//     ~13.7 KB (16 envs/SM, pinned from the other side by 128 registers per thread) in the common case.  Dead
+//     dynamics temporaries and the constraint rows share one union; matrices are packed lower triangles; the
+//     constraint Jacobian is stored BLOCKED by row type (robot rows: 12 columns, cube rows: 6, coupled rows: 18,
+//     joint-limit rows: none);
+//   * capacity comes in three tiers (EnvS<TIER>): 48 rows for the common case, 88 rows / 10 envs per CTA for
+//     contact-rich envs (a grasp), 128 rows / one env per CTA as the last resort.  An env that does not fit its tier
+//     aborts untouched, is queued on a device list and is redone by the next tier's launch;
 //   * the block structure robot(12) + cube(6) is used everywhere: M's cube block never couples, H couples
-//     only through finger-cube contact rows, so the usual factorizations are 12x12 and 6x6, fully unrolled.
+//     only through finger-cube contact rows, so the usual factorizations are 12x12 and 6x6, fully unrolled, as
+//     L D L' with rows in registers and a branch-free reciprocal (chol_solve_blk);
+//   * the kinematic tree is compiled in (kTreeParent): fk and the RNE / CRB passes are register chain walks;
+//   * only a quarter of the executed instructions are FP64 math, so instruction count and code footprint matter as
+//     much as the math: no division slow paths, explicit 32-bit shuffles, out-of-line helpers on the hot path;
+//   * warps of a CTA run free or in lockstep groups (named barriers), chosen per batch by mcb_autotune().
 //
 // Stage map (what each device function restates; the reference reaches all of it through
 // mujoco.mj_step, mycobotgym/envs/mycobot.py:193 -> gymnasium MujocoEnv.do_simulation):
 //   fk()              mj_kinematics              cinert_cdof()  mj_comPos
-//   crb_mass()        mj_crb                     chol_blk()     mj_factorM (dense LL' per block, not sparse L'DL)
+//   crb_mass()        mj_crb                     chol_solve_blk() mj_factorM / mj_solveM (dense L D L' per block)
 //   velocity_rne()    mj_comVel, mj_rne          actuation_smooth() mj_passive, mj_fwdActuation
 //   collide()         mj_collision (plane-box, box-box)
 //   make_rows()       mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint
 //   Newton            mj_solNewton (pyramidal cones, exact line search)
 //   euler()           mj_Euler + mj_integratePos
 //   write_obs() etc.  MyCobotEnv._get_obs / compute_reward / _is_success / reset_model (mycobot.py:207-298,342-400)
+//   ik_target() / ik_update_ctrl()  IKController (utils.py:469-556); mocap branch of the step: mycobot.py:172-189
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -119,8 +127,7 @@ struct StepArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-env shared-memory working set.  BIG = false: the common case; BIG = true: the fallback for envs whose
-// contact set does not fit (grasps, pile-ups).
+// per-env shared-memory working set, one layout per capacity tier (see the table in DESIGN.md section 3).
 // TIER 0: the common case (16 envs per CTA); TIER 1: contact-rich envs -- a grasp, pushing, the gripper resting on the
 // table (10 envs per CTA); TIER 2: the last resort, one env per CTA, rows beyond its capacity are dropped and counted.
 template <int TIER>
@@ -1014,7 +1021,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     int nR = ne0 + nRc;
     bool fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
     if (!fits) {
-      // drop contacts from the end until it fits (the small layout aborts the env instead, see the kernel)
+      // drop contacts from the end until it fits (tiers 0 and 1 abort the env instead, see the kernel)
       s.overflow += 1;
       while (nc > 0 && !fits) {
         nc--;
@@ -1960,9 +1967,9 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The env kernel: one warp per env.  BIG = false is the first launch over all envs, WPB warps per CTA running the
-// substep loop in lockstep; envs whose constraint set overflows the small layout leave every output untouched and
-// enqueue themselves on redo_list, which the BIG = true launch (one warp per CTA, grid-stride over the list) serves.
+// The env kernel: one warp per env.  TIER 0 is the first launch over all envs, WPB_SMALL warps per CTA; envs whose
+// constraint set overflows a tier's layout leave every output untouched and enqueue themselves on that tier's redo list,
+// which the next tier's launch serves (grid-stride over the list; tier 1: WPB_MID warps per CTA, tier 2: one).
 #define WPB_SMALL WPB_SMALL_
 #ifndef ENV_LB_THREADS
 #define ENV_LB_THREADS (32 * WPB_SMALL)      // register budget of the common-layout kernel = 65536 / ENV_LB_THREADS (tuning knob)
