@@ -35,6 +35,24 @@ def test_fk_known_answers(flat):
     np.testing.assert_allclose(eef, [-0.05154491, 0.01053502, 0.3448586], atol=5e-9)
     q = fk[1][flat.body_names.index("gripper_tcp")]
     np.testing.assert_allclose(q, [0.01762876, -0.70526013, 0.0078235, 0.70868623], atol=5e-8)
+    # reference known answer: at the keyframe the tool orientation is the fetch IK target [0, -0.707, 0, 0.707]
+    # (mycobot.py:140) to two digits
+    np.testing.assert_allclose(q, [0.0, -0.707, 0.0, 0.707], atol=0.02)
+
+
+def test_mocap_keyframe_orientation_known_answer():
+    # mycobot280_mocap.xml:8: the keyframe's mocap quaternion (0.50235287 -0.499 -0.5 0.49764296), composed with the weld's
+    # relative pose, is the orientation of gripper_tcp at that keyframe's qpos -- an independent check of the FK rotations,
+    # the weld relpose computed by the set_const restatement and the quaternion conventions
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP)
+    fk = mjcf.fk_numpy(fm, fm.key_qpos[0])
+    tcp = fm.body_names.index("gripper_tcp")
+    want = mjcf.quat_mul(fm.key_mquat[0], fm.eq_data[0, 6:10])
+    got = fk[1][tcp]
+    if np.dot(want, got) < 0:
+        want = -want
+    np.testing.assert_allclose(got, want, atol=5e-3)
+    np.testing.assert_allclose(fk[0][tcp], fm.key_mpos[0], atol=2e-3)        # and the mocap body sits on the tool (weld at rest)
 
 
 def test_classes_and_defaults(flat):
