@@ -306,8 +306,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                          # dram__bytes_read.sum + dram__bytes_write.sum of mcb_env_kernel<0> for this workload at 16384 envs, from
-                         # the ncu --set full capture summarised in profiles/r01o_ncu_summary.txt (15.47 MB + 48.80 MB)
-                         "traffic": 64.27e6 if (args.workload == "pick" and n == 16384) else None, "traffic_unit": "B/launch",
+                         # the ncu --set full capture summarised in profiles/r01za_ncu_summary.txt (12.29 MB read + 26.33 MB written)
+                         "traffic": 38.62e6 if (args.workload == "pick" and n == 16384) else None, "traffic_unit": "B/launch",
                          "note": "dominant kernel = mcb_env_kernel (the whole step); algorithmic FLOP/env-step from DESIGN.md; "
                                  "peak = DFMA micro-kernel measured in this run (FP64 peak is not in MEASURED_PEAKS.json)",
                          "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
