@@ -39,3 +39,24 @@ for name, fn in (("step (device buffers)", lambda t: env.step(acts[t])), ("step 
         fn(t)
     torch.cuda.synchronize()
     print(f"{wl} {name}: {(time.perf_counter() - t0) / 20 * 1e3:.2f} ms/step wall")
+
+# host-side cost of one step() call (returns before the GPU finishes unless something inside blocks)
+torch.cuda.synchronize()
+ts = []
+for t in range(10):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    env.step(acts[t])
+    ts.append((time.perf_counter() - t0) * 1e3)
+print(f"{wl} host time inside step(): " + " ".join(f"{x:.2f}" for x in ts) + " ms")
+
+# GPU time per step (events) when the host synchronises after every step
+evs = []
+for t in range(10):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    env.step(acts[t])
+    e1.record()
+    torch.cuda.current_stream().synchronize()
+    evs.append(e0.elapsed_time(e1))
+print(f"{wl} GPU event time per synced step: " + " ".join(f"{x:.2f}" for x in evs) + " ms")
