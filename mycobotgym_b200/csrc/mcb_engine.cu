@@ -2006,8 +2006,11 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
   }
   const int lockstep = (TIER == 0 && a.lockstep_warps > 1) ? a.lockstep_warps : 0;
 
-  for (int item0 = blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
-    const int item = item0 + wid;
+  // Tier 0: CTA b takes the 16 consecutive envs [16 b, 16 b + 16).  Tier 1: the list is dealt round-robin over the CTAs
+  // (item = slot * gridDim.x + b), so a list shorter than one full wave spreads over all SMs with few warps each instead of
+  // filling half of them -- the latency of a pass is set by how many heavy envs share an SM.
+  for (int item0 = TIER == 1 ? 0 : blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
+    const int item = TIER == 1 ? item0 + wid * (int)gridDim.x + (int)blockIdx.x : item0 + wid;
     bool valid = item < nwork;
     const int env = valid ? (TIER == 0 ? item : work_list[item]) : 0;
     if (valid && a.mode == MODE_RESET && a.mask && !a.mask[env]) valid = false;
@@ -2323,7 +2326,7 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
   a.redo_count = b->redo_count; a.redo_list = b->redo_list;
   a.lockstep_warps = b->lockstep_warps;
-  a.mid_threshold = b->mid_only ? -1 : b->big_grid;
+  a.mid_threshold = b->mid_only ? -1 : 2 * b->big_grid;    // up to two waves of the last tier are cheaper than a middle-tier pass (profiles/README.md)
   CK(cudaMemsetAsync(b->redo_count, 0, 2 * sizeof(int), st));
   if (b->big_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list + b->n_envs, b->redo_count + 1, b->n_envs);
   else if (b->mid_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
