@@ -222,7 +222,7 @@ int32_t mcb_stats(mcb_batch* b, double* out, int32_t reset_after, void* stream);
  * (dist, pos3, normal3) * ncon.  cap must be >= 3170.  Returns the number of doubles written. */
 int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out, int32_t cap, void* stream);
 
-/* Picks the lockstep grouping of the step kernel for this batch (cfg.lockstep_warps == 0): rolls the batch 12 steps
+/* Picks the lockstep grouping of the step kernel for this batch (cfg.lockstep_warps == 0): rolls the batch 32 steps
  * ahead (the state right after a reset is not representative), times `steps_per_candidate` (0 -> 4) steps per candidate
  * from that state, keeps the fastest and restores state, episode clocks, RNG streams and statistics exactly.  `actions`
  * (device float32 [N, action_dim]) are applied at every tuning step; NULL -> uniform random actions from a private

@@ -2550,7 +2550,7 @@ int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candi
     double* tn_state = nullptr; double* tn_ret = nullptr; int* tn_el = nullptr; unsigned long long* tn_ctr = nullptr;
     TCK(cudaMalloc(&tn_state, N * MCB_STATE_STRIDE * sizeof(double))); TCK(cudaMalloc(&tn_ret, N * sizeof(double)));
     TCK(cudaMalloc(&tn_el, N * sizeof(int))); TCK(cudaMalloc(&tn_ctr, N * sizeof(unsigned long long)));
-    for (int k = 0; k < 12 && okay; k++) one_step(k);
+    for (int k = 0; k < 32 && okay; k++) one_step(k);
     TCK(cudaMemcpyAsync(tn_state, b->state, N * MCB_STATE_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
     TCK(cudaMemcpyAsync(tn_ret, b->ep_return, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
     TCK(cudaMemcpyAsync(tn_el, b->elapsed, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
