@@ -190,6 +190,18 @@ __device__ __noinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
   return v;
 }
+// three warp sums in one butterfly: after two rounds every lane carries one of the (up to four) quantities, so the
+// remaining three rounds move one value instead of three -- 9 double shuffles (incl. the broadcasts) instead of 15
+__device__ __noinline__ void warp_sum3(double& a, double& b, double& c, int lane) {
+  const bool odd = lane & 1, hi = lane & 2;
+  const double r1 = shfl_xor_d(odd ? a : b, 1);      // even lanes collect a and c, odd lanes collect b
+  const double r2 = shfl_xor_d(c, 1);
+  const double x = (odd ? b : a) + r1, y = odd ? 0.0 : c + r2;
+  const double r3 = shfl_xor_d(hi ? x : y, 2);       // lanes 4k: a, 4k+1: b, 4k+2: c (4k+3 carries nothing)
+  double z = (hi ? y : x) + r3;
+  z += shfl_xor_d(z, 4); z += shfl_xor_d(z, 8); z += shfl_xor_d(z, 16);
+  a = shfl_d(z, 0); b = shfl_d(z, 1); c = shfl_d(z, 2);
+}
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ void cross3(double* r, const double* a, const double* b) {
   r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
@@ -1453,7 +1465,8 @@ struct Newton {
       int r = lane + 32 * t;
       if (r < nefc && active(r, s.eJaref[r] + a * s.eJv[r])) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
     }
-    q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
+    warp_sum3(q0, q1, q2, lane);
+    q0 += qg0; q1 += qg1; q2 += qg2;
     p.cost = a * a * q2 + a * q1 + q0;
     p.d0 = 2 * a * q2 + q1;
     p.d1 = 2 * q2;
