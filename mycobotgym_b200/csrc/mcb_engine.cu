@@ -1321,11 +1321,6 @@ struct Newton {
       out[r] = sub_aref ? d - s.earef[r] : d;
     }
   }
-  __device__ double cost_rows(const double* jar) const {
-    double c = 0;
-    for (int r = lane; r < nefc; r += 32) { double j = jar[r]; if (active(r, j)) c += 0.5 * s.eD[r] * j * j; }
-    return warp_sum(c);
-  }
   // cost and gradient at the current point (Jaref, Ma valid); eJv is used as the efc_force scratch
   __device__ void update_cost_grad() {
     double c = 0;
@@ -1536,17 +1531,21 @@ struct Newton {
     const double scale = 1.0 / (MDL.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
+    double cw = 0, cs = 0;      // constraint cost of the two candidates, accumulated while their residuals are formed
     for (int r = lane; r < nefc; r += 32) {
       double dw, ds;
       row_dot2(s, r, s.warm, s.qacc_smooth, dw, ds);
-      const double ar = s.earef[r];
-      s.eJaref[r] = dw - ar; s.eJv[r] = ds - ar;
+      const double ar = s.earef[r], D = s.eD[r];
+      dw -= ar; ds -= ar;
+      s.eJaref[r] = dw; s.eJv[r] = ds;
+      if (active(r, dw)) cw += 0.5 * D * dw * dw;
+      if (active(r, ds)) cs += 0.5 * D * ds * ds;
     }
     double ma = mulM_row(s, lane, nva, s.warm), g = 0;
     if (lane < nva) g = 0.5 * (ma - s.qfrc_smooth[lane]) * (s.warm[lane] - s.qacc_smooth[lane]);
     __syncwarp();
-    double cw = cost_rows(s.eJaref) + warp_sum(g);
-    double cs = cost_rows(s.eJv);
+    warp_sum3(cw, cs, g, lane);
+    cw += g;
     bool use_smooth = cw > cs;
     if (use_smooth) {
       for (int r = lane; r < nefc; r += 32) s.eJaref[r] = s.eJv[r];
