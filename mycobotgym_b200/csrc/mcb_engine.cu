@@ -1468,17 +1468,21 @@ struct Newton {
     if (p.d1 <= 0) p.d1 = MINVAL;
   }
   __device__ double line_search(double scale) {
-    double sn = 0;
-    if (lane < nva) sn = s.search[lane] * s.search[lane];
-    double snorm = sqrt(warp_sum(sn));
+    // |search|^2 and the two Gauss-term coefficients in one butterfly (M * search is needed for the latter, so it is formed
+    // before the zero-norm early-out instead of after it)
+    double mv = mulM_row(s, lane, nva, s.search);
+    double sn = 0, g1 = 0, g2 = 0;
+    if (lane < nva) {
+      const double sl = s.search[lane];
+      sn = sl * sl; g1 = sl * (s.Ma[lane] - s.qfrc_smooth[lane]); g2 = sl * mv;
+      s.Mv[lane] = mv;
+    }
+    warp_sum3(sn, g1, g2, lane);
+    const double snorm = sqrt(sn);
     if (snorm < MINVAL) return 0;
     double gtol = MDL.d.tolerance * MDL.d.ls_tolerance * snorm / scale;
-    double mv = mulM_row(s, lane, nva, s.search);
-    if (lane < nva) s.Mv[lane] = mv;
     rows_times(s.search, s.eJv, false);
-    double g1 = 0, g2 = 0;
-    if (lane < nva) { g1 = s.search[lane] * (s.Ma[lane] - s.qfrc_smooth[lane]); g2 = s.search[lane] * mv; }
-    qg0 = gauss; qg1 = warp_sum(g1); qg2 = 0.5 * warp_sum(g2);
+    qg0 = gauss; qg1 = g1; qg2 = 0.5 * g2;
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < S::NROW / 32 + 1; t++) {
