@@ -1322,10 +1322,12 @@ struct Newton {
     }
   }
   // cost and gradient at the current point (Jaref, Ma valid); eJv is used as the efc_force scratch
-  __device__ void update_cost_grad() {
+  // (alpha != 0: the residuals are first advanced along the search direction, Jaref += alpha * J search, in the same pass)
+  __device__ void update_cost_grad(double alpha = 0.0) {
     double c = 0;
     for (int r = lane; r < nefc; r += 32) {
       double jar = s.eJaref[r];
+      if (alpha != 0.0) { jar += alpha * s.eJv[r]; s.eJaref[r] = jar; }
       bool act = active(r, jar);
       s.eJv[r] = act ? -s.eD[r] * jar : 0.0;
       if (act) c += 0.5 * s.eD[r] * jar * jar;
@@ -1567,10 +1569,9 @@ struct Newton {
       double alpha = line_search(scale);
       if (alpha == 0) break;
       if (lane < nva) { s.qacc[lane] += alpha * s.search[lane]; s.Ma[lane] += alpha * s.Mv[lane]; }
-      for (int r = lane; r < nefc; r += 32) s.eJaref[r] += alpha * s.eJv[r];
       __syncwarp();
       double oldcost = cost;
-      update_cost_grad();
+      update_cost_grad(alpha);
       iter++;
       double gn = 0;
       if (lane < nva) gn = s.grad[lane] * s.grad[lane];
