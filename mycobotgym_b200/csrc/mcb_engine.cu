@@ -1175,9 +1175,13 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   for (int r = lane; r < nefc; r += 32) {
     int meta = s.rmeta[r], kind = (meta >> 12) & 7, idx = meta & 0xff, sub = (meta >> 9) & 7;
     const double *solref, *solimp;
-    double pos, diag, pyr = 0;
+    double pos, diag, pyr = 0, ipos = -1;     // ipos >= 0: the residual norm the row's impedance is evaluated at (getposdim)
     if (kind == 0) {
-      pos = s.anchors[(2 * idx) * 3 + sub] - s.anchors[(2 * idx + 1) * 3 + sub];
+      const double* a1 = s.anchors + (2 * idx) * 3;
+      const double* a2 = a1 + 3;
+      pos = a1[sub] - a2[sub];
+      const double e0 = a1[0] - a2[0], e1 = a1[1] - a2[1], e2 = a1[2] - a2[2];
+      ipos = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
       solref = MDL.d.con_solref[idx]; solimp = MDL.d.con_solimp[idx]; diag = MDL.d.con_diag[idx];
     } else if (kind == 1) {
       int d1 = MDL.d.jeq_dof1, d2 = MDL.d.jeq_dof2;
@@ -1187,7 +1191,9 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       solref = MDL.d.jeq_solref; solimp = MDL.d.jeq_solimp; diag = MDL.d.jeq_diag;
     } else if (kind == 4) {
       pos = s.ik[sub];
-      solref = MDL.d.weld_solref; solimp = MDL.d.weld_solimp; diag = MDL.d.weld_diag[sub < 3 ? 0 : 1];
+      ipos = sqrt(s.ik[0] * s.ik[0] + s.ik[1] * s.ik[1] + s.ik[2] * s.ik[2] + s.ik[3] * s.ik[3] + s.ik[4] * s.ik[4] + s.ik[5] * s.ik[5]);
+      // all six rows take the translational inverse weight (2.3.2's mj_diagApprox; pinned by the mocap keyframe, see the oracle)
+      solref = MDL.d.weld_solref; solimp = MDL.d.weld_solimp; diag = MDL.d.weld_diag[0];
     } else if (kind == 2) {
       double v = s.qpos[idx];
       pos = (meta & 0x100) ? MDL.d.jnt_range[idx][1] - v : v - MDL.d.jnt_range[idx][0];
@@ -1202,7 +1208,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     }
     double sr0 = solref[0], sr1 = solref[1];
     if (sr0 > 0) sr0 = fmax(sr0, 2 * h);
-    double imp = impedance(solimp, pos);
+    double imp = impedance(solimp, ipos >= 0 ? ipos : pos);
     double R = fmax(MINVAL, (1 - imp) * diag / imp);
     if (pyr > 0) R = 2 * pyr * pyr * R;
     double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));

@@ -704,9 +704,16 @@ void o_make_constraint(const omodel* m, odata* d) {
         mulquat(q3, qa, quat);
         for (int r = 0; r < 3; r++) Jrot[r * nv + c] = 0.5 * q3[1 + r] * torquescale;
       }
+      /* mj_diagApprox: in 2.3.2 connect and weld share one branch (body translation for every row); the
+         `weldcnt > 2` split into translational / rotational inverse weight is a later fix.  The choice is PINNED by the
+         reference's mocap keyframe (mycobot280_mocap.xml:7-9, a recorded equilibrium at a near-singular elbow pose):
+         with `rot` here the arm's residual acceleration at that state is 6.5 rad/s^2 and the weld offset settles at
+         0.42 mm instead of the recorded 1.149 mm; with `tran` (and getposdim's norm below) 0.18 rad/s^2 / 1.147 mm
+         (tests/test_keyframe_equilibria.py). */
+      (void)rot;
       for (int r = 0; r < 3; r++) {
         int row = add_row(d, nv, Jrot + r * nv, cpos[3 + r], 0, EFC_EQUALITY, e);
-        d->efc_diagApprox[row] = rot;
+        d->efc_diagApprox[row] = tran;
       }
     } else if (m->eq_type[e] == EQ_JOINT) {
       int q1 = m->jnt_qposadr[o1], q2 = m->jnt_qposadr[o2];
@@ -782,8 +789,17 @@ void o_make_constraint(const omodel* m, odata* d) {
     else if (d->efc_type[i] == EFC_LIMIT) { solref[0] = m->jnt_solref[2 * id]; solref[1] = m->jnt_solref[2 * id + 1]; solimp = m->jnt_solimp + 5 * id; }
     else { solref[0] = d->contact[id].solref[0]; solref[1] = d->contact[id].solref[1]; solimp = d->contact[id].solimp; }
     if (solref[0] > 0) solref[0] = fmax(solref[0], 2 * m->timestep); /* refsafe */
-    double imp;
-    get_impedance(solimp, d->efc_pos[i], d->efc_margin[i], &imp);
+    double imp, ipos = d->efc_pos[i];
+    /* getposdim(): connect (3 rows) and weld (6 rows) share ONE impedance, evaluated at the norm of the whole residual
+       (that is why torquescale is "notionally in units of length") */
+    if (d->efc_type[i] == EFC_EQUALITY && m->eq_type[id] != EQ_JOINT) {
+      int n = m->eq_type[id] == EQ_WELD ? 6 : 3, i0 = i;
+      while (i0 > 0 && d->efc_type[i0 - 1] == EFC_EQUALITY && d->efc_id[i0 - 1] == id) i0--;
+      double s2 = 0;
+      for (int k = i0; k < i0 + n; k++) s2 += d->efc_pos[k] * d->efc_pos[k];
+      ipos = sqrt(s2);
+    }
+    get_impedance(solimp, ipos, d->efc_margin[i], &imp);
     d->efc_R[i] = fmax(MINVAL, (1 - imp) * d->efc_diagApprox[i] / imp);
     double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
     double K, B;

@@ -118,22 +118,23 @@ def controller_rollout(name, controller, fetch, seed, nsteps=3):
 
         def step_rec(n):
             orig(n - 1)
-            last_pre[key] = e.sim.qpos[:6].copy()
+            last_pre[key] = e.sim.qpos.copy()
             orig(1)
         e.sim.step = step_rec
 
     wrap(env, "a"); wrap(env2, "b")
-    rec = {k: [] for k in ["qpos0", "qvel0", "ctrl0", "warm0", "qprev0", "mocap0", "actions", "qpos", "qvel", "ctrl", "warm", "qprev", "mocap", "obs",
+    rec = {k: [] for k in ["qpos0", "qvel0", "ctrl0", "warm0", "qprev0", "qstale0", "mocap0", "actions", "qpos", "qvel", "ctrl", "warm", "qprev", "mocap", "obs",
                            "reward", "sens"]}
     qprev = env.sim.qpos[:6].copy()                     # frames are fresh after reset
+    qstale = env.sim.qpos.copy()                        # full previous-substep configuration: bit-exact restarts of the oracle
     for t in range(nsteps):
         s = env.sim
         rec["qpos0"].append(s.qpos.copy()); rec["qvel0"].append(s.qvel.copy()); rec["ctrl0"].append(s.ctrl.copy())
-        rec["warm0"].append(s.qacc_warmstart.copy()); rec["qprev0"].append(qprev.copy())
+        rec["warm0"].append(s.qacc_warmstart.copy()); rec["qprev0"].append(qprev.copy()); rec["qstale0"].append(qstale.copy())
         rec["mocap0"].append(np.concatenate((s.mocap_pos, s.mocap_quat)))
         # the perturbed twin starts from the same state with stale frames re-created the same way the tests do it
         for e, scale in ((env2, 1 + 2.2e-16),):
-            q_stale = s.qpos.copy(); q_stale[:6] = qprev
+            q_stale = qstale.copy()
             e.sim.set_state(q_stale, s.qvel, s.ctrl, s.qacc_warmstart)
             e.sim.kinematics()
             e.sim.qpos[:] = s.qpos
@@ -145,7 +146,8 @@ def controller_rollout(name, controller, fetch, seed, nsteps=3):
             a[3:7] = (s.xquat[tcp] + 0.1 * rng.uniform(-1, 1, 4)).astype(np.float32)
         o, r, te, tr, info = env.step(a)
         env2.step(a)
-        qprev = last_pre["a"].copy()
+        qstale = last_pre["a"].copy()
+        qprev = qstale[:6].copy()
         rec["actions"].append(a); rec["qpos"].append(s.qpos.copy()); rec["qvel"].append(s.qvel.copy()); rec["ctrl"].append(s.ctrl.copy())
         rec["warm"].append(s.qacc_warmstart.copy()); rec["qprev"].append(qprev.copy())
         rec["mocap"].append(np.concatenate((s.mocap_pos, s.mocap_quat)))
