@@ -147,7 +147,7 @@ typedef struct mcb_task_cfg {
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
   int32_t control_steps;       /* IK: DLS solves per env-step, each followed by frame_skip substeps (5; mycobot.py:35,162) */
   int32_t lockstep_warps;      /* scheduling only, results do not depend on it: warps per lockstep group of the step kernel
-                                * (1 free-running ... 16 whole CTA); 0 = measured per batch by mcb_autotune() at the first mcb_step */
+                                * (1 free-running ... 16 whole CTA); 0 = free-running until the caller runs mcb_autotune() */
   double distance_threshold;   /* 0.01 */
 } mcb_task_cfg;
 
@@ -175,6 +175,14 @@ int32_t mcb_batch_action_dim(const mcb_batch* b);   /* 7 (joint, IK), 8 (mocap),
  * Injected values are what the reference's seeded sampler produced (bit-exact goals). */
 int32_t mcb_reset(mcb_batch* b, const uint8_t* mask, const double* obj_xy, const double* goals,
                   double* obs, double* achieved_goal, double* desired_goal, void* stream);
+/* Same call with HOST buffers (any pointer may be NULL): the other half of the drop-in surface next to mcb_step_host
+ * (mycobot.py:506-514 returns the first observation).  Synchronises `stream`. */
+int32_t mcb_reset_host(mcb_batch* b, const uint8_t* h_mask, const double* h_obj_xy, const double* h_goals,
+                       double* h_obs, double* h_achieved_goal, double* h_desired_goal, void* stream);
+/* replaces `self._np_random, seed = seeding.np_random(seed)` of MyCobotEnv.reset(seed=) (mycobot.py:509-510) for the
+ * device sampler: the masked envs (all if mask == NULL, a device pointer) get Philox key `seed` and draw counter 0, so
+ * the goals / cube positions drawn by the following resets are a function of (seed, env index) only. */
+int32_t mcb_seed(mcb_batch* b, uint64_t seed, const uint8_t* mask, void* stream);
 
 /* replaces MyCobotEnv.step, joint (mycobot.py:132-133,190-205) and IK (mycobot.py:134-170, utils.py:499-556) controllers
  * incl. TimeLimit truncation.  actions float32[N, action_dim]; reward float32[N] (sparse) or float64[N] (dense); flags uint8[N].
@@ -203,6 +211,11 @@ int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, cons
                       const double* qacc_warmstart, const double* goal, const int32_t* elapsed, const double* qprev,
                       const double* mocap, void* stream);
 
+/* the rest of a checkpoint: per-env Philox key, draw counter and running episode return (device pointers, any may be NULL).
+ * A batch restored with mcb_set_state + mcb_set_rng_state continues the same goal stream and episode statistics. */
+int32_t mcb_get_rng_state(mcb_batch* b, uint64_t* env_seed, uint64_t* draw_counter, double* ep_return, void* stream);
+int32_t mcb_set_rng_state(mcb_batch* b, const uint64_t* env_seed, const uint64_t* draw_counter, const double* ep_return, void* stream);
+
 /* replaces mujoco.mj_forward on every env (mycobot.py:213,229,306); refreshes qacc_warmstart; optional obs out */
 int32_t mcb_forward(mcb_batch* b, double* obs, double* achieved_goal, double* desired_goal, void* stream);
 
@@ -226,17 +239,22 @@ int32_t mcb_debug_forward(mcb_batch* b, int32_t env, int32_t what, double* h_out
  * ahead (the state right after a reset is not representative), times `steps_per_candidate` (0 -> 4) steps per candidate
  * from that state, keeps the fastest and restores state, episode clocks, RNG streams and statistics exactly.  `actions`
  * (device float32 [N, action_dim]) are applied at every tuning step; NULL -> uniform random actions from a private
- * Philox stream.  Synchronises the stream.  mcb_step calls it once by itself (with NULL); call it explicitly before
- * capturing mcb_step in a CUDA graph.  Returns the chosen grouping. */
+ * Philox stream.  Synchronises the stream and allocates scratch: it is never called implicitly -- mcb_step only enqueues
+ * its three kernels on the caller's stream (no hidden sync, CUDA-graph capturable).  Returns the chosen grouping. */
 int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candidate, void* stream);
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b);
 /* how many envs of the most recent step overflowed the common shared-memory layout and were redone by the middle-tier
  * kernel (return value) and how many of those also overflowed the middle tier (*last_tier_envs, may be NULL).
  * Synchronises the stream; diagnostics for bench.py. */
 int32_t mcb_last_fallback_envs(mcb_batch* b, int32_t* last_tier_envs, void* stream);
+/* the env indices behind that count: up to `cap` of the envs of the most recent step that left the common layout are
+ * copied to the HOST array h_envs; returns how many there were.  Synchronises the stream (parity tests compare exactly
+ * these envs with the oracle). */
+int32_t mcb_last_fallback_list(mcb_batch* b, int32_t* h_envs, int32_t cap, void* stream);
 
 /* measurement helpers used by bench.py */
-int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step */
+int32_t mcb_last_step_launches(const mcb_batch* b); /* kernels launched by the most recent mcb_step (counted at the launch sites) */
+int64_t mcb_total_launches(const mcb_batch* b);     /* all kernels this library launched for the batch since mcb_batch_create */
 int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out); /* DFMA micro-kernel, CUDA-event timed */
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ EXPORTS = [
     "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
     "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
     "mcb_autotune", "mcb_batch_lockstep_warps", "mcb_last_fallback_envs", "mcb_her_create", "mcb_her_destroy", "mcb_her_add", "mcb_her_size", "mcb_her_episode_table",
-    "mcb_her_sample",
+    "mcb_her_sample", "mcb_reset_host", "mcb_seed", "mcb_get_rng_state", "mcb_set_rng_state", "mcb_last_fallback_list", "mcb_total_launches",
 ]
 
 
@@ -86,6 +86,13 @@ def load():
     L.mcb_autotune.argtypes = [vp, vp, i32, vp]
     L.mcb_batch_lockstep_warps.argtypes = [vp]
     L.mcb_last_fallback_envs.argtypes = [vp, C.POINTER(i32), vp]
+    L.mcb_reset_host.argtypes = [vp] + [vp] * 7
+    L.mcb_seed.argtypes = [vp, u64, vp, vp]
+    L.mcb_get_rng_state.argtypes = [vp] + [vp] * 4
+    L.mcb_set_rng_state.argtypes = [vp] + [vp] * 4
+    L.mcb_last_fallback_list.argtypes = [vp, vp, i32, vp]
+    L.mcb_total_launches.argtypes = [vp]
+    L.mcb_total_launches.restype = i64
     L.mcb_her_create.argtypes = [i32, i32, i32, i32, i32, i32, dbl, u64, C.POINTER(vp)]
     L.mcb_her_destroy.argtypes = [vp]
     L.mcb_her_destroy.restype = None

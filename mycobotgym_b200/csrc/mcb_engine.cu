@@ -107,7 +107,7 @@ struct StepArgs {
   int lockstep_warps;        // warps per lockstep group of the common-layout kernel (1 = free-running), see group_sync()
   int mid_threshold;         // the middle tier only runs when more envs than this left the common layout (else: straight to the last tier)
   mcb_task_cfg cfg;
-  uint64_t seed;
+  const unsigned long long* env_seed;  // [N] Philox key per env (mcb_seed)
   double* state;             // [N, 72]
   int* elapsed;              // [N]
   double* ep_return;         // [N]
@@ -1931,7 +1931,7 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
       else {
         int guard = 0;
         while (sqrt((oxy[0] - gx0) * (oxy[0] - gx0) + (oxy[1] - gy0) * (oxy[1] - gy0)) < 0.1 && guard++ < 10000) {
-          sample_goal(m, a.cfg, a.seed, env, ctr, g);
+          sample_goal(m, a.cfg, a.env_seed[env], env, ctr, g);
           oxy[0] = g[0]; oxy[1] = g[1];
         }
       }
@@ -1940,8 +1940,8 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
     if (a.inj_goal) { g[0] = a.inj_goal[(size_t)env * 3]; g[1] = a.inj_goal[(size_t)env * 3 + 1]; g[2] = a.inj_goal[(size_t)env * 3 + 2]; }
     else {
       int guard = 0;
-      sample_goal(m, a.cfg, a.seed, env, ctr, g);
-      while (sqrt((g[0] - oxy[0]) * (g[0] - oxy[0]) + (g[1] - oxy[1]) * (g[1] - oxy[1])) < 0.1 && guard++ < 10000) sample_goal(m, a.cfg, a.seed, env, ctr, g);
+      sample_goal(m, a.cfg, a.env_seed[env], env, ctr, g);
+      while (sqrt((g[0] - oxy[0]) * (g[0] - oxy[0]) + (g[1] - oxy[1]) * (g[1] - oxy[1])) < 0.1 && guard++ < 10000) sample_goal(m, a.cfg, a.env_seed[env], env, ctr, g);
     }
     s.goal[0] = g[0]; s.goal[1] = g[1]; s.goal[2] = g[2];
   }
@@ -2247,7 +2247,7 @@ __global__ void reward_kernel(const double* __restrict__ ag, const double* __res
   else ((double*)out)[i] = -d;
 }
 
-__global__ void init_state_kernel(double* state, int* elapsed, double* ep_return, unsigned long long* ctr, const DevModel* m, int n, int fetch) {
+__global__ void init_state_kernel(double* state, int* elapsed, double* ep_return, unsigned long long* ctr, unsigned long long* env_seed, unsigned long long seed, const DevModel* m, int n, int fetch) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* st = state + (size_t)i * MCB_STATE_STRIDE;
@@ -2261,7 +2261,7 @@ __global__ void init_state_kernel(double* state, int* elapsed, double* ep_return
   const double* mq = fetch ? m->d.key_mocap_quat : m->d.mocap_quat0;
   for (int k = 0; k < 3; k++) st[71 + k] = mp[k];
   for (int k = 0; k < 4; k++) st[74 + k] = mq[k];
-  elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0;
+  elapsed[i] = 0; ep_return[i] = 0; ctr[i] = 0; env_seed[i] = seed;
 }
 
 // gather / scatter between the resident state record and caller arrays
@@ -2311,6 +2311,19 @@ __global__ void random_actions_kernel(float* act, int n, uint64_t seed, unsigned
   act[i] = (float)(2.0 * philox_uniform(seed, (uint32_t)i, ctr) - 1.0);
 }
 
+// mcb_seed(): MyCobotEnv.reset(seed=) reseeds the env's generator (mycobot.py:509-510) -> new Philox key, draw counter 0
+__global__ void seed_kernel(unsigned long long* env_seed, unsigned long long* ctr, const uint8_t* mask, unsigned long long seed, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (!mask || mask[i])) { env_seed[i] = seed; ctr[i] = 0; }
+}
+// the part of a checkpoint mcb_get_state / mcb_set_state do not carry: RNG streams and running episode returns
+__global__ void rng_io_kernel(unsigned long long* env_seed, unsigned long long* ctr, double* ep_return, unsigned long long* u_seed, unsigned long long* u_ctr,
+                              double* u_ret, int n, int write) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (write) { if (u_seed) env_seed[i] = u_seed[i]; if (u_ctr) ctr[i] = u_ctr[i]; if (u_ret) ep_return[i] = u_ret[i]; }
+  else { if (u_seed) u_seed[i] = env_seed[i]; if (u_ctr) u_ctr[i] = ctr[i]; if (u_ret) u_ret[i] = ep_return[i]; }
+}
 __global__ void iota_kernel(int* list, int* count, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) list[i] = i;
@@ -2322,6 +2335,13 @@ __global__ void iota_kernel(int* list, int* count, int n) {
 }  // namespace
 
 // ================================================================================================
+// ABI calls that need a particular device make it current for their own duration only (the caller's current device is restored)
+struct DevGuard {
+  int prev = -1; bool ok = true;
+  explicit DevGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess); if (prev == dev) prev = -1; }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct mcb_model {
   int device;
   DevModel* dev;
@@ -2335,9 +2355,10 @@ struct mcb_batch {
   int* redo_count; int* redo_list;
   mcb_task_cfg cfg;
   uint64_t seed;
-  double* state; int* elapsed; double* ep_return; unsigned long long* rng_ctr; double* stats;
+  double* state; int* elapsed; double* ep_return; unsigned long long* rng_ctr; unsigned long long* env_seed; double* stats;
   double* debug;
   int last_launches;
+  long long launches_total;   // kernels this library launched on behalf of the batch (counted at the launch sites)
   int lockstep_warps, tuned;
   // staging for the host-buffer entry point
   float* d_actions; double *d_obs, *d_ag, *d_dg, *d_fobs; void* d_reward; uint8_t* d_flags;
@@ -2345,7 +2366,7 @@ struct mcb_batch {
 };
 
 static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
-  a.m = b->model->dev; a.n_envs = b->n_envs; a.cfg = b->cfg; a.seed = b->seed;
+  a.m = b->model->dev; a.n_envs = b->n_envs; a.cfg = b->cfg; a.env_seed = b->env_seed;
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
   a.redo_count = b->redo_count; a.redo_list = b->redo_list;
   a.lockstep_warps = b->lockstep_warps;
@@ -2355,6 +2376,7 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   else if (b->mid_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list, b->redo_count, b->n_envs);
   else mcb_env_kernel<0><<<(b->n_envs + WPB_SMALL - 1) / WPB_SMALL, 32 * WPB_SMALL, b->smem_small, st>>>(a);
   CK(cudaGetLastError());
+  b->launches_total += 1 + (b->big_only ? 0 : 1) + 1;      // this one, the middle tier (unless last-tier-only), the last tier
   // envs that overflowed the common layout (grid-stride over the device list; empty in contact-free workloads) ...
   if (!b->big_only) mcb_env_kernel<1><<<b->mid_only ? (b->n_envs + WPB_MID - 1) / WPB_MID : b->mid_grid, 32 * WPB_MID, b->smem_mid, st>>>(a);
   CK(cudaGetLastError());
@@ -2379,7 +2401,8 @@ int32_t mcb_task_cfg_size(void) { return (int32_t)sizeof(mcb_task_cfg); }
 
 int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** out) {
   if (!d || !out) return fail("mcb_model_create: null argument");
-  CK(cudaSetDevice(device));
+  DevGuard guard(device);
+  if (!guard.ok) return fail("mcb_model_create: cannot select the device", cudaGetLastError());
   mcb_model* m = new mcb_model();
   m->device = device;
   DevModel& h = m->host;
@@ -2431,8 +2454,9 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
     pp.tran = d->geom_invweight[g1][0] + d->geom_invweight[g2][0];
     pp.rot = d->geom_invweight[g1][1] + d->geom_invweight[g2][1];
   }
-  CK(cudaMalloc(&m->dev, sizeof(DevModel)));
-  CK(cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  cudaError_t ce = cudaMalloc(&m->dev, sizeof(DevModel));
+  if (ce == cudaSuccess) ce = cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(m->dev); delete m; return fail("mcb_model_create: upload", ce); }
   *out = m;
   return 0;
 }
@@ -2453,7 +2477,8 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
   if (cfg->controller_type == 1 && (cfg->control_steps < 1 || cfg->control_steps > 50)) return fail("mcb_batch_create: control_steps out of range");
   if (cfg->reward_type < 0 || cfg->reward_type > 2 || (cfg->reward_type == 2 && !cfg->has_object)) return fail("mcb_batch_create: reward_type must be 0, 1 or 2 (2 needs has_object)");
-  CK(cudaSetDevice(m->device));
+  DevGuard guard(m->device);
+  if (!guard.ok) return fail("mcb_batch_create: cannot select the model's device", cudaGetLastError());
   mcb_batch* b = new mcb_batch();
   memset(b, 0, sizeof *b);
   b->model = m; b->n_envs = n_envs; b->cfg = *cfg; b->seed = seed;
@@ -2465,7 +2490,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   b->smem_mid = MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID;
   b->smem_big = MODEL_BYTES + sizeof(EnvS<2>);
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, m->device));
+  if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete b; return fail("mcb_batch_create: cudaGetDeviceProperties", cudaGetLastError()); }
   b->big_grid = prop.multiProcessorCount * 5;      // five one-warp CTAs of the last tier are resident per SM (44.5 KB each)
   b->mid_grid = prop.multiProcessorCount;
   cudaError_t e = cudaFuncSetAttribute(mcb_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_small);
@@ -2475,20 +2500,25 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(shared memory)", e); }
   size_t N = (size_t)n_envs;
-  CK(cudaMalloc(&b->state, N * MCB_STATE_STRIDE * sizeof(double)));
-  CK(cudaMalloc(&b->elapsed, N * sizeof(int)));
-  CK(cudaMalloc(&b->ep_return, N * sizeof(double)));
-  CK(cudaMalloc(&b->rng_ctr, N * sizeof(unsigned long long)));
-  CK(cudaMalloc(&b->stats, 8 * sizeof(double)));
-  CK(cudaMalloc(&b->redo_count, 2 * sizeof(int)));
-  CK(cudaMalloc(&b->redo_list, 2 * N * sizeof(int)));
-  CK(cudaMemset(b->redo_count, 0, 2 * sizeof(int)));
-  CK(cudaMalloc(&b->debug, DEBUG_DOUBLES * sizeof(double)));
-  CK(cudaMemset(b->stats, 0, 8 * sizeof(double)));
-  init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, m->dev, n_envs, cfg->fetch_env);
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  b->lockstep_warps = cfg->lockstep_warps ? cfg->lockstep_warps : WPB_SMALL;   // 0: mcb_autotune() decides at the first step
+  // partial allocations are released on failure (mcb_batch_destroy frees whatever is non-null)
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mcb_batch_destroy(b); return fail(#call, e_); } } while (0)
+  CKB(cudaMalloc(&b->state, N * MCB_STATE_STRIDE * sizeof(double)));
+  CKB(cudaMalloc(&b->elapsed, N * sizeof(int)));
+  CKB(cudaMalloc(&b->ep_return, N * sizeof(double)));
+  CKB(cudaMalloc(&b->rng_ctr, N * sizeof(unsigned long long)));
+  CKB(cudaMalloc(&b->env_seed, N * sizeof(unsigned long long)));
+  CKB(cudaMalloc(&b->stats, 8 * sizeof(double)));
+  CKB(cudaMalloc(&b->redo_count, 2 * sizeof(int)));
+  CKB(cudaMalloc(&b->redo_list, 2 * N * sizeof(int)));
+  CKB(cudaMemset(b->redo_count, 0, 2 * sizeof(int)));
+  CKB(cudaMalloc(&b->debug, DEBUG_DOUBLES * sizeof(double)));
+  CKB(cudaMemset(b->stats, 0, 8 * sizeof(double)));
+  init_state_kernel<<<(n_envs + 127) / 128, 128>>>(b->state, b->elapsed, b->ep_return, b->rng_ctr, b->env_seed, (unsigned long long)seed, m->dev, n_envs, cfg->fetch_env);
+  CKB(cudaGetLastError());
+  CKB(cudaDeviceSynchronize());
+#undef CKB
+  b->launches_total = 1;
+  b->lockstep_warps = cfg->lockstep_warps ? cfg->lockstep_warps : 1;   // 0: free-running until mcb_autotune() is called (explicitly: mcb_step never tunes)
   b->tuned = cfg->lockstep_warps != 0;
   *out = b;
   return 0;
@@ -2496,7 +2526,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
 
 int32_t mcb_batch_destroy(mcb_batch* b) {
   if (!b) return 0;
-  cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->stats); cudaFree(b->debug); cudaFree(b->redo_count); cudaFree(b->redo_list);
+  cudaFree(b->state); cudaFree(b->elapsed); cudaFree(b->ep_return); cudaFree(b->rng_ctr); cudaFree(b->env_seed); cudaFree(b->stats); cudaFree(b->debug); cudaFree(b->redo_count); cudaFree(b->redo_list);
   if (b->d_actions) { cudaFree(b->d_actions); cudaFree(b->d_obs); cudaFree(b->d_fobs); cudaFree(b->d_ag); cudaFree(b->d_dg); cudaFree(b->d_reward); cudaFree(b->d_flags); }
   if (b->h_actions) { cudaFreeHost(b->h_actions); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_fobs); cudaFreeHost(b->h_ag); cudaFreeHost(b->h_dg); cudaFreeHost(b->h_reward); cudaFreeHost(b->h_flags); }
   delete b;
@@ -2519,9 +2549,10 @@ int32_t mcb_step(mcb_batch* b, const float* actions, double* obs, double* ag, do
   StepArgs a; memset(&a, 0, sizeof a);
   a.mode = MODE_STEP; a.actions = actions; a.obs = obs; a.ag = ag; a.dg = dg; a.reward = reward;
   a.terminated = terminated; a.truncated = truncated; a.success = success; a.final_obs = final_obs;
-  b->last_launches = 3;  // one kernel per layout tier (the second and third usually find an empty list)
-  if (!b->tuned && !b->big_only && !b->mid_only) { if (mcb_autotune(b, nullptr, 0, stream) < 0) return -1; }
-  return launch(b, a, (cudaStream_t)stream);
+  const long long before = b->launches_total;
+  const int rc = launch(b, a, (cudaStream_t)stream);      // nothing but kernel launches on the caller's stream: graph-capturable, no hidden sync
+  b->last_launches = (int)(b->launches_total - before);   // one kernel per layout tier (the second and third usually find an empty list)
+  return rc;
 }
 
 int32_t mcb_batch_lockstep_warps(const mcb_batch* b) { return b ? b->lockstep_warps : -1; }
@@ -2563,7 +2594,7 @@ int32_t mcb_autotune(mcb_batch* b, const float* actions, int32_t steps_per_candi
     TCK(cudaMemcpyAsync(sv_el, b->elapsed, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
     TCK(cudaMemcpyAsync(sv_ctr, b->rng_ctr, N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     auto one_step = [&](int k) {
-      if (!actions) random_actions_kernel<<<(unsigned)((N * adim + 255) / 256), 256, 0, st>>>(t_act, (int)(N * adim), b->seed ^ 0x74756e65ull, (unsigned)k);
+      if (!actions) { random_actions_kernel<<<(unsigned)((N * adim + 255) / 256), 256, 0, st>>>(t_act, (int)(N * adim), b->seed ^ 0x74756e65ull, (unsigned)k); b->launches_total++; }
       StepArgs a; memset(&a, 0, sizeof a);
       a.mode = MODE_STEP; a.actions = actions ? actions : t_act; a.reward = t_reward;
       a.terminated = t_flags; a.truncated = t_flags + N; a.success = t_flags + 2 * N;
@@ -2636,6 +2667,7 @@ int32_t mcb_get_state(mcb_batch* b, double* qpos, double* qvel, double* ctrl, do
   if (!b) return fail("mcb_get_state: null batch");
   state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, qpos, qvel, ctrl, warm, goal, elapsed, qprev, mocap, 0);
   CK(cudaGetLastError());
+  b->launches_total++;
   return 0;
 }
 int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const double* goal,
@@ -2644,6 +2676,7 @@ int32_t mcb_set_state(mcb_batch* b, const double* qpos, const double* qvel, cons
   state_io_kernel<<<(b->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->state, b->elapsed, b->n_envs, (double*)qpos, (double*)qvel, (double*)ctrl,
                                                                              (double*)warm, (double*)goal, (int*)elapsed, (double*)qprev, (double*)mocap, 1);
   CK(cudaGetLastError());
+  b->launches_total++;
   return 0;
 }
 
@@ -2674,6 +2707,7 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
     CK(cudaMalloc(&b->d_actions, N * ad * sizeof(float)));
     CK(cudaMalloc(&b->d_obs, N * od * sizeof(double)));
     CK(cudaMalloc(&b->d_fobs, N * od * sizeof(double)));
+    CK(cudaMemset(b->d_fobs, 0, N * od * sizeof(double)));      // rows of envs that did not auto-reset are never written
     CK(cudaMallocHost(&b->h_fobs, N * od * sizeof(double)));
     CK(cudaMalloc(&b->d_ag, N * 3 * sizeof(double)));
     CK(cudaMalloc(&b->d_dg, N * 3 * sizeof(double)));
@@ -2715,11 +2749,76 @@ int32_t mcb_step_host(mcb_batch* b, const float* h_actions, double* h_obs, doubl
   return 0;
 }
 
+int32_t mcb_reset_host(mcb_batch* b, const uint8_t* h_mask, const double* h_obj_xy, const double* h_goals, double* h_obs, double* h_ag, double* h_dg, void* stream) {
+  if (!b) return fail("mcb_reset_host: null batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)b->n_envs, od = (size_t)b->obs_dim;
+  // small per-call device staging (a reset is not the hot path); freed before returning
+  uint8_t* d_mask = nullptr; double *d_xy = nullptr, *d_g = nullptr, *d_o = nullptr, *d_a = nullptr, *d_d = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (!src || e != cudaSuccess) return;
+    e = cudaMalloc(dst, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  up((void**)&d_mask, h_mask, N); up((void**)&d_xy, h_obj_xy, N * 2 * sizeof(double)); up((void**)&d_g, h_goals, N * 3 * sizeof(double));
+  if (e == cudaSuccess && h_obs) e = cudaMalloc(&d_o, N * od * sizeof(double));
+  if (e == cudaSuccess && h_ag) e = cudaMalloc(&d_a, N * 3 * sizeof(double));
+  if (e == cudaSuccess && h_dg) e = cudaMalloc(&d_d, N * 3 * sizeof(double));
+  int rc = 0;
+  if (e == cudaSuccess) rc = mcb_reset(b, d_mask, d_xy, d_g, d_o, d_a, d_d, stream);
+  if (e == cudaSuccess && rc == 0 && h_obs) e = cudaMemcpyAsync(h_obs, d_o, N * od * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0 && h_ag) e = cudaMemcpyAsync(h_ag, d_a, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0 && h_dg) e = cudaMemcpyAsync(h_dg, d_d, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_mask); cudaFree(d_xy); cudaFree(d_g); cudaFree(d_o); cudaFree(d_a); cudaFree(d_d);
+  if (e != cudaSuccess) return fail("mcb_reset_host", e);
+  return rc;
+}
+
+int32_t mcb_seed(mcb_batch* b, uint64_t seed, const uint8_t* mask, void* stream) {
+  if (!b) return fail("mcb_seed: null batch");
+  seed_kernel<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->env_seed, b->rng_ctr, mask, (unsigned long long)seed, b->n_envs);
+  CK(cudaGetLastError());
+  b->launches_total++;
+  if (!mask) b->seed = seed;
+  return 0;
+}
+
+int32_t mcb_get_rng_state(mcb_batch* b, uint64_t* env_seed, uint64_t* draw_counter, double* ep_return, void* stream) {
+  if (!b) return fail("mcb_get_rng_state: null batch");
+  rng_io_kernel<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->env_seed, b->rng_ctr, b->ep_return, (unsigned long long*)env_seed,
+                                                                        (unsigned long long*)draw_counter, ep_return, b->n_envs, 0);
+  CK(cudaGetLastError());
+  b->launches_total++;
+  return 0;
+}
+int32_t mcb_set_rng_state(mcb_batch* b, const uint64_t* env_seed, const uint64_t* draw_counter, const double* ep_return, void* stream) {
+  if (!b) return fail("mcb_set_rng_state: null batch");
+  rng_io_kernel<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->env_seed, b->rng_ctr, b->ep_return, (unsigned long long*)env_seed,
+                                                                        (unsigned long long*)draw_counter, (double*)ep_return, b->n_envs, 1);
+  CK(cudaGetLastError());
+  b->launches_total++;
+  return 0;
+}
+
+int32_t mcb_last_fallback_list(mcb_batch* b, int32_t* h_envs, int32_t cap, void* stream) {
+  if (!b || (cap > 0 && !h_envs) || cap < 0) return fail("mcb_last_fallback_list: bad argument");
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, b->redo_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  const int m = n < cap ? n : cap;
+  if (m > 0) CK(cudaMemcpy(h_envs, b->redo_list, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int64_t mcb_total_launches(const mcb_batch* b) { return b ? (int64_t)b->launches_total : -1; }
 int32_t mcb_last_step_launches(const mcb_batch* b) { return b ? b->last_launches : -1; }
 
 int32_t mcb_fp64_peak_probe(int32_t device, int32_t iters, double* tflops_out) {
   if (!tflops_out || iters <= 0) return fail("mcb_fp64_peak_probe: bad argument");
-  CK(cudaSetDevice(device));
+  DevGuard guard(device);
+  if (!guard.ok) return fail("mcb_fp64_peak_probe: cannot select the device", cudaGetLastError());
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   double* out;

@@ -84,6 +84,11 @@ class DeviceHerReplayBuffer:
         (the achieved goal is the object / gripper position inside it, mycobot.py:342-388)."""
         obs, rew, term, trunc, info = step_out
         nobs, nag = obs["observation"], obs["achieved_goal"]
+        # MyCobotVectorEnv.step returns its persistent output buffers: a `prev_obs` that was not cloned before the step now
+        # holds the NEW observation and the stored transition would have obs == next_obs
+        for k in ("observation", "achieved_goal"):
+            if torch.is_tensor(prev_obs[k]) and prev_obs[k].data_ptr() == obs[k].data_ptr():
+                raise ValueError(f"add_step: prev_obs[{k!r}] aliases the step's output buffer -- clone the observation before calling env.step()")
         if "final_observation" in info:
             done = info["_final_observation"]
             fo = info["final_observation"]

@@ -17,7 +17,12 @@ from .vector_env import MyCobotVectorEnv
 
 class MyCobotSB3VecEnv:
     def __init__(self, num_envs, **kwargs):
-        kwargs.setdefault("auto_reset", True)
+        # SB3 VecEnvs always reset finished sub-envs inside step_wait; here that happens inside the step kernel, which needs
+        # the device sampler.  Configurations that would leave finished episodes running are refused, not half-served.
+        if not kwargs.setdefault("auto_reset", True):
+            raise ValueError("MyCobotSB3VecEnv: auto_reset=False is not a VecEnv (step_wait must return the first observation of the next episode)")
+        if kwargs.get("goal_source", "device") != "device":
+            raise ValueError("MyCobotSB3VecEnv: goal_source='reference' resets on the host between steps; use MyCobotVectorEnv.step() for it")
         self.venv = MyCobotVectorEnv(num_envs=num_envs, **kwargs)
         self.num_envs = self.venv.num_envs
         self.observation_space = self.venv.single_observation_space
@@ -38,8 +43,8 @@ class MyCobotSB3VecEnv:
         return out
 
     def seed(self, seed=None):
-        self.venv._sampler.seed(seed)
-        return [seed] * self.num_envs
+        # VecEnv.seed: takes effect at the next reset of each env, like `env.reset(seed=...)` in the reference (mycobot.py:509-510)
+        return self.venv.seed(seed)
 
     def step_async(self, actions):
         self._actions = np.ascontiguousarray(actions, dtype=np.float32)

@@ -143,7 +143,7 @@ def _device_model(device_index, variant="joint"):
         flat = mjcf.load_compiled(mjcf.COMPILED_MOCAP if variant == "mocap" else mjcf.COMPILED_JOINT)
         desc = flatten.reduce_model(flat)
         h = C.c_void_p()
-        _lib.check(L.mcb_model_create(C.byref(desc), device_index, C.byref(h)))
+        _lib.check(L.mcb_model_create(C.byref(desc), device_index, C.byref(h)))       # restores the caller's current device
         _MODEL_CACHE[key] = (h, desc, flat)
     return _MODEL_CACHE[key]
 
@@ -159,7 +159,12 @@ class MyCobotVectorEnv:
                  control_steps=5, controller_type="joint", obj_range=0.1, target_in_the_air=True,
                  distance_threshold=0.01, initial_qpos=None, fetch_env=False, reward_type="sparse", frame_skip=20,
                  max_episode_steps=50, device="cuda:0", seed=0, auto_reset=True, goal_source="device", nefc_max=0,
-                 lockstep_warps=0, **kwargs):
+                 lockstep_warps=0, autotune=True, **kwargs):
+        """Constructor kwargs are the reference's (mycobot.py:30-46).  `obj_range` and `initial_qpos` are accepted and only
+        stored, exactly like the reference does (mycobot.py:54,56 assign them; nothing reads them: the cube is placed by
+        `generate_random_point_inside_rectangle`, mycobot.py:220-222, and the start pose is qpos0 / keyframe 0).
+        `lockstep_warps=0, autotune=True`: the first full `reset()` ends with one explicit `mcb_autotune` call (it
+        synchronises and is never hidden inside `step`); `autotune=False` keeps the free-running default."""
         if controller_type not in ("joint", "IK", "mocap"):
             raise ValueError(f"unknown controller_type {controller_type!r}")
         if fetch_env and controller_type == "joint":
@@ -181,6 +186,8 @@ class MyCobotVectorEnv:
         self.target_in_the_air, self.distance_threshold = bool(target_in_the_air), float(distance_threshold)
         self.reward_type, self.frame_skip, self.control_steps = reward_type, int(frame_skip), control_steps
         self.controller_type, self.fetch_env, self.obj_range = controller_type, fetch_env, obj_range
+        self.initial_qpos = {} if initial_qpos is None else initial_qpos
+        self._want_autotune = bool(autotune) and int(lockstep_warps) == 0 and int(nefc_max) == 0
         self.max_episode_steps = int(max_episode_steps)
         self.goal_source = goal_source
         self.auto_reset = bool(auto_reset)
@@ -240,11 +247,17 @@ class MyCobotVectorEnv:
     # ------------------------------------------------------------------ gymnasium surface
     def reset(self, *, seed=None, options=None, mask=None, object_xy=None, goals=None):
         """mycobot.py:506-514.  `mask` restricts the reset to some envs; `object_xy` / `goals` inject sampler
-        outputs (float64 [N,2] / [N,3], numpy or torch)."""
+        outputs (float64 [N,2] / [N,3], numpy or torch).  `seed` reseeds the sampler of the (masked) envs like
+        `seeding.np_random(seed)` does in the reference: the host protocol sampler (goal_source='reference') and the
+        device Philox streams (key := seed, draw counter := 0).  The returned tensors are the env's persistent output
+        buffers: the next `reset` / `step` overwrites them (clone to keep)."""
         self._sampler.seed(seed)
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        if seed is not None:
+            with torch.cuda.device(self._dev_index):
+                _lib.check(self._L.mcb_seed(self._batch, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(m), self._stream()))
         if self.goal_source == "reference" and goals is None:
             ids = range(self.num_envs) if m is None else torch.nonzero(m).flatten().tolist()
             object_xy, goals = self._sampler.sample(ids)
@@ -257,11 +270,49 @@ class MyCobotVectorEnv:
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_reset(self._batch, _ptr(m), _ptr(xy_t), _ptr(g_t), _ptr(self._obs), _ptr(self._ag),
                                         _ptr(self._dg), self._stream()))
+        if self._want_autotune and m is None:
+            self._want_autotune = False
+            self.autotune()
         return self._obs_dict(), {}
+
+    def seed(self, seed=None):
+        """Reseed every env's sampler without resetting (SB3 VecEnv.seed)."""
+        self._sampler.seed(seed)
+        if seed is not None:
+            with torch.cuda.device(self._dev_index):
+                _lib.check(self._L.mcb_seed(self._batch, int(seed) & 0xFFFFFFFFFFFFFFFF, None, self._stream()))
+        return [seed] * self.num_envs
+
+    def reset_host(self, *, seed=None, mask=None, object_xy=None, goals=None):
+        """`reset` through HOST buffers (numpy in / numpy out): what a reference-side adapter holding numpy arrays calls."""
+        self._sampler.seed(seed)
+        N = self.num_envs
+        mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        if seed is not None:
+            md = None if mk is None else torch.as_tensor(mk, device=self.device)
+            with torch.cuda.device(self._dev_index):
+                _lib.check(self._L.mcb_seed(self._batch, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(md), self._stream()))
+        if self.goal_source == "reference" and goals is None:
+            ids = range(N) if mk is None else np.nonzero(mk)[0].tolist()
+            object_xy, goals = self._sampler.sample(ids)
+            if not self.has_object:
+                object_xy = None
+        xy = None if object_xy is None else np.ascontiguousarray(object_xy, dtype=np.float64)
+        g = None if goals is None else np.ascontiguousarray(goals, dtype=np.float64)
+        out = dict(observation=np.empty((N, self.obs_dim)), achieved_goal=np.empty((N, 3)), desired_goal=np.empty((N, 3)))
+        p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        with torch.cuda.device(self._dev_index):
+            _lib.check(self._L.mcb_reset_host(self._batch, p(mk), p(xy), p(g), p(out["observation"]), p(out["achieved_goal"]),
+                                             p(out["desired_goal"]), self._stream()))
+        return out, {}
 
     def step(self, actions):
         """mycobot.py:132-205 (joint controller) for all envs; TimeLimit folded in.  `actions`: float32 [N,7]
-        torch CUDA tensor (or anything convertible)."""
+        torch CUDA tensor (or anything convertible).
+
+        ALIASING CONTRACT: observation / achieved_goal / desired_goal / reward / final_observation are the env's persistent
+        device buffers -- the kernel writes straight into them and the next `step` / `reset` overwrites them.  Clone what
+        must outlive the next call (`HerReplay.add_step` refuses a `prev_obs` that aliases the new one)."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
         if tuple(actions.shape) != (self.num_envs, self.action_dim):
@@ -306,14 +357,19 @@ class MyCobotVectorEnv:
         st = dict(qpos=torch.empty(N, 19, dtype=torch.float64, device=dev), qvel=torch.empty(N, 18, dtype=torch.float64, device=dev),
                   ctrl=torch.empty(N, 7, dtype=torch.float64, device=dev), qacc_warmstart=torch.empty(N, 18, dtype=torch.float64, device=dev),
                   goal=torch.empty(N, 3, dtype=torch.float64, device=dev), elapsed=torch.empty(N, dtype=torch.int32, device=dev),
-                  qprev=torch.empty(N, 6, dtype=torch.float64, device=dev), mocap=torch.empty(N, 7, dtype=torch.float64, device=dev))
+                  qprev=torch.empty(N, 6, dtype=torch.float64, device=dev), mocap=torch.empty(N, 7, dtype=torch.float64, device=dev),
+                  env_seed=torch.empty(N, dtype=torch.int64, device=dev), rng_counter=torch.empty(N, dtype=torch.int64, device=dev),
+                  ep_return=torch.empty(N, dtype=torch.float64, device=dev))
         with torch.cuda.device(self._dev_index):
+            _lib.check(self._L.mcb_get_rng_state(self._batch, _ptr(st["env_seed"]), _ptr(st["rng_counter"]), _ptr(st["ep_return"]), self._stream()))
             _lib.check(self._L.mcb_get_state(self._batch, _ptr(st["qpos"]), _ptr(st["qvel"]), _ptr(st["ctrl"]),
                                             _ptr(st["qacc_warmstart"]), _ptr(st["goal"]), _ptr(st["elapsed"]), _ptr(st["qprev"]),
                                             _ptr(st["mocap"]), self._stream()))
         return st
 
-    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None, qprev=None, mocap=None):
+    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, goal=None, elapsed=None, qprev=None, mocap=None,
+                  env_seed=None, rng_counter=None, ep_return=None):
+        """Inverse of `get_state` (a full checkpoint: physics state, goals, episode clocks, RNG streams, running returns)."""
         def prep(x, shape, dt):
             if x is None:
                 return None
@@ -325,13 +381,18 @@ class MyCobotVectorEnv:
         ts = [prep(qpos, (N, 19), torch.float64), prep(qvel, (N, 18), torch.float64), prep(ctrl, (N, 7), torch.float64),
               prep(qacc_warmstart, (N, 18), torch.float64), prep(goal, (N, 3), torch.float64), prep(elapsed, (N,), torch.int32),
               prep(qprev, (N, 6), torch.float64), prep(mocap, (N, 7), torch.float64)]
+        rs = [prep(env_seed, (N,), torch.int64), prep(rng_counter, (N,), torch.int64), prep(ep_return, (N,), torch.float64)]
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_set_state(self._batch, *[_ptr(t) for t in ts], self._stream()))
+            if any(t is not None for t in rs):
+                _lib.check(self._L.mcb_set_rng_state(self._batch, *[_ptr(t) for t in rs], self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
 
     def autotune(self, actions=None, steps_per_candidate=0):
-        """Pick the step kernel's lockstep grouping for this batch now (otherwise the first `step` does it); the state is
-        restored exactly.  Returns the chosen number of warps per group."""
+        """Pick the step kernel's lockstep grouping for this batch (explicit: `step` never tunes; the constructor's
+        `autotune=True` calls this once at the end of the first full `reset`).  Synchronises; the state is restored exactly.
+        Returns the chosen number of warps per group."""
+        self._want_autotune = False
         a = None if actions is None else torch.as_tensor(actions).to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self._dev_index):
             return _lib.check(self._L.mcb_autotune(self._batch, _ptr(a), int(steps_per_candidate), self._stream()))
@@ -347,6 +408,18 @@ class MyCobotVectorEnv:
         with torch.cuda.device(self._dev_index):
             n = _lib.check(self._L.mcb_last_fallback_envs(self._batch, C.byref(last), self._stream()))
         return n, int(last.value)
+
+    def last_fallback_list(self, cap=None):
+        """Indices of the envs of the most recent step that left the common layout (host list); synchronises."""
+        cap = self.num_envs if cap is None else int(cap)
+        buf = np.zeros(max(cap, 1), dtype=np.int32)
+        with torch.cuda.device(self._dev_index):
+            n = _lib.check(self._L.mcb_last_fallback_list(self._batch, buf.ctypes.data_as(C.c_void_p), cap, self._stream()))
+        return buf[:min(n, cap)].copy()
+
+    @property
+    def total_launches(self):
+        return int(self._L.mcb_total_launches(self._batch))
 
     def forward(self):
         """mj_forward on every env (refreshes frames, qacc_warmstart and the observation buffers)."""
