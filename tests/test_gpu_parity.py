@@ -116,7 +116,7 @@ def _oracle_step(flat, has_object, block_gripper, reward_type, qpos, qvel, ctrl,
     return oe, o, r, te, tr, inf, free
 
 
-def _step_compare(flat, has_object, block_gripper, reward_type, qpos, qvel, ctrl, goals, acts, require_free=False):
+def _step_compare(flat, has_object, block_gripper, reward_type, qpos, qvel, ctrl, goals, acts, require_free=False, max_hatch=0):
     n = qpos.shape[0]
     env = _env(num_envs=n, has_object=has_object, block_gripper=block_gripper, reward_type=reward_type, auto_reset=False)
     env.set_state(qpos=qpos, qvel=qvel, ctrl=ctrl, qacc_warmstart=np.zeros((n, 18)), goal=goals, elapsed=np.zeros(n, dtype=np.int32))
@@ -124,24 +124,25 @@ def _step_compare(flat, has_object, block_gripper, reward_type, qpos, qvel, ctrl
     st = env.get_state()
     gq, gv = st["qpos"].cpu().numpy(), st["qvel"].cpu().numpy()
     nq, nv = (19, 18) if has_object else (12, 12)
-    nfree = 0
+    nfree, hatch = 0, 0
     for i in range(n):
         oe, o, r, te, tr, inf, free = _oracle_step(flat, has_object, block_gripper, reward_type, qpos[i], qvel[i], ctrl[i], goals[i], acts[i])
-        tol = TOL_FREE if free else TOL_CONTACT
-        if not free:
-            # the reference algorithm stops its Newton solve at a cost tolerance of 1e-8; where that alone moves the
-            # result by more than the contact bound the case is ill-conditioned and the bound is 10x that sensitivity
+        tol = TOL_FREE if free else TOL_CONTACT        # north star: 1e-9 contact-free, 1e-5 with contact -- qpos, qvel and observations alike
+        eq = np.abs(gq[i, :nq] - oe.sim.qpos[:nq]).max()
+        ev = np.abs(gv[i, :nv] - oe.sim.qvel[:nv]).max()
+        eo = max(np.abs(obs["observation"][i].cpu().numpy() - o["observation"]).max(), np.abs(obs["achieved_goal"][i].cpu().numpy() - o["achieved_goal"]).max())
+        if max(eq, ev, eo) > tol:
+            # counted escape: the reference algorithm stops its Newton solve at a cost tolerance of 1e-8; where that alone moves
+            # the oracle's own result by more than the bound, the case is ill-conditioned and the bound is 10x that sensitivity
             oe2 = _oracle_step(flat, has_object, block_gripper, reward_type, qpos[i], qvel[i], ctrl[i], goals[i], acts[i], tolerance=1e-13)[0]
-            sens = max(np.abs(oe2.sim.qpos - oe.sim.qpos).max(), np.abs(oe2.sim.qvel - oe.sim.qvel).max() * 1e-2)
-            tol = max(tol, 10 * sens)
+            sens = max(np.abs(oe2.sim.qpos - oe.sim.qpos).max(), np.abs(oe2.sim.qvel - oe.sim.qvel).max())
+            assert max(eq, ev, eo) <= max(tol, 10 * sens), f"env {i} free={free}: qpos {eq:.2e} qvel {ev:.2e} obs {eo:.2e} sensitivity {sens:.2e}"
+            hatch += 1
         nfree += free
-        np.testing.assert_allclose(gq[i, :nq], oe.sim.qpos[:nq], atol=tol, rtol=0, err_msg=f"qpos env {i} free={free}")
-        np.testing.assert_allclose(gv[i, :nv], oe.sim.qvel[:nv], atol=tol if free else tol * 100, rtol=0, err_msg=f"qvel env {i} free={free}")
-        np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol * 10, rtol=0)
-        np.testing.assert_allclose(obs["achieved_goal"][i].cpu().numpy(), o["achieved_goal"], atol=tol, rtol=0)
         assert np.array_equal(obs["desired_goal"][i].cpu().numpy(), goals[i])          # goals bit-exact
         assert abs(float(rew[i]) - float(r)) <= (TOL_REWARD if free or reward_type == "sparse" else tol)
         assert bool(term[i]) == te and bool(trunc[i]) == tr and bool(info["is_success"][i]) == inf["is_success"]
+    assert hatch <= max_hatch, f"{hatch} of {n} envs needed the sensitivity-scaled bound (allowed: {max_hatch})"
     assert rew.dtype == (torch.float32 if reward_type == "sparse" else torch.float64)
     if require_free:
         assert nfree >= n // 2, f"only {nfree}/{n} test states were contact-free"
@@ -176,7 +177,7 @@ def test_single_step_with_table_contact(flat, block_gripper):
     rng = np.random.default_rng(10)
     goals = rng.uniform(-0.1, 0.1, (n, 3)) + np.array([0, 0, 0.21])
     acts = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
-    _step_compare(flat, True, block_gripper, "sparse", qpos, qvel, ctrl, goals, acts)
+    _step_compare(flat, True, block_gripper, "sparse", qpos, qvel, ctrl, goals, acts, max_hatch=1)
 
 
 @pytest.mark.parametrize("name", ["reach_dense_seed0", "reach_dense_seed1_perturbed", "pick_sparse_seed0",
@@ -194,8 +195,8 @@ def test_against_committed_golden_rollouts(name):
         st = env.get_state()
         # the GPU state is re-injected from the golden trajectory every step => every step is a single-step test
         np.testing.assert_allclose(st["qpos"][0, :nq].cpu().numpy(), g["qpos"][t][:nq], atol=tol, rtol=0)
-        np.testing.assert_allclose(st["qvel"][0, :nv].cpu().numpy(), g["qvel"][t][:nv], atol=tol * (100 if has_object else 1), rtol=0)
-        np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), g["obs"][t], atol=tol * 10, rtol=0)
+        np.testing.assert_allclose(st["qvel"][0, :nv].cpu().numpy(), g["qvel"][t][:nv], atol=tol, rtol=0)
+        np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), g["obs"][t], atol=tol, rtol=0)
         assert abs(float(rew[0]) - float(g["reward"][t])) <= TOL_REWARD
         assert bool(term[0]) == bool(g["terminated"][t]) and bool(info["is_success"][0]) == bool(g["success"][t])
         warm = g["warm"][t][None].copy()
@@ -218,13 +219,13 @@ def test_against_committed_controller_golden(name):
                       goal=g["goal"][None], elapsed=np.zeros(1, dtype=np.int32), qprev=g["qprev0"][t][None], mocap=g["mocap0"][t][None])
         obs, rew, term, trunc, info = env.step(torch.as_tensor(g["actions"][t][None]))
         st = env.get_state()
-        tol = min(max(1e-7, 100 * float(g["sens"][t])), 1e-4)
+        tol = min(max(1e-7, 100 * float(g["sens"][t])), TOL_CONTACT)
         np.testing.assert_allclose(st["qpos"][0].cpu().numpy(), g["qpos"][t], atol=tol, rtol=0, err_msg=f"step {t}")
         np.testing.assert_allclose(st["ctrl"][0, :nu].cpu().numpy(), g["ctrl"][t], atol=tol, rtol=0)
         np.testing.assert_allclose(st["qprev"][0].cpu().numpy(), g["qprev"][t], atol=tol, rtol=0)
         np.testing.assert_allclose(st["mocap"][0].cpu().numpy(), g["mocap"][t], atol=1e-12 if controller == "mocap" else 1.0, rtol=0)
-        np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), g["obs"][t], atol=tol * 10, rtol=0)
-        assert abs(float(rew[0]) - float(g["reward"][t])) < tol * 10
+        np.testing.assert_allclose(obs["observation"][0].cpu().numpy(), g["obs"][t], atol=tol, rtol=0)
+        assert abs(float(rew[0]) - float(g["reward"][t])) <= tol
     env.close()
 
 
@@ -533,13 +534,13 @@ def test_ik_controller_matches_oracle(flat, fetch_env, has_object):
             o, r, te, tr, inf = oe.step(acts[i])
             oes_tight[i].step(acts[i])
             # 100 substeps of the bang-bang PD loop are chaotic: a one-ulp change of qvel can move the result by
-            # 1e-7.  The bound is 1e-7 or 100x what a one-ulp perturbation + solver tolerance 1e-13 moves the oracle itself (<= 1e-4).
+            # 1e-7.  The bound is 1e-7 or 100x what a one-ulp perturbation + solver tolerance 1e-13 moves the oracle itself (<= 1e-5, the north star's with-contact bound).
             sens = np.abs(oes_tight[i].sim.qpos[:nq] - oe.sim.qpos[:nq]).max()
-            tol = min(max(1e-7, 100 * sens), 1e-4)      # the GPU differs from the oracle in many roundings, not in one ulp
+            tol = min(max(1e-7, 100 * sens), TOL_CONTACT)      # the GPU differs from the oracle in many roundings, not in one ulp
             np.testing.assert_allclose(after["qpos"][i, :nq].cpu().numpy(), oe.sim.qpos[:nq], atol=tol, rtol=0, err_msg=f"step {t} env {i}")
             np.testing.assert_allclose(after["ctrl"][i].cpu().numpy(), oe.sim.ctrl, atol=tol, rtol=0, err_msg=f"ctrl step {t} env {i}")
-            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol * 10, rtol=0)
-            assert abs(float(rew[i]) - float(r)) < tol * 10 and bool(term[i]) == te
+            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol, rtol=0)
+            assert abs(float(rew[i]) - float(r)) <= tol and bool(term[i]) == te
     env.close()
 
 
@@ -602,13 +603,13 @@ def test_mocap_controller_matches_oracle(fetch_env, has_object):
             o, r, te, tr, inf = oe.step(acts[i])
             oes_tight[i].step(acts[i])
             sens = np.abs(oes_tight[i].sim.qpos[:nq] - oe.sim.qpos[:nq]).max()
-            tol = min(max(1e-7, 100 * sens), 1e-4)
+            tol = min(max(1e-7, 100 * sens), TOL_CONTACT)
             np.testing.assert_allclose(after["mocap"][i].cpu().numpy(), np.concatenate((oe.sim.mocap_pos, oe.sim.mocap_quat)), atol=1e-13,
                                        err_msg=f"mocap pose step {t} env {i}")
             np.testing.assert_allclose(after["qpos"][i, :nq].cpu().numpy(), oe.sim.qpos[:nq], atol=tol, rtol=0, err_msg=f"step {t} env {i}")
             assert abs(float(after["ctrl"][i, 0]) - oe.sim.ctrl[0]) == 0.0
-            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol * 10, rtol=0)
-            assert abs(float(rew[i]) - float(r)) < tol * 10 and bool(term[i]) == te
+            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=tol, rtol=0)
+            assert abs(float(rew[i]) - float(r)) <= tol and bool(term[i]) == te
     assert np.abs(after["qpos"][:, :6].cpu().numpy() - st0["qpos"][:, :6].cpu().numpy()).max() > 0.05     # the weld really moved the arm
     env.close()
 

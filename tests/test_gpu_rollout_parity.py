@@ -1,0 +1,111 @@
+"""Parity on ROLLOUT states at BASELINE.json's sizes (configs 2-4): 16384 pick-and-place / push envs, 4096 reach envs.
+
+The single-step tests in test_gpu_parity.py start from synthetic states; here the batch is rolled 25 random-action steps
+with auto-reset (episode clocks staggered, so resets happen inside the roll) and ONE more step of the whole batch is then
+compared, env by env, with the oracle's restatement of `MyCobotEnv.step` (mycobot.py:132-205) started from the same
+(qpos, qvel, ctrl, qacc_warmstart, goal, elapsed): 256 random envs plus every env that left the common shared-memory
+layout in that step (the contact-rich ones).  Bounds are the north star's: 1e-9 contact-free, 1e-5 (qpos AND qvel) with
+contact, rewards 1e-9, flags exact.  The only escape is counted: where the reference algorithm's own Newton stopping
+tolerance (1e-8) moves the oracle's result by more than the bound, the bound is 10x that sensitivity -- and at most 2 % of
+the compared envs may need it.  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_FREE, TOL_CONTACT, TOL_REWARD = 1e-9, 1e-5, 1e-9
+WORK = {
+    "pick": (dict(has_object=True, reward_type="sparse"), 16384),
+    "push": (dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse"), 16384),
+    "reach": (dict(has_object=False, reward_type="dense"), 4096),
+}
+
+
+def _oracle_env(flat, kw, st, i, tolerance=None):
+    from mycobotgym_b200 import mjcf
+    from oracle.oracle import OracleEnv
+
+    f = flat
+    if tolerance is not None:
+        f = mjcf.FlatModel(flat)
+        f["tolerance"] = tolerance
+    oe = OracleEnv(f, has_object=kw["has_object"], block_gripper=kw.get("block_gripper", False),
+                   target_in_the_air=kw.get("target_in_the_air", True), reward_type=kw["reward_type"])
+    oe.sim.set_state(st["qpos"][i], st["qvel"][i], st["ctrl"][i], st["qacc_warmstart"][i])
+    oe.goal = st["goal"][i].copy()
+    oe.elapsed = int(st["elapsed"][i])
+    return oe
+
+
+@pytest.mark.parametrize("workload", ["pick", "push", "reach"])
+def test_one_step_from_rollout_states_at_baseline_size(workload):
+    from mycobotgym_b200 import mjcf
+    from mycobotgym_b200.vector_env import MyCobotVectorEnv
+
+    flat = mjcf.load_compiled()
+    kw, n = WORK[workload]
+    env = MyCobotVectorEnv(num_envs=n, seed=3, autotune=False, **kw)
+    env.reset()
+    env.set_state(elapsed=torch.arange(n, dtype=torch.int32) % 50)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)
+    for _ in range(25):
+        env.step(torch.rand(n, 7, device="cuda", generator=gen) * 2 - 1)
+    st_t = env.get_state()
+    st = {k: v.cpu().numpy() for k, v in st_t.items()}
+    acts_t = torch.rand(n, 7, device="cuda", generator=gen) * 2 - 1
+    acts = acts_t.cpu().numpy()
+    stats = env.stats().cpu().numpy()
+    assert stats[0] > n // 4                                     # resets happened inside the roll
+    env.close()
+
+    env2 = MyCobotVectorEnv(num_envs=n, auto_reset=False, autotune=False, **kw)
+    env2.set_state(**{k: st_t[k] for k in ("qpos", "qvel", "ctrl", "qacc_warmstart", "goal", "elapsed", "qprev")})
+    obs, rew, term, trunc, info = env2.step(acts_t)
+    left = env2.last_fallback_list()
+    after = {k: v.cpu().numpy() for k, v in env2.get_state().items()}
+    obs_np = {k: v.cpu().numpy() for k, v in obs.items()}
+    rew_np, term_np, trunc_np, succ_np = rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy(), info["is_success"].cpu().numpy()
+    assert env2.stats().cpu().numpy()[5] == 0                    # no constraint rows dropped anywhere in the batch
+    env2.close()
+
+    rng = np.random.default_rng(5)
+    chosen = sorted(set(rng.choice(n, 256, replace=False).tolist()) | set(left[:256].tolist()))
+    nq, nv = (19, 18) if kw["has_object"] else (12, 12)
+    hatch, nfree, worst = 0, 0, dict(free_q=0.0, free_v=0.0, con_q=0.0, con_v=0.0, obs=0.0)
+    for i in chosen:
+        # contact-free in the north star's sense: no inequality row (limit or contact) active in any substep
+        probe = _oracle_env(flat, kw, st, i)
+        probe.sim.ctrl[:] = np.clip(acts[i], -1, 1).astype(np.float64)
+        free = True
+        for _ in range(probe.frame_skip):
+            probe.sim.step(1)
+            free &= probe.sim.nefc == 7
+        oe = _oracle_env(flat, kw, st, i)
+        o, r, te, tr, inf = oe.step(acts[i])
+        tol = TOL_FREE if free else TOL_CONTACT
+        eq = np.abs(after["qpos"][i, :nq] - oe.sim.qpos[:nq]).max()
+        ev = np.abs(after["qvel"][i, :nv] - oe.sim.qvel[:nv]).max()
+        eo = max(np.abs(obs_np["observation"][i] - o["observation"]).max(), np.abs(obs_np["achieved_goal"][i] - o["achieved_goal"]).max())
+        if max(eq, ev, eo) > tol:
+            oe2 = _oracle_env(flat, kw, st, i, tolerance=1e-13)
+            oe2.step(acts[i])
+            sens = max(np.abs(oe2.sim.qpos - oe.sim.qpos).max(), np.abs(oe2.sim.qvel - oe.sim.qvel).max())
+            assert max(eq, ev, eo) <= max(tol, 10 * sens), (workload, i, free, eq, ev, eo, sens)
+            hatch += 1
+        nfree += free
+        worst["free_q" if free else "con_q"] = max(worst["free_q" if free else "con_q"], eq)
+        worst["free_v" if free else "con_v"] = max(worst["free_v" if free else "con_v"], ev)
+        worst["obs"] = max(worst["obs"], eo)
+        assert np.array_equal(obs_np["desired_goal"][i], st["goal"][i])
+        if kw["reward_type"] == "sparse":
+            d = np.linalg.norm(o["achieved_goal"] - st["goal"][i])
+            assert float(rew_np[i]) == float(r) or abs(d - 0.01) < 1e-9
+        else:
+            assert abs(float(rew_np[i]) - float(r)) <= max(TOL_REWARD, tol if not free else 0)
+        assert bool(term_np[i]) == te and bool(trunc_np[i]) == tr and bool(succ_np[i]) == inf["is_success"]
+    print(f"\n{workload}: {len(chosen)} envs compared ({len(left)} left the common layout, {nfree} contact-free), "
+          f"sensitivity-scaled bound used by {hatch}; worst |gpu - oracle| {worst}")
+    assert hatch <= max(1, len(chosen) // 50), f"{hatch} of {len(chosen)} envs needed the sensitivity-scaled bound"
