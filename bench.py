@@ -27,14 +27,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (env kwargs, envs per GPU, algorithmic FLOP per env-step [DESIGN.md "Algorithmic work"])
-    "reach": (dict(has_object=False, reward_type="dense"), 4096, 0.60e6),
-    "push": (dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse"), 16384, 1.27e6),
-    "pick": (dict(has_object=True, reward_type="sparse"), 16384, 1.25e6),
+    # name: (env kwargs, envs per GPU, algorithmic FLOP per env-step).  FLOP: INSTRUMENTED count of the CPU oracle's arithmetic
+    # on the same random-action protocol (tools/count_flops.py: every add / mul / div / sqrt of oracle/mjc_oracle.c counted by a
+    # wrapper type; frozen in BASELINE.md section 4; FMA = 2).  Round 1 used the survey's estimates (pick 1.25e6).
+    "reach": (dict(has_object=False, reward_type="dense"), 4096, 0.600e6),
+    "push": (dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse"), 16384, 1.254e6),
+    "pick": (dict(has_object=True, reward_type="sparse"), 16384, 1.036e6),
     # IK controller (the reference's default): 5 x (6x6 DLS solve + 20 substeps) per env-step
-    "ik": (dict(has_object=True, reward_type="sparse", controller_type="IK"), 16384, 5 * 1.25e6),
+    "ik": (dict(has_object=True, reward_type="sparse", controller_type="IK"), 16384, 5.180e6),
     # mocap controller on the mocap model variant: a 6-row weld drags the arm (13 equality rows instead of 7)
-    "mocap": (dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml"), 16384, 1.45e6),
+    "mocap": (dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml"), 16384, 1.247e6),
+    # contact-rich regime (what a trained pick-and-place policy looks like): EVERY env holds the cube between the finger layers
+    # (tests/golden/grasp_pick_sparse.npz replicated + small velocity noise), no auto-reset, the action keeps the grip closed
+    "grasp": (dict(has_object=True, reward_type="sparse", auto_reset=False), 16384, 1.406e6),
 }
 METRIC = "env-steps/sec (pick-and-place, 16K envs/GPU) at 1/2/4/8 B200 vs CPU MuJoCo"
 UNIT = "env-steps/s"
@@ -173,7 +178,7 @@ def run_reference(args):
         return
     kw, per_gpu, _ = WORKLOADS[args.workload]
     # each "step" of this arm = a bounded sample of the workload; K steps + W warm-up must end within minutes
-    per_step_budget = 2000
+    per_step_budget = 20000      # >= 20 k env-steps per timed step (1250 per worker on 16 cores): run-to-run spread ~5 %
     vals = []
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_port_throughput(args.workload, per_step_budget)
@@ -215,14 +220,26 @@ def run_ours(args):
     n = args.envs_per_gpu or per_gpu
     env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, lockstep_warps=int(os.environ.get("MCB_LOCKSTEP", "0")), **kw)
     env.reset()
-    # steady-state rollout: episode clocks staggered uniformly over the 50-step horizon, so ~2 % of the envs hit the
-    # TimeLimit and auto-reset (two extra forward passes + goal / cube resampling) inside every timed step
-    stagger = torch.arange(n, device=dev, dtype=torch.int32) % env.max_episode_steps
-    env.set_state(elapsed=stagger)
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    acts = torch.rand(K + W, n, env.action_dim, device=dev, generator=gen) * 2 - 1
+    if args.workload == "grasp":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "grasp_pick_sparse.npz"))
+        rep = lambda x: torch.as_tensor(np.repeat(np.asarray(x)[None], n, 0), device=dev)
+        qvel = rep(g["qvel0"]) + 1e-3 * torch.randn(n, 18, device=dev, dtype=torch.float64, generator=gen)
+        env.set_state(qpos=rep(g["qpos0"]), qvel=qvel, ctrl=rep(g["ctrl0"]), qacc_warmstart=rep(g["warm0"]), goal=rep(g["goal"]),
+                      elapsed=torch.zeros(n, dtype=torch.int32), qprev=rep(g["qpos0"][:6]))
+        acts = torch.zeros(K + W, n, env.action_dim, device=dev)
+        acts[:, :, :6] = torch.as_tensor(g["qpos0"][:6], device=dev, dtype=torch.float32) + 0.02 * (torch.rand(K + W, n, 6, device=dev, generator=gen) * 2 - 1)
+        acts[:, :, 6] = 0.8
+        args.preroll = 0
+        env.autotune(acts[0])
+    else:
+        # steady-state rollout: episode clocks staggered uniformly over the 50-step horizon, so ~2 % of the envs hit the
+        # TimeLimit and auto-reset (two extra forward passes + goal / cube resampling) inside every timed step
+        stagger = torch.arange(n, device=dev, dtype=torch.int32) % env.max_episode_steps
+        env.set_state(elapsed=stagger)
+        acts = torch.rand(K + W, n, env.action_dim, device=dev, generator=gen) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # pre-roll one full episode horizon (untimed, before the W warm-up steps): with staggered clocks every env has then been
     # reset at a different step, so the timed steps see the steady-state mix of early- and late-episode states (arm near the
@@ -254,6 +271,19 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     if world > 1:
         dist.barrier()
+    allreduce_us = None
+    if world > 1:                          # the "64 B, latency-bound" claim as a number: event-timed all-reduce of the statistics vector
+        probe = stats.clone()
+        for _ in range(3):
+            all_reduce_stats(probe)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); dist.barrier()
+        a0.record()
+        for _ in range(20):
+            all_reduce_stats(probe)
+        a1.record()
+        torch.cuda.synchronize()
+        allreduce_us = a0.elapsed_time(a1) / 20 * 1e3
     ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -279,12 +309,18 @@ def run_ours(args):
     h2d, d2h = n * env.action_dim * 4, n * ((env.obs_dim + 6) * 8 + rbytes + 3)
 
     her = None
-    if rank == 0 and world == 1 and kw["reward_type"] in ("sparse", "dense") and not args.no_her:
+    if rank == 0 and world == 1 and kw["reward_type"] in ("sparse", "dense") and not args.no_her and args.workload != "grasp":
         her = her_relabel_leg(env, acts, dev, flush)
 
     if rank == 0:
         L = _lib.load()
         import ctypes as C
+
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{n}", {})
+        except Exception:
+            pass
 
         peak = C.c_double(0)
         _lib.check(L.mcb_fp64_peak_probe(local, 20000, C.byref(peak)))
@@ -305,16 +341,18 @@ def run_ours(args):
             "gpu_launches": K * env.last_step_launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of mcb_env_kernel<0> for this workload at 16384 envs, from
-                         # the ncu --set full capture summarised in profiles/r01za_ncu_summary.txt (12.29 MB read + 26.33 MB written)
-                         "traffic": 38.62e6 if (args.workload == "pick" and n == 16384) else None, "traffic_unit": "B/launch",
-                         "note": "dominant kernel = mcb_env_kernel (the whole step); algorithmic FLOP/env-step from DESIGN.md; "
+                         # dram__bytes_read.sum + dram__bytes_write.sum of mcb_env_kernel<0>, read from the committed ncu --set full
+                         # capture of this build (profiles/traffic.json, written by tools/ncu_summary.py --traffic)
+                         "traffic": traffic.get("bytes_per_launch"), "traffic_unit": "B/launch", "traffic_source": traffic.get("source"),
+                         "flop_per_env_step": flop_per_step,
+                         "note": "dominant kernel = mcb_env_kernel (the whole step); algorithmic FLOP/env-step = instrumented count of the CPU oracle (tools/count_flops.py, BASELINE.md 4); "
                                  "peak = DFMA micro-kernel measured in this run (FP64 peak is not in MEASURED_PEAKS.json)",
                          "hbm_GBps": per_gpu_rate * state_bytes / 1e9},
             "cpu_baseline": None if cpu_val is None else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "episode_stats": {"episodes": st[0], "successes": st[1], "return_sum": st[2], "length_sum": st[3], "env_steps": st[4],
                               "row_overflows": st[5], "fallback_envs_last_step": fallback_envs[0], "last_tier_envs_last_step": fallback_envs[1], "solver_iters_per_substep": (st[6] / st[7]) if st[7] else None},
             "wall_s_timed_region": t_wall,
+            "stats_allreduce_us": allreduce_us,
             "her_relabel": her,
         }
         print(json.dumps(line), flush=True)
