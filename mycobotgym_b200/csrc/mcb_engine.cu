@@ -805,8 +805,10 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
       else if (side == 1) { da = hx + ax_; db = hx + bx; }
       else if (side == 2) { da = hy - ay_; db = hy - by; }
       else { da = hy + ay_; db = hy + by; }
-      keep = da >= 0;
-      crossing = (da >= 0) != (db >= 0);
+      // a vertex within 1e-12 of the clip line counts as inside (an incident edge that coincides with the reference face's border
+      // would otherwise be cut at a point chosen by rounding noise; see clip_poly in the oracle)
+      keep = da >= -1e-12;
+      crossing = keep != (db >= -1e-12);
       if (crossing) { double t = da / (da - db); ix = ax_ + t * (bx - ax_); iy = ay_ + t * (by - ay_); }
       emit = (keep ? 1 : 0) + (crossing ? 1 : 0);
     }

@@ -415,6 +415,7 @@ static int plane_box(rawcon* out, const double* ppos, const double* pmat, const 
  * MuJoCo's mjc_BoxBox (engine_collision_box.c) is the algorithm restated; the degenerate
  * tie-breaking here (first face axis wins; an edge axis must beat faces by 5%) is ours and
  * is mirrored exactly by the CUDA kernel. Normal points from box 1 to box 2. */
+#define CLIP_EPS 1e-12
 static int clip_poly(double* px, double* py, int n, double hx, double hy) {
   /* Sutherland-Hodgman against |x|<=hx, |y|<=hy */
   double qx[16], qy[16];
@@ -428,8 +429,11 @@ static int clip_poly(double* px, double* py, int n, double hx, double hy) {
       else if (side == 1) { da = hx + ax; db = hx + bx; }
       else if (side == 2) { da = hy - ay; db = hy - by; }
       else { da = hy + ay; db = hy + by; }
-      if (da >= 0) { qx[cnt] = ax; qy[cnt] = ay; cnt++; }
-      if ((da >= 0) != (db >= 0)) {
+      /* a vertex within CLIP_EPS of the clip line counts as inside: when an edge of the incident face coincides with the
+         border of the reference face (the two finger pads share their y extent) its end points sit +-1 ulp around the
+         line and a strict test would cut it at a point chosen by rounding noise -- a contact of arbitrary depth */
+      if (da >= -CLIP_EPS) { qx[cnt] = ax; qy[cnt] = ay; cnt++; }
+      if ((da >= -CLIP_EPS) != (db >= -CLIP_EPS)) {
         double t = da / (da - db);
         qx[cnt] = ax + t * (bx - ax); qy[cnt] = ay + t * (by - ay); cnt++;
       }
