@@ -192,7 +192,7 @@ __device__ __noinline__ double warp_sum(double v) {
 }
 // three warp sums in one butterfly: after two rounds every lane carries one of the (up to four) quantities, so the
 // remaining three rounds move one value instead of three -- 9 double shuffles (incl. the broadcasts) instead of 15
-__device__ __noinline__ void warp_sum3(double& a, double& b, double& c, int lane) {
+__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c, int lane) {   // (out of line the three references live in local memory)
   const bool odd = lane & 1, hi = lane & 2;
   const double r1 = shfl_xor_d(odd ? a : b, 1);      // even lanes collect a and c, odd lanes collect b
   const double r2 = shfl_xor_d(c, 1);
@@ -1317,8 +1317,7 @@ template <class S>
 struct Newton {
   S& s; const DevModel* __restrict__ m; int lane, nva, nefc;
   bool coupled;
-  double gauss, cost, qg0, qg1, qg2;
-  double qa[S::NROW / 32 + 1], qb[S::NROW / 32 + 1], qc[S::NROW / 32 + 1];  // per-lane quadratic coefficients of rows lane + 32 t
+  double gauss, cost;
 
   __device__ __forceinline__ bool active(int r, double jar) const { return !(s.rmeta[r] & RM_INEQ) || jar < 0; }
 
@@ -1463,21 +1462,24 @@ struct Newton {
     __syncwarp();
   }
   struct Pt { double alpha, cost, d0, d1; };
-  __device__ void ls_eval(Pt& p) {
-    double a = p.alpha, q0 = 0, q1 = 0, q2 = 0;
+  __device__ __forceinline__ double line_search(double scale) {
+    // per-lane quadratic coefficients of rows lane + 32 t and the Gauss term's: locals of this (inlined) function, so they stay
+    // in registers -- as members of a struct whose other methods are out of line they lived in local memory (profiles/r02a)
+    double qa[S::NROW / 32 + 1], qb[S::NROW / 32 + 1], qc[S::NROW / 32 + 1], qg0, qg1, qg2;
+    auto ls_eval = [&](Pt& p) {
+      double a = p.alpha, q0 = 0, q1 = 0, q2 = 0;
 #pragma unroll
-    for (int t = 0; t < S::NROW / 32 + 1; t++) {
-      int r = lane + 32 * t;
-      if (r < nefc && active(r, s.eJaref[r] + a * s.eJv[r])) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
-    }
-    warp_sum3(q0, q1, q2, lane);
-    q0 += qg0; q1 += qg1; q2 += qg2;
-    p.cost = a * a * q2 + a * q1 + q0;
-    p.d0 = 2 * a * q2 + q1;
-    p.d1 = 2 * q2;
-    if (p.d1 <= 0) p.d1 = MINVAL;
-  }
-  __device__ double line_search(double scale) {
+      for (int t = 0; t < S::NROW / 32 + 1; t++) {
+        int r = lane + 32 * t;
+        if (r < nefc && active(r, s.eJaref[r] + a * s.eJv[r])) { q0 += qa[t]; q1 += qb[t]; q2 += qc[t]; }
+      }
+      warp_sum3(q0, q1, q2, lane);
+      q0 += qg0; q1 += qg1; q2 += qg2;
+      p.cost = a * a * q2 + a * q1 + q0;
+      p.d0 = 2 * a * q2 + q1;
+      p.d1 = 2 * q2;
+      if (p.d1 <= 0) p.d1 = MINVAL;
+    };
     // |search|^2 and the two Gauss-term coefficients in one butterfly (M * search is needed for the latter, so it is formed
     // before the zero-norm early-out instead of after it)
     double mv = mulM_row(s, lane, nva, s.search);
@@ -1541,7 +1543,7 @@ struct Newton {
     return (p1.cost < p2.cost ? p1.alpha : p2.alpha);
   }
 
-  __device__ void solve() {
+  __device__ __forceinline__ void solve() {
     const double scale = 1.0 / (MDL.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
