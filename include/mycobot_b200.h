@@ -136,7 +136,8 @@ typedef struct mcb_task_cfg {
   int32_t has_object;          /* mycobot.py:33 */
   int32_t block_gripper;       /* mycobot.py:34 */
   int32_t target_in_the_air;   /* mycobot.py:38 */
-  int32_t reward_type;         /* 0 sparse (float32 out), 1 dense (float64 out), 2 reward_shaping (float64 out, object envs); mycobot.py:289-298 */
+  int32_t reward_type;         /* 0 sparse (float32 out), 1 dense (float64 out), 2 reward_shaping (float64 out; in reach envs the hidden cube is then simulated,
+                                * pass a model whose object geom has size 0 like mycobot.py:475-481 leaves it); mycobot.py:289-298 */
   int32_t max_episode_steps;   /* 50 */
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */

@@ -2017,8 +2017,12 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
     __syncthreads();
   }
   const mcb_task_cfg& cfg = a.cfg;
-  const int nba = cfg.has_object ? NB : NB - 1;
-  const int nva = cfg.has_object ? NV : NH;
+  // reach envs: the hidden cube (mycobot.py:475-481 only zeroes its geom / site size) is frozen -- it is not observable and the
+  // robot's dynamics do not depend on it -- except under reward_shaping, whose reach term reads its position
+  // (mycobot.py:402-448): there it is simulated, with the zero-size box the model variant carries
+  const bool sim_cube = cfg.has_object || cfg.reward_type == 2;
+  const int nba = sim_cube ? NB : NB - 1;
+  const int nva = sim_cube ? NV : NH;
   const int nwork = TIER == 0 ? a.n_envs : a.redo_count[TIER - 1];
   const int* work_list = TIER == 0 ? nullptr : a.redo_list + (size_t)(TIER - 1) * a.n_envs;
   if (TIER > 0 && nwork == 0) return;
@@ -2182,9 +2186,10 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
         if (bad) { dist = 1e10; rew = cfg.reward_type == 0 ? -1.0 : 0.0; }
         if (cfg.reward_type == 2 && !bad) {
           // stage_rewards (mycobot.py:402-448): reach / grasp / lift from the sites and the contact list of the last
-          // forward pass; write_obs left grip_pos in o[0..2] and object_pos in o[3..5]
+          // forward pass; write_obs left grip_pos in o[0..2]; object_pos = the cube body's origin (site object0 sits on it)
           const double* o = s.grad;
-          double gx = o[0] - o[3], gy = o[1] - o[4], gz = o[2] - o[5];
+          const double* op = s.xpos + CUBE * 3;
+          double gx = o[0] - op[0], gy = o[1] - op[1], gz = o[2] - op[2];
           double r_reach = (1 - tanh(sqrt(gx * gx + gy * gy + gz * gz))) * 0.2;
           bool tr = false, tl = false;
           for (int c = 0; c < s.ncon; c++) {
@@ -2195,7 +2200,7 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
           }
           double r_grasp = (tr && tl) ? 0.5 : 0.0, r_lift = 0.0;
           if (r_grasp > 0.0) {
-            double tx = o[3] - MDL.d.target0_pos[0], ty = o[4] - MDL.d.target0_pos[1], tz = o[5] - MDL.d.target0_pos[2];
+            double tx = op[0] - MDL.d.target0_pos[0], ty = op[1] - MDL.d.target0_pos[1], tz = op[2] - MDL.d.target0_pos[2];
             r_lift = 0.5 + (1 - tanh(sqrt(tx * tx + ty * ty + tz * tz))) * (0.9 - 0.5);
           }
           rew = fmax(fmax(r_reach, r_grasp), r_lift) * 100;
@@ -2480,7 +2485,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   if ((cfg->controller_type == 2) != (m->host.d.has_weld != 0)) return fail("mcb_batch_create: the mocap controller needs the mocap model variant, the other controllers the joint variant");
   if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
   if (cfg->controller_type == 1 && (cfg->control_steps < 1 || cfg->control_steps > 50)) return fail("mcb_batch_create: control_steps out of range");
-  if (cfg->reward_type < 0 || cfg->reward_type > 2 || (cfg->reward_type == 2 && !cfg->has_object)) return fail("mcb_batch_create: reward_type must be 0, 1 or 2 (2 needs has_object)");
+  if (cfg->reward_type < 0 || cfg->reward_type > 2) return fail("mcb_batch_create: reward_type must be 0 (sparse), 1 (dense) or 2 (reward_shaping)");
   DevGuard guard(m->device);
   if (!guard.ok) return fail("mcb_batch_create: cannot select the model's device", cudaGetLastError());
   mcb_batch* b = new mcb_batch();

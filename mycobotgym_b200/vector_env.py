@@ -140,8 +140,13 @@ def _device_model(device_index, variant="joint"):
     key = (device_index, variant)
     if key not in _MODEL_CACHE:
         L = _lib.load()
-        flat = mjcf.load_compiled(mjcf.COMPILED_MOCAP if variant == "mocap" else mjcf.COMPILED_JOINT)
+        flat = mjcf.load_compiled(mjcf.COMPILED_MOCAP if variant.startswith("mocap") else mjcf.COMPILED_JOINT)
         desc = flatten.reduce_model(flat)
+        if variant.endswith("+hidden"):
+            # "Hide object in Reach env" (mycobot.py:475-481): geom_size[object0] = 0 AFTER compilation, so geom_rbound keeps the
+            # visible cube's value; only the reach + reward_shaping ids simulate this cube (it is frozen otherwise)
+            for k in range(3):
+                desc.geom_size[desc.geom_object][k] = 0.0
         h = C.c_void_p()
         _lib.check(L.mcb_model_create(C.byref(desc), device_index, C.byref(h)))       # restores the caller's current device
         _MODEL_CACHE[key] = (h, desc, flat)
@@ -171,8 +176,6 @@ class MyCobotVectorEnv:
             raise AssertionError("Joint controller not supported for Fetch env")        # mycobot.py:96
         if reward_type not in ("sparse", "dense", "reward_shaping"):
             raise ValueError(f"unknown reward_type {reward_type!r}")
-        if reward_type == "reward_shaping" and not has_object:
-            raise NotImplementedError("reward_shaping on the reach env needs the hidden cube simulated (it is frozen here, DESIGN.md)")
         if ("mocap" in model_path) != (controller_type == "mocap"):
             raise ValueError("the mocap controller needs mycobot280_mocap.xml and the joint/IK controllers mycobot280.xml "
                              "(the reference would fail on data.mocap_pos / on the missing actuators)")
@@ -194,7 +197,8 @@ class MyCobotVectorEnv:
         self._L = _lib.load()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._dev_index = dev_index
-        self._model, self._desc, self._flat = _device_model(dev_index, "mocap" if controller_type == "mocap" else "joint")
+        variant = ("mocap" if controller_type == "mocap" else "joint") + ("+hidden" if (reward_type == "reward_shaping" and not has_object) else "")
+        self._model, self._desc, self._flat = _device_model(dev_index, variant)
         cfg = flatten.TaskCfg(
             has_object=int(has_object), block_gripper=int(block_gripper), target_in_the_air=int(target_in_the_air),
             reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,

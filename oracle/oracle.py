@@ -334,7 +334,16 @@ class OracleEnv:
         self.has_object, self.block_gripper = has_object, block_gripper
         self.target_in_the_air, self.distance_threshold = target_in_the_air, distance_threshold
         self.reward_type, self.frame_skip, self.max_episode_steps = reward_type, frame_skip, max_episode_steps
-        self.sim = OracleSim(flat, disable_cube=not has_object)
+        if not has_object and reward_type == "reward_shaping":
+            # "Hide object in Reach env" (mycobot.py:475-481): the cube stays in the simulation with a zero-size box (geom_rbound
+            # keeps its compiled value); only this reward reads it (mycobot.py:402-448), so only here it is not frozen
+            hidden = type(flat)(flat)
+            gs = np.array(flat["geom_size"], dtype=np.float64).copy()
+            gs[list(flat["geom_names"]).index("object0")] = 0.0
+            hidden["geom_size"] = gs
+            self.sim = OracleSim(hidden, disable_cube=False)
+        else:
+            self.sim = OracleSim(flat, disable_cube=not has_object)
         self.site_eef = flat["site_names"].index("EEF")
         self.site_obj = flat["site_names"].index("object0")
         jn = flat["jnt_names"]

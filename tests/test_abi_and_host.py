@@ -57,8 +57,6 @@ def test_registry_matches_reference_registration():
 
 
 def test_unbuilt_rows_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        vector_env.MyCobotVectorEnv(num_envs=1, reward_type="reward_shaping", has_object=False)
     for kwargs in (dict(controller_type="mocap"), dict(model_path="./assets/mycobot280_mocap.xml"), dict(controller_type="osc")):
         with pytest.raises(ValueError):                      # controller and model variant must agree
             vector_env.MyCobotVectorEnv(num_envs=1, **kwargs)

@@ -702,3 +702,38 @@ def test_make_registry_ids_and_reference_goal_autoreset():
     assert not torch.equal(obs["desired_goal"], g0) and bool((env.get_state()["elapsed"] == 0).all())
     assert not torch.equal(inf["final_observation"], obs["observation"])
     env.close()
+
+
+def test_reach_reward_shaping_matches_oracle(flat):
+    # the 5 MyCobot[Fetch]Reach-RewardShaping-* ids: the hidden cube is simulated (zero-size box), the reward reads its position
+    from mycobotgym_b200 import vector_env
+    from oracle.oracle import OracleEnv
+
+    n = 8
+    env = _env(num_envs=n, has_object=False, reward_type="reward_shaping", auto_reset=False, goal_source="reference")
+    oes = [OracleEnv(flat, has_object=False, reward_type="reward_shaping") for _ in range(n)]
+    random.seed(3)
+    env.reset(seed=3)
+    st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+    for i, oe in enumerate(oes):
+        oe.reset(seed=0, goal=st["goal"][i])
+    rng = np.random.default_rng(12)
+    for t in range(4):
+        acts = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(acts))
+        after = env.get_state()
+        assert rew.dtype == torch.float64 and obs["observation"].shape == (n, 10)
+        for i, oe in enumerate(oes):
+            oe.sim.set_state(st["qpos"][i], st["qvel"][i], st["ctrl"][i], st["qacc_warmstart"][i])
+            o, r, te, tr, inf = oe.step(acts[i])
+            np.testing.assert_allclose(after["qpos"][i].cpu().numpy(), oe.sim.qpos, atol=TOL_CONTACT, rtol=0)     # cube included
+            np.testing.assert_allclose(obs["observation"][i].cpu().numpy(), o["observation"], atol=TOL_CONTACT, rtol=0)
+            assert abs(float(rew[i]) - float(r)) < 1e-7 and bool(term[i]) == te
+    assert float(after["qpos"][:, 14].max()) < 0.2001                      # the point cube rests on the table top
+    env.close()
+    for name in ("MyCobotReach-RewardShaping-joint-v0", "MyCobotFetchReach-RewardShaping-IK-v0", "MyCobotReach-RewardShaping-mocap-v0"):
+        e = vector_env.make(name, num_envs=2, autotune=False)
+        e.reset()
+        e.step(torch.zeros(2, e.action_dim))
+        e.close()

@@ -223,3 +223,19 @@ def test_mocap_controller_on_the_oracle():
         env = OracleEnv(fm, has_object=True, controller_type="mocap", fetch_env=True)
         np.testing.assert_allclose(env.sim.mocap_pos, [-0.05154491, 0.01053502, 0.3448586], atol=1e-12)   # mycobot280_mocap.xml:8
         assert abs(env.height_offset - 0.209981) < 1e-9
+
+
+def test_reach_reward_shaping_simulates_the_hidden_cube(flat):
+    # MyCobotReach-RewardShaping-* (mycobotgym/__init__.py:6-35): compute_reward -> stage_rewards reads the object0 site
+    # (mycobot.py:402-448) of the cube that _env_setup only hid (zero geom / site size, mycobot.py:475-481)
+    env = OracleEnv(flat, has_object=False, reward_type="reward_shaping")
+    random.seed(0)
+    o, _ = env.reset(seed=0)
+    assert o["observation"].shape == (10,)
+    z0 = env.sim.qpos[14]
+    for _ in range(5):
+        o, r, te, tr, info = env.step(np.zeros(7, dtype=np.float32))
+    assert 0.1999 < env.sim.qpos[14] < 0.2 and z0 > 0.2099              # the zero-size box fell from 0.21 onto the table top (one contact: 4x the depth)
+    d = np.linalg.norm(env.sim.site_xpos[env.site_eef] - env.sim.site_xpos[env.site_obj])
+    assert abs(float(r) - (1 - np.tanh(d)) * 0.2 * 100) < 1e-12           # reach term only: nothing can grasp a point
+    assert np.array_equal(o["achieved_goal"], o["observation"][:3])       # reach: achieved goal = gripper position
