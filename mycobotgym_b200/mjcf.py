@@ -789,13 +789,16 @@ def set_const(m):
 # ----------------------------------------------------------------------------------
 
 
-def flatmodel_from_mjmodel(mjm, names=None):  # pragma: no cover - needs mujoco, which is not installable in this image
+def flatmodel_from_mjmodel(mjm, mujoco=None):
     """Fill the same table from a live `mujoco.MjModel` -- the reference's compiled model (`MujocoEnv.__init__`,
     mycobot.py:69-75).  Field names follow mjModel.  Only plane / box geoms are kept as collision geoms (mesh hulls are
     a documented gap); `set_const()` is NOT re-run: invweight0 / meaninertia / connect anchors come from MuJoCo's own
     mj_setConst, so diffing this table against `compile_mjcf()` checks the mini-compiler field by field
-    (`diff_flatmodels`).  Untested here (no mujoco wheel offline)."""
-    import mujoco
+    (`diff_flatmodels`).  `mujoco`: the module providing mj_id2name and the mjtObj / mjtWrap / mjtEq / mjtTrn enums
+    (default: `import mujoco`); tests/test_model_compiler.py executes this function against a stand-in mjModel built
+    from the compiled table (tests/fake_mujoco.py), since no mujoco wheel is installable offline."""
+    if mujoco is None:
+        import mujoco  # pragma: no cover - needs the real package
 
     m = FlatModel()
     nv, nq, nbody, njnt = mjm.nv, mjm.nq, mjm.nbody, mjm.njnt

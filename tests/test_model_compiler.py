@@ -132,3 +132,25 @@ def test_reduced_model_is_consistent(flat):
         jp, jr = mjcf.jac_point(flat, fk, b, com)
         M += d.mass[k] * jp.T @ jp + jr.T @ (R @ Ib @ R.T) @ jr
     np.testing.assert_allclose(M, flat.M0, atol=1e-16, rtol=1e-12)
+
+
+@pytest.mark.parametrize("which", ["joint", "mocap"])
+def test_live_mjmodel_loader_path_executes(which):
+    """north_star subsystem 1 ("takes the reference's compiled mjModel"): `flatmodel_from_mjmodel` + `diff_flatmodels` + the
+    flattening into the device descriptor, executed against an MjModel-shaped stand-in (tests/fake_mujoco.py)."""
+    import ctypes
+
+    import fake_mujoco
+    from mycobotgym_b200 import flatten, mjcf
+
+    compiled = mjcf.load_compiled(mjcf.COMPILED_MOCAP if which == "mocap" else mjcf.COMPILED_JOINT)
+    mjm = fake_mujoco.model_from_flat(compiled)
+    assert mjm.ngeom == compiled["ngeom"] + 3                       # mesh geoms are present in the "live" model ...
+    live = mjcf.flatmodel_from_mjmodel(mjm, mujoco=fake_mujoco)
+    assert live["ngeom"] == compiled["ngeom"] and live["geom_names"] == compiled["geom_names"]      # ... and dropped by the loader
+    assert mjcf.diff_flatmodels(compiled, live) == {}
+    a, b = flatten.reduce_model(compiled), flatten.reduce_model(live)
+    assert bytes(ctypes.string_at(ctypes.addressof(a), ctypes.sizeof(a))) == bytes(ctypes.string_at(ctypes.addressof(b), ctypes.sizeof(b)))
+    # the diff tool does flag a wrong field
+    live["body_mass"] = live["body_mass"] * 1.01
+    assert "body_mass" in mjcf.diff_flatmodels(compiled, live)
