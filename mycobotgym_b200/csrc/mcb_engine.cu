@@ -76,7 +76,10 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 
 struct PairParam {
   int g1, g2, dim, ptype;  // ptype: 0 rows touch robot dofs only, 1 cube dofs only, 2 both
-  double friction[3], solref[2], solimp[5], tran, rot;
+  double friction[3];
+  double KB[2];            // on the device: (K, B) of mj_makeImpedance (the host fills the mixed solref here first, row_constants() converts)
+  double solimp[5];        // clamped once at model creation
+  double tran, pyr2;       // body_invweight0 sum (translational), 2 mu^2 / impratio (the pyramid's regulariser scale)
 };
 
 struct DevModel {
@@ -791,7 +794,15 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
   // Sutherland-Hodgman against |x| <= hx, |y| <= hy: lane i handles the polygon edge (i, i+1)
   const double hx = sr[r1], hy = sr[r2];
   int n = 4;
-  for (int side = 0; side < 4; side++) {
+  // the common case (the cube resting on the table, a pad flat on the cube): all four vertices of the incident face pass all four
+  // half-plane tests, so every clipping pass would copy the polygon unchanged -- skip the passes (same tests, same tolerance)
+  bool allin;
+  {
+    bool in = true;
+    if (lane < 4) { const double x = cs[CS_PX + lane], y = cs[CS_PY + lane]; in = (hx - x >= -1e-12) && (hx + x >= -1e-12) && (hy - y >= -1e-12) && (hy + y >= -1e-12); }
+    allin = __all_sync(FULLMASK, in);
+  }
+  for (int side = 0; side < (allin ? 0 : 4); side++) {
     const double* px = cs + ((side & 1) ? CS_QX : CS_PX);
     const double* py = cs + ((side & 1) ? CS_QY : CS_PY);
     double* qx = cs + ((side & 1) ? CS_PX : CS_QX);
@@ -843,7 +854,9 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
   }
   // duplicates: a point within 1e-10 of an earlier penetrating point is dropped
   bool dup = false;
-  for (int e = 0; e < 15; e++) {
+  // (an unclipped face with edges longer than 2e-9 has four vertices that are pairwise farther apart than the 1e-10 test radius)
+  const bool distinct = allin && si[i1] > 1e-9 && si[i2] > 1e-9;
+  for (int e = 0; e < (distinct ? 0 : 15); e++) {
     double ex = __shfl_sync(FULLMASK, pt[0], e), ey = __shfl_sync(FULLMASK, pt[1], e), ez = __shfl_sync(FULLMASK, pt[2], e);
     int ev = __shfl_sync(FULLMASK, (int)valid, e);
     if (e < lane && ev) { double qx_ = pt[0] - ex, qy_ = pt[1] - ey, qz_ = pt[2] - ez; if (qx_ * qx_ + qy_ * qy_ + qz_ * qz_ < 1e-20) dup = true; }
@@ -908,9 +921,10 @@ __device__ __noinline__ void collide(S& s, int lane, int nba) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ double impedance(const double* solimp_in, double pos) {
-  double s0 = fmin(MAXIMP, fmax(MINIMP, solimp_in[0])), s1 = fmin(MAXIMP, fmax(MINIMP, solimp_in[1]));
-  double s2 = fmax(0.0, solimp_in[2]), s3 = fmin(MAXIMP, fmax(MINIMP, solimp_in[3])), s4 = fmax(1.0, solimp_in[4]);
+// solimp arrives clamped (mcb_model_create applies getimpedance's limits once: d0, d1, midpoint in [MINIMP, MAXIMP], width >= 0,
+// power >= 1)
+__device__ double impedance(const double* solimp, double pos) {
+  const double s0 = solimp[0], s1 = solimp[1], s2 = solimp[2], s3 = solimp[3], s4 = solimp[4];
   if (s0 == s1 || s2 <= MINVAL) return 0.5 * (s0 + s1);
   double x = fabs(pos / s2);
   if (x >= 1 || x <= 0) return (x >= 1 ? s1 : s0);
@@ -1023,39 +1037,38 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   }
   unsigned bal = __ballot_sync(FULLMASK, lim);
   const int nU = __popc(bal);
-  // row bookkeeping (lane 0): contacts -> groups
-  if (lane == 0) {
-    int nRc = 0, nC = 0, nF = 0, nc = s.ncon;
-    for (int c = 0; c < nc; c++) {
-      const PairParam& pp = MDL.pair[s.cpair[c]];
-      int rows = 2 * (pp.dim - 1);
-      if (pp.ptype == 0) nRc += rows; else if (pp.ptype == 1) nC += rows; else nF += rows;
-    }
+  // row bookkeeping: contacts -> groups.  Lane c owns contact c; group sizes and the contacts' first rows are prefix counts
+  // over ballots (a contact has 4 or 6 rows); lane 0 only steps in when the layout overflows.
+  {
     const int ne0 = MDL.d.has_weld ? 13 : 7;
-    int nR = ne0 + nRc;
+    int nc = s.ncon;
+    int pt = -1, rows = 0;
+    if (lane < nc) { const PairParam& pp = MDL.pair[s.cpair[lane]]; pt = pp.ptype; rows = 2 * (pp.dim - 1); }
+    unsigned m0 = __ballot_sync(FULLMASK, pt == 0), m1 = __ballot_sync(FULLMASK, pt == 1), m2 = __ballot_sync(FULLMASK, pt == 2);
+    unsigned m6 = __ballot_sync(FULLMASK, rows == 6);
+    auto count = [&](unsigned m) { return 4 * __popc(m) + 2 * __popc(m & m6); };
+    int nRc = count(m0), nC = count(m1), nF = count(m2), nR = ne0 + nRc;
     bool fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
     if (!fits) {
       // drop contacts from the end until it fits (tiers 0 and 1 abort the env instead, see the kernel)
-      s.overflow += 1;
+      if (lane == 0) s.overflow += 1;
       while (nc > 0 && !fits) {
         nc--;
-        const PairParam& pp = MDL.pair[s.cpair[nc]];
-        int rows = 2 * (pp.dim - 1);
-        if (pp.ptype == 0) { nRc -= rows; nR -= rows; } else if (pp.ptype == 1) nC -= rows; else nF -= rows;
+        const unsigned keep = (nc == 0) ? 0u : (FULLMASK >> (32 - nc));
+        m0 &= keep; m1 &= keep; m2 &= keep;
+        nRc = count(m0); nC = count(m1); nF = count(m2); nR = ne0 + nRc;
         fits = (nR + nC + nF + nU <= S::NROW) && (nR * SR + nC * SC + nF * SF <= S::POOL);
       }
-      s.ncon = nc;
+      if (lane == 0) s.ncon = nc;
     }
-    int r0 = ne0, r1 = nR, r2 = nR + nC, orow = ne0 + nU;
-    for (int c = 0; c < nc; c++) {
-      const PairParam& pp = MDL.pair[s.cpair[c]];
-      int rows = 2 * (pp.dim - 1), base;
-      if (pp.ptype == 0) { base = r0; r0 += rows; } else if (pp.ptype == 1) { base = r1; r1 += rows; } else { base = r2; r2 += rows; }
-      s.crow[c] = base;
-      s.cscr[c] = (double)orow;            // collision scratch is free again: contact's first row in MuJoCo's ordering
-      orow += rows;
+    if (lane < nc) {
+      const unsigned lt = (1u << lane) - 1;
+      const unsigned mg = pt == 0 ? m0 : pt == 1 ? m1 : m2;
+      const int start = pt == 0 ? ne0 : pt == 1 ? nR : nR + nC;
+      s.crow[lane] = start + count(mg & lt);
+      s.cscr[lane] = (double)(ne0 + nU + count((m0 | m1 | m2) & lt));   // collision scratch is free again: contact's first row in MuJoCo's ordering
     }
-    s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU;
+    if (lane == 0) { s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU; }
   }
   __syncwarp();
   const int ne0 = MDL.d.has_weld ? 13 : 7, eq0 = ne0 - 7;      // equality rows: [weld (6)] connect (3 + 3) joint coupling (1)
@@ -1176,47 +1189,42 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
   const int nefc = s.nefc;
   for (int r = lane; r < nefc; r += 32) {
     int meta = s.rmeta[r], kind = (meta >> 12) & 7, idx = meta & 0xff, sub = (meta >> 9) & 7;
-    const double *solref, *solimp;
-    double pos, diag, pyr = 0, ipos = -1;     // ipos >= 0: the residual norm the row's impedance is evaluated at (getposdim)
+    const double *solimp, *KB;
+    double pos, diag, pyr2 = 0, ipos = -1;     // ipos >= 0: the residual norm the row's impedance is evaluated at (getposdim)
     if (kind == 0) {
       const double* a1 = s.anchors + (2 * idx) * 3;
       const double* a2 = a1 + 3;
       pos = a1[sub] - a2[sub];
       const double e0 = a1[0] - a2[0], e1 = a1[1] - a2[1], e2 = a1[2] - a2[2];
       ipos = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
-      solref = MDL.d.con_solref[idx]; solimp = MDL.d.con_solimp[idx]; diag = MDL.d.con_diag[idx];
+      KB = MDL.d.con_solref[idx]; solimp = MDL.d.con_solimp[idx]; diag = MDL.d.con_diag[idx];
     } else if (kind == 1) {
       int d1 = MDL.d.jeq_dof1, d2 = MDL.d.jeq_dof2;
       double p1 = s.qpos[d1] - MDL.d.qpos0[d1], dif = s.qpos[d2] - MDL.d.qpos0[d2];
       const double* pc = MDL.d.jeq_polycoef;
       pos = p1 - pc[0] - pc[1] * dif - pc[2] * dif * dif - pc[3] * dif * dif * dif - pc[4] * dif * dif * dif * dif;
-      solref = MDL.d.jeq_solref; solimp = MDL.d.jeq_solimp; diag = MDL.d.jeq_diag;
+      KB = MDL.d.jeq_solref; solimp = MDL.d.jeq_solimp; diag = MDL.d.jeq_diag;
     } else if (kind == 4) {
       pos = s.ik[sub];
       ipos = sqrt(s.ik[0] * s.ik[0] + s.ik[1] * s.ik[1] + s.ik[2] * s.ik[2] + s.ik[3] * s.ik[3] + s.ik[4] * s.ik[4] + s.ik[5] * s.ik[5]);
       // all six rows take the translational inverse weight (2.3.2's mj_diagApprox; pinned by the mocap keyframe, see the oracle)
-      solref = MDL.d.weld_solref; solimp = MDL.d.weld_solimp; diag = MDL.d.weld_diag[0];
+      KB = MDL.d.weld_solref; solimp = MDL.d.weld_solimp; diag = MDL.d.weld_diag[0];
     } else if (kind == 2) {
       double v = s.qpos[idx];
       pos = (meta & 0x100) ? MDL.d.jnt_range[idx][1] - v : v - MDL.d.jnt_range[idx][0];
-      solref = MDL.d.jnt_solref[idx]; solimp = MDL.d.jnt_solimp[idx]; diag = MDL.d.dof_invweight0[idx];
+      KB = MDL.d.jnt_solref[idx]; solimp = MDL.d.jnt_solimp[idx]; diag = MDL.d.dof_invweight0[idx];
     } else {
       const PairParam& pp = MDL.pair[s.cpair[idx]];
       double mu = pp.friction[0];
       pos = s.cdist[idx];
-      solref = pp.solref; solimp = pp.solimp;
+      KB = pp.KB; solimp = pp.solimp;
       diag = pp.tran + mu * mu * pp.tran;     // the pyramid's first-row diagApprox; all rows share R = 2 mu^2 R_first
-      pyr = mu / sqrt(MDL.d.impratio);
+      pyr2 = pp.pyr2;
     }
-    double sr0 = solref[0], sr1 = solref[1];
-    if (sr0 > 0) sr0 = fmax(sr0, 2 * h);
     double imp = impedance(solimp, ipos >= 0 ? ipos : pos);
     double R = fmax(MINVAL, (1 - imp) * diag / imp);
-    if (pyr > 0) R = 2 * pyr * pyr * R;
-    double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
-    double K, B;
-    if (sr0 > 0) { K = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmax(MINVAL, dmax * sr0); }
-    else { K = -sr0 / fmax(MINVAL, dmax * dmax); B = -sr1 / fmax(MINVAL, dmax); }
+    if (pyr2 > 0) R = pyr2 * R;
+    const double K = KB[0], B = KB[1];
     double vel = row_dot(s, r, s.qvel);
     s.eD[r] = 1 / R;
     s.earef[r] = -B * vel - K * imp * pos;
@@ -2455,13 +2463,40 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
     else if (sa < MINVAL && sb < MINVAL) mix = 0.5;
     else if (sa < MINVAL) mix = 0.0; else mix = 1.0;
     const double *ra = d->geom_solref[g1], *rb = d->geom_solref[g2];
-    if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) pp.solref[k] = mix * ra[k] + (1 - mix) * rb[k];
-    else for (int k = 0; k < 2; k++) pp.solref[k] = fmin(ra[k], rb[k]);
+    if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) pp.KB[k] = mix * ra[k] + (1 - mix) * rb[k];
+    else for (int k = 0; k < 2; k++) pp.KB[k] = fmin(ra[k], rb[k]);
     for (int k = 0; k < 5; k++) pp.solimp[k] = mix * d->geom_solimp[g1][k] + (1 - mix) * d->geom_solimp[g2][k];
     { int b1 = d->geom_body[g1], b2 = d->geom_body[g2]; bool c1 = b1 == CUBE, c2 = b2 == CUBE, r1 = b1 >= 0 && !c1, r2 = b2 >= 0 && !c2;
       pp.ptype = ((c1 || c2) && (r1 || r2)) ? 2 : ((c1 || c2) ? 1 : 0); }
     pp.tran = d->geom_invweight[g1][0] + d->geom_invweight[g2][0];
-    pp.rot = d->geom_invweight[g1][1] + d->geom_invweight[g2][1];
+  }
+  // row constants of mj_makeImpedance that do not depend on the state: solimp clamped once, (K, B) from solref (refsafe applied).
+  // In the DEVICE copy of the model every *_solref pair is overwritten with its (K, B) -- the kernels never need the raw solref.
+  {
+    auto clamp_solimp = [](double* si) {
+      si[0] = fmin(MAXIMP, fmax(MINIMP, si[0])); si[1] = fmin(MAXIMP, fmax(MINIMP, si[1])); si[2] = fmax(0.0, si[2]);
+      si[3] = fmin(MAXIMP, fmax(MINIMP, si[3])); si[4] = fmax(1.0, si[4]);
+    };
+    const double hstep = h.d.timestep;
+    auto row_constants = [hstep](double* solref_to_KB, const double* solimp_clamped) {
+      double* KB = solref_to_KB;
+      double sr0 = KB[0], sr1 = KB[1];
+      if (sr0 > 0) sr0 = fmax(sr0, 2 * hstep);
+      const double dmax = solimp_clamped[1];
+      if (sr0 > 0) { KB[0] = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); KB[1] = 2 / fmax(MINVAL, dmax * sr0); }
+      else { KB[0] = -sr0 / fmax(MINVAL, dmax * dmax); KB[1] = -sr1 / fmax(MINVAL, dmax); }
+    };
+    for (int e = 0; e < 2; e++) { clamp_solimp(h.d.con_solimp[e]); row_constants(h.d.con_solref[e], h.d.con_solimp[e]); }
+    clamp_solimp(h.d.jeq_solimp); row_constants(h.d.jeq_solref, h.d.jeq_solimp);
+    clamp_solimp(h.d.weld_solimp); row_constants(h.d.weld_solref, h.d.weld_solimp);
+    for (int j = 0; j < NH; j++) { clamp_solimp(h.d.jnt_solimp[j]); row_constants(h.d.jnt_solref[j], h.d.jnt_solimp[j]); }
+    for (int p = 0; p < d->npair; p++) {
+      PairParam& pp = h.pair[p];
+      clamp_solimp(pp.solimp);
+      row_constants(pp.KB, pp.solimp);
+      const double pyr = pp.friction[0] / sqrt(h.d.impratio);
+      pp.pyr2 = 2 * pyr * pyr;
+    }
   }
   cudaError_t ce = cudaMalloc(&m->dev, sizeof(DevModel));
   if (ce == cudaSuccess) ce = cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice);
