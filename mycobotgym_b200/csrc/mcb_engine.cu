@@ -845,7 +845,8 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
     double x = cs[CS_PX + lane], y = cs[CS_PY + lane];
     double dx = x - fx, dy = y - fy, h;
     if (fabs(det) > 1e-12) {
-      double al = (dx * a22 - dy * a21) / det, be = (dy * a11 - dx * a12) / det;
+      const double idet = det < 0 ? -fast_rcp(-det) : fast_rcp(det);
+      double al = (dx * a22 - dy * a21) * idet, be = (dy * a11 - dx * a12) * idet;
       h = o_n + al * u1 + be * u2;
     } else h = o_n;
     depth = sr[ax] - h;
@@ -921,16 +922,17 @@ __device__ __noinline__ void collide(S& s, int lane, int nba) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// solimp arrives clamped (mcb_model_create applies getimpedance's limits once: d0, d1, midpoint in [MINIMP, MAXIMP], width >= 0,
-// power >= 1)
+// solimp arrives clamped (mcb_model_create applies getimpedance's limits once: d0, d1, midpoint in [MINIMP, MAXIMP], power >= 1)
+// and with slot 2 holding 1 / width (0 for a width <= MINVAL): IEEE divisions are ~30 dependent instructions each and sat in
+// series on every row's critical path (pos / width, then 1 / midpoint); reciprocals by fast_rcp() differ by <= 1 ulp.
 __device__ double impedance(const double* solimp, double pos) {
-  const double s0 = solimp[0], s1 = solimp[1], s2 = solimp[2], s3 = solimp[3], s4 = solimp[4];
-  if (s0 == s1 || s2 <= MINVAL) return 0.5 * (s0 + s1);
-  double x = fabs(pos / s2);
+  const double s0 = solimp[0], s1 = solimp[1], iw = solimp[2], s3 = solimp[3], s4 = solimp[4];
+  if (s0 == s1 || iw == 0.0) return 0.5 * (s0 + s1);
+  double x = fabs(pos * iw);
   if (x >= 1 || x <= 0) return (x >= 1 ? s1 : s0);
   double y;
   if (s4 == 1) y = x;
-  else if (s4 == 2) { y = (x <= s3) ? (1 / s3) * (x * x) : 1 - (1 / (1 - s3)) * ((1 - x) * (1 - x)); }   // pow(v, 2) == v * v, pow(v, 1) == v
+  else if (s4 == 2) { y = (x <= s3) ? fast_rcp(s3) * (x * x) : 1 - fast_rcp(1 - s3) * ((1 - x) * (1 - x)); }   // pow(v, 2) == v * v, pow(v, 1) == v
   else if (x <= s3) { double a = 1 / pow(s3, s4 - 1); y = a * pow(x, s4); }
   else { double b = 1 / pow(1 - s3, s4 - 1); y = 1 - b * pow(1 - x, s4); }
   return s0 + y * (s1 - s0);
@@ -1222,11 +1224,11 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       pyr2 = pp.pyr2;
     }
     double imp = impedance(solimp, ipos >= 0 ? ipos : pos);
-    double R = fmax(MINVAL, (1 - imp) * diag / imp);
+    double R = fmax(MINVAL, (1 - imp) * diag * fast_rcp(imp));      // imp in [MINIMP, MAXIMP]
     if (pyr2 > 0) R = pyr2 * R;
     const double K = KB[0], B = KB[1];
     double vel = row_dot(s, r, s.qvel);
-    s.eD[r] = 1 / R;
+    s.eD[r] = fast_rcp(R);
     s.earef[r] = -B * vel - K * imp * pos;
   }
   __syncwarp();
@@ -1500,7 +1502,7 @@ struct Newton {
     warp_sum3(sn, g1, g2, lane);
     const double snorm = sqrt(sn);
     if (snorm < MINVAL) return 0;
-    double gtol = MDL.d.tolerance * MDL.d.ls_tolerance * snorm / scale;
+    double gtol = MDL.d.tolerance * MDL.d.ls_tolerance * snorm * (MDL.d.meaninertia * (double)NV);   // 1 / scale
     rows_times(s.search, s.eJv, false);
     qg0 = gauss; qg1 = g1; qg2 = 0.5 * g2;
     __syncwarp();
@@ -1515,19 +1517,19 @@ struct Newton {
     const int lsmax = MDL.d.ls_iterations;
     Pt p0, p1, p2, pmid, p1n, p2n;
     p0.alpha = 0; ls_eval(p0);
-    p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(p1);
+    p1.alpha = p0.alpha - p0.d0 * fast_rcp(p0.d1); ls_eval(p1);
     if (p0.cost < p1.cost) p1 = p0;
     if (fabs(p1.d0) < gtol) return p1.alpha;
     int dir = p1.d0 < 0 ? 1 : -1, iter = 0, p2update = 0;
     p2 = p1;
     while (p1.d0 * dir <= -gtol && iter < lsmax) {
       p2 = p1; p2update = 1;
-      p1.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1); iter++;
+      p1.alpha = p1.alpha - p1.d0 * fast_rcp(p1.d1); ls_eval(p1); iter++;
       if (fabs(p1.d0) < gtol) return p1.alpha;
     }
     if (iter >= lsmax || !p2update) return p1.alpha;
     p2n = p1;
-    p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n);
+    p1n.alpha = p1.alpha - p1.d0 * fast_rcp(p1.d1); ls_eval(p1n);
     while (iter < lsmax) {
       pmid.alpha = 0.5 * (p1.alpha + p2.alpha); ls_eval(pmid); iter++;
       // candidates in the order p1next, p2next, midpoint
@@ -1545,14 +1547,14 @@ struct Newton {
       { Pt c = pmid; LS_BRACKET(c) }
 #undef LS_BRACKET
       if (!b1 && !b2) break;
-      if (b1) { p1n.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(p1n); }
-      if (b2) { p2n.alpha = p2.alpha - p2.d0 / p2.d1; ls_eval(p2n); }
+      if (b1) { p1n.alpha = p1.alpha - p1.d0 * fast_rcp(p1.d1); ls_eval(p1n); }
+      if (b2) { p2n.alpha = p2.alpha - p2.d0 * fast_rcp(p2.d1); ls_eval(p2n); }
     }
     return (p1.cost < p2.cost ? p1.alpha : p2.alpha);
   }
 
   __device__ __forceinline__ void solve() {
-    const double scale = 1.0 / (MDL.d.meaninertia * (double)NV);
+    const double scale = fast_rcp(MDL.d.meaninertia * (double)NV);
     coupled = s.nF > 0;
     // warmstart(): better of qacc_warmstart and qacc_smooth.  jar(warm) -> eJaref, jar(smooth) -> eJv
     double cw = 0, cs = 0;      // constraint cost of the two candidates, accumulated while their residuals are formed
@@ -1593,8 +1595,9 @@ struct Newton {
       iter++;
       double gn = 0;
       if (lane < nva) gn = s.grad[lane] * s.grad[lane];
-      double improvement = scale * (oldcost - cost), gradient = scale * sqrt(warp_sum(gn));
-      if (improvement < MDL.d.tolerance || gradient < MDL.d.tolerance) break;
+      // gradient norm test on squares: scale * sqrt(gn) < tolerance  <=>  scale^2 gn < tolerance^2 (no sqrt on the critical path)
+      double improvement = scale * (oldcost - cost), grad2 = scale * scale * warp_sum(gn);
+      if (improvement < MDL.d.tolerance || grad2 < MDL.d.tolerance * MDL.d.tolerance) break;
       newton_direction();
     }
     if (lane == 0) s.iters += iter;
@@ -2474,7 +2477,7 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   // In the DEVICE copy of the model every *_solref pair is overwritten with its (K, B) -- the kernels never need the raw solref.
   {
     auto clamp_solimp = [](double* si) {
-      si[0] = fmin(MAXIMP, fmax(MINIMP, si[0])); si[1] = fmin(MAXIMP, fmax(MINIMP, si[1])); si[2] = fmax(0.0, si[2]);
+      si[0] = fmin(MAXIMP, fmax(MINIMP, si[0])); si[1] = fmin(MAXIMP, fmax(MINIMP, si[1])); si[2] = fmax(0.0, si[2]) <= MINVAL ? 0.0 : 1.0 / si[2];   // slot 2: 1 / width
       si[3] = fmin(MAXIMP, fmax(MINIMP, si[3])); si[4] = fmax(1.0, si[4]);
     };
     const double hstep = h.d.timestep;
