@@ -2014,7 +2014,7 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 #endif
 #define WPB_MID 10
 template <int TIER>
-__global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * WPB_MID : 32, TIER == 2 ? 5 : 1) mcb_env_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * WPB_MID : 32, TIER == 2 ? 5 : 1) mcb_env_kernel(const __grid_constant__ StepArgs a) {   // (reset_env takes the arguments by reference: without __grid_constant__ the whole struct is copied to the stack)
   typedef EnvS<TIER> S;
   constexpr bool BIG = TIER == 2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -30,3 +30,25 @@ for vals in rows[2:]:
     print("   warp-state samples:")
     for v, k in sorted(out, reverse=True)[:9]:
         print(f"      {100 * v / tot:5.1f}%  {k.replace('smsp__pcsamp_warps_issue_stalled_', '')}")
+
+# --traffic <workload:envs> <traffic.json> <source label>: record dram__bytes_read.sum + dram__bytes_write.sum of the step
+# kernel's launch in profiles/traffic.json, where bench.py reads `roofline.traffic` from (no literals in bench.py)
+if "--traffic" in sys.argv:
+    import json
+    import os
+
+    i = sys.argv.index("--traffic")
+    key, path, label = sys.argv[i + 1], sys.argv[i + 2], sys.argv[i + 3]
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals))
+        if "mcb_env_kernel<(int)0>" not in d.get("Kernel Name", "") and "mcb_env_kernel<0>" not in d.get("Kernel Name", ""):
+            continue
+        rd = float(d["dram__bytes_read.sum"]) * unit[rows[1][hdr.index("dram__bytes_read.sum")]]
+        wr = float(d["dram__bytes_write.sum"]) * unit[rows[1][hdr.index("dram__bytes_write.sum")]]
+        table = json.load(open(path)) if os.path.exists(path) else {}
+        table[key] = {"bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": label,
+                      "kernel_ms": float(d["gpu__time_duration.sum"])}
+        json.dump(table, open(path, "w"), indent=1)
+        print("traffic", key, table[key])
+        break
