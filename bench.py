@@ -230,7 +230,7 @@ def run_ours(args):
         env.set_state(qpos=rep(g["qpos0"]), qvel=qvel, ctrl=rep(g["ctrl0"]), qacc_warmstart=rep(g["warm0"]), goal=rep(g["goal"]),
                       elapsed=torch.zeros(n, dtype=torch.int32), qprev=rep(g["qpos0"][:6]))
         acts = torch.zeros(K + W, n, env.action_dim, device=dev)
-        acts[:, :, :6] = torch.as_tensor(g["qpos0"][:6], device=dev, dtype=torch.float32) + 0.02 * (torch.rand(K + W, n, 6, device=dev, generator=gen) * 2 - 1)
+        acts[:, :, :6] = torch.as_tensor(g["qpos0"][:6], device=dev, dtype=torch.float32) + float(os.environ.get("MCB_GRASP_NOISE", "0.002")) * (torch.rand(K + W, n, 6, device=dev, generator=gen) * 2 - 1)
         acts[:, :, 6] = 0.8
         args.preroll = 0
         env.autotune(acts[0])

@@ -2013,12 +2013,13 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
 #define ENV_LB_THREADS (32 * WPB_SMALL)      // register budget of the common-layout kernel = 65536 / ENV_LB_THREADS (tuning knob)
 #endif
 #define WPB_MID 10
+#define WPB_BIG 5       // last tier: five envs per CTA (one CTA per SM), so that they can run in lockstep like the other tiers
 template <int TIER>
-__global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * WPB_MID : 32, TIER == 2 ? 5 : 1) mcb_env_kernel(const __grid_constant__ StepArgs a) {   // (reset_env takes the arguments by reference: without __grid_constant__ the whole struct is copied to the stack)
+__global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * WPB_MID : 32 * WPB_BIG, 1) mcb_env_kernel(const __grid_constant__ StepArgs a) {   // (reset_env takes the arguments by reference: without __grid_constant__ the whole struct is copied to the stack)
   typedef EnvS<TIER> S;
   constexpr bool BIG = TIER == 2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int wpb = TIER == 0 ? WPB_SMALL : TIER == 1 ? WPB_MID : 1;
+  const int wpb = TIER == 0 ? WPB_SMALL : TIER == 1 ? WPB_MID : WPB_BIG;
   S& s = *reinterpret_cast<S*>(smem_raw + MODEL_BYTES + (size_t)wid * sizeof(S));
   const DevModel* __restrict__ m = a.m;
   {  // stage the model (global -> shared), once per CTA
@@ -2046,13 +2047,15 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
     if (blockIdx.x == 0 && threadIdx.x == 0) a.redo_count[1] = nwork;
     return;
   }
-  const int lockstep = (TIER == 0 && a.lockstep_warps > 1) ? a.lockstep_warps : 0;
+  // the middle tier follows the batch's grouping when it is the whole CTA (its ten warps then share instruction-cache lines the
+  // same way; sub-groups would not divide ten warps evenly), and so do the five warps of a last-tier CTA
+  const int lockstep = (TIER == 0 && a.lockstep_warps > 1) ? a.lockstep_warps : (TIER >= 1 && a.lockstep_warps >= WPB_SMALL_) ? WPB_SMALL_ : 0;
 
   // Tier 0: CTA b takes the 16 consecutive envs [16 b, 16 b + 16).  Tier 1: the list is dealt round-robin over the CTAs
   // (item = slot * gridDim.x + b), so a list shorter than one full wave spreads over all SMs with few warps each instead of
   // filling half of them -- the latency of a pass is set by how many heavy envs share an SM.
-  for (int item0 = TIER == 1 ? 0 : blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
-    const int item = TIER == 1 ? item0 + wid * (int)gridDim.x + (int)blockIdx.x : item0 + wid;
+  for (int item0 = TIER >= 1 ? 0 : blockIdx.x * wpb; item0 < nwork; item0 += gridDim.x * wpb) {
+    const int item = TIER >= 1 ? item0 + wid * (int)gridDim.x + (int)blockIdx.x : item0 + wid;
     bool valid = item < nwork;
     const int env = valid ? (TIER == 0 ? item : work_list[item]) : 0;
     if (valid && a.mode == MODE_RESET && a.mask && !a.mask[env]) valid = false;
@@ -2401,7 +2404,7 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   if (!b->big_only) mcb_env_kernel<1><<<b->mid_only ? (b->n_envs + WPB_MID - 1) / WPB_MID : b->mid_grid, 32 * WPB_MID, b->smem_mid, st>>>(a);
   CK(cudaGetLastError());
   // ... and the few that overflowed the middle one
-  mcb_env_kernel<2><<<b->big_only ? b->n_envs : b->big_grid, 32, b->smem_big, st>>>(a);
+  mcb_env_kernel<2><<<b->big_only ? (b->n_envs + WPB_BIG - 1) / WPB_BIG : b->big_grid / WPB_BIG, 32 * WPB_BIG, b->smem_big, st>>>(a);
   CK(cudaGetLastError());
   return 0;
 }
@@ -2409,10 +2412,10 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
 extern "C" {
 
 const char* mcb_version(void) {
-  static char buf[256];
-  snprintf(buf, sizeof buf, "mycobot_b200 0.4 (sm_100a; shared memory per env: %zu B common layout (16 per CTA), %zu B middle tier (%d per CTA), %zu B last tier; model %zu B; CTAs %zu / %zu / %zu B)",
-           sizeof(EnvS<0>), sizeof(EnvS<1>), WPB_MID, sizeof(EnvS<2>), (size_t)MODEL_BYTES, (size_t)(MODEL_BYTES + sizeof(EnvS<0>) * WPB_SMALL),
-           (size_t)(MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID), (size_t)(MODEL_BYTES + sizeof(EnvS<2>)));
+  static char buf[320];
+  snprintf(buf, sizeof buf, "mycobot_b200 0.5 (sm_100a; shared memory per env: %zu B common layout (16 per CTA), %zu B middle tier (%d per CTA), %zu B last tier (%d per CTA); model %zu B; CTAs %zu / %zu / %zu B)",
+           sizeof(EnvS<0>), sizeof(EnvS<1>), WPB_MID, sizeof(EnvS<2>), WPB_BIG, (size_t)MODEL_BYTES, (size_t)(MODEL_BYTES + sizeof(EnvS<0>) * WPB_SMALL),
+           (size_t)(MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID), (size_t)(MODEL_BYTES + sizeof(EnvS<2>) * WPB_BIG));
   return buf;
 }
 const char* mcb_last_error(void) { return g_err.c_str(); }
@@ -2535,16 +2538,17 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   b->mid_only = cfg->nefc_max == 88;
   b->smem_small = MODEL_BYTES + sizeof(EnvS<0>) * WPB_SMALL;
   b->smem_mid = MODEL_BYTES + sizeof(EnvS<1>) * WPB_MID;
-  b->smem_big = MODEL_BYTES + sizeof(EnvS<2>);
+  b->smem_big = MODEL_BYTES + sizeof(EnvS<2>) * WPB_BIG;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete b; return fail("mcb_batch_create: cudaGetDeviceProperties", cudaGetLastError()); }
-  b->big_grid = prop.multiProcessorCount * 5;      // five one-warp CTAs of the last tier are resident per SM (44.5 KB each)
+  b->big_grid = prop.multiProcessorCount * WPB_BIG;      // envs of one last-tier wave: one five-warp CTA per SM
   b->mid_grid = prop.multiProcessorCount;
   cudaError_t e = cudaFuncSetAttribute(mcb_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_small);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_mid);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_big);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mcb_env_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { delete b; return fail("cudaFuncSetAttribute(shared memory)", e); }
   size_t N = (size_t)n_envs;
   // partial allocations are released on failure (mcb_batch_destroy frees whatever is non-null)
