@@ -122,3 +122,84 @@ def test_one_step_from_rollout_states_at_baseline_size(workload):
     print(f"\n{workload}: {len(chosen)} envs compared ({len(left)} left the common layout, {nfree} contact-free), "
           f"sensitivity-scaled bound used by {hatch}; worst |gpu - oracle| {worst}")
     assert hatch <= max(1, len(chosen) // 50), f"{hatch} of {len(chosen)} envs needed the sensitivity-scaled bound"
+
+
+CTRL = {
+    "ik": (dict(has_object=True, reward_type="sparse", controller_type="IK"), 7, 6),
+    "mocap": (dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml"), 8, 12),
+}
+
+
+@pytest.mark.parametrize("workload", ["ik", "mocap"])
+def test_one_step_from_rollout_states_ik_and_mocap(workload):
+    """The same check for the other two controllers (16384 envs): rollout, then one step of 96 random envs plus up to 96 envs that
+    left the common layout (about 4 % of these batches press the gripper onto the table).  The oracle is started from the GPU
+    state INCLUDING the stale frames the reference's controllers read (kinematics at qprev) and the mocap pose.  An IK step is
+    100 substeps of the bang-bang actuators: the bound is the with-contact 1e-5 or, where it is smaller, 1e-7 /
+    100x what a one-ulp perturbation of the arm velocities plus the Newton stopping tolerance move the oracle itself."""
+    from mycobotgym_b200 import mjcf
+    from mycobotgym_b200.vector_env import MyCobotVectorEnv
+    from oracle.oracle import OracleEnv
+
+    kw, adim, roll = CTRL[workload]
+    okw = {k: v for k, v in kw.items() if k != "model_path"}
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP if workload == "mocap" else mjcf.COMPILED_JOINT)
+    tight = mjcf.FlatModel(fm)
+    tight["tolerance"] = 1e-13
+    n = 16384
+    env = MyCobotVectorEnv(num_envs=n, seed=5, autotune=False, lockstep_warps=16, **kw)
+    env.reset()
+    env.set_state(elapsed=torch.arange(n, dtype=torch.int32) % 50)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    for _ in range(roll):
+        env.step(torch.rand(n, adim, device="cuda", generator=gen) * 2 - 1)
+    st_t = env.get_state()
+    st = {k: v.cpu().numpy() for k, v in st_t.items()}
+    acts_t = torch.rand(n, adim, device="cuda", generator=gen) * 2 - 1
+    acts = acts_t.cpu().numpy()
+    env.close()
+    env2 = MyCobotVectorEnv(num_envs=n, auto_reset=False, autotune=False, lockstep_warps=16, **kw)
+    env2.set_state(**{k: st_t[k] for k in ("qpos", "qvel", "ctrl", "qacc_warmstart", "goal", "elapsed", "qprev", "mocap")})
+    obs, rew, term, trunc, info = env2.step(acts_t)
+    left = env2.last_fallback_list()
+    after = {k: v.cpu().numpy() for k, v in env2.get_state().items()}
+    obs_np = obs["observation"].cpu().numpy()
+    rew_np, term_np = rew.cpu().numpy(), term.cpu().numpy()
+    dropped = env2.stats().cpu().numpy()[5]
+    env2.close()
+    nu = 1 if workload == "mocap" else 7
+
+    def start(f, i, ulp=False):
+        oe = OracleEnv(f, **okw)
+        q_stale = st["qpos"][i].copy()
+        q_stale[:6] = st["qprev"][i]
+        oe.sim.set_state(q_stale, st["qvel"][i], st["ctrl"][i][:nu], st["qacc_warmstart"][i])
+        oe.sim.mocap_pos[:], oe.sim.mocap_quat[:] = st["mocap"][i][:3], st["mocap"][i][3:]
+        oe.sim.kinematics()                       # the frames the reference still holds from its last mj_step
+        oe.sim.qpos[:] = st["qpos"][i]
+        if ulp:
+            oe.sim.qvel[:6] *= 1 + 2.2e-16
+        oe.goal = st["goal"][i].copy()
+        oe.elapsed = int(st["elapsed"][i])
+        return oe
+
+    rng = np.random.default_rng(9)
+    chosen = sorted(set(rng.choice(n, 96, replace=False).tolist()) | set(left[:96].tolist()))
+    worst, loose, failures = 0.0, 0, []
+    for i in chosen:
+        oe, oe2 = start(fm, i), start(tight, i, ulp=True)
+        o, r, te, tr, inf = oe.step(acts[i])
+        oe2.step(acts[i])
+        sens = np.abs(oe2.sim.qpos - oe.sim.qpos).max()
+        tol = min(max(1e-7, 100 * sens), TOL_CONTACT)
+        eq = np.abs(after["qpos"][i] - oe.sim.qpos).max()
+        eo = np.abs(obs_np[i] - o["observation"]).max()
+        if max(eq, eo) > tol:
+            failures.append((i, float(eq), float(eo), float(sens)))
+        worst = max(worst, eq)
+        loose += tol > 1e-7
+        assert bool(term_np[i]) == te
+    print(f"\n{workload}: {len(chosen)} envs compared ({len(left)} left the common layout, rows dropped in the last tier: {dropped}), "
+          f"worst |qpos gpu - oracle| {worst:.2e}, {loose} envs with a sensitivity-scaled bound above 1e-7")
+    assert not failures, f"{workload}: {len(failures)} of {len(chosen)} out of bounds (env, qpos, obs, one-ulp sensitivity): {failures[:8]}"
