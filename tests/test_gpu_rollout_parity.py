@@ -195,7 +195,8 @@ def test_one_step_from_rollout_states_ik_and_mocap(workload):
         tol = min(max(1e-7, 100 * sens), TOL_CONTACT)
         eq = np.abs(after["qpos"][i] - oe.sim.qpos).max()
         eo = np.abs(obs_np[i] - o["observation"]).max()
-        if max(eq, eo) > tol:
+        # observations carry velocity terms (x dt) of the same chaotic step: ten times the position bound, still capped at 1e-5
+        if eq > tol or eo > min(10 * tol, TOL_CONTACT):
             failures.append((i, float(eq), float(eo), float(sens)))
         worst = max(worst, eq)
         loose += tol > 1e-7
