@@ -14,6 +14,7 @@ from .flatten import ModelDesc, TaskCfg
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("MCB_LIB") or os.path.join(PKG_DIR, "libmycobot_b200.so")   # MCB_LIB: tuning experiments only
+CANARY_PATH = os.path.join(PKG_DIR, "libmycobot_b200_canary.so")   # -DMCB_CANARY: guard words in the shared-memory records (tests only)
 SRC = os.path.join(PKG_DIR, "csrc", "mcb_engine.cu")
 HDR = os.path.join(ROOT, "include", "mycobot_b200.h")
 DEPS = (SRC, HDR, os.path.join(PKG_DIR, "csrc", "mcb_her.cuh"))
@@ -31,10 +32,11 @@ EXPORTS = [
 ]
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
+def needs_build(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     return any(os.path.exists(p) and os.path.getmtime(p) > t for p in DEPS)
 
 
@@ -48,6 +50,16 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
     return LIB_PATH
+
+
+def build_canary(force=False):
+    """The same source with -DMCB_CANARY (guard words between the arrays of every per-env shared-memory record, checked when the
+    env is stored): the bounds-check build tests/test_gpu_canary.py runs, since compute-sanitizer is closed on the GPU pool."""
+    if not force and not needs_build(CANARY_PATH):
+        return CANARY_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DMCB_CANARY", "-I", os.path.join(ROOT, "include"), "-o", CANARY_PATH, SRC])
+    return CANARY_PATH
 
 
 _lib = None

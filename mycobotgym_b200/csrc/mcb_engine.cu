@@ -41,6 +41,7 @@
 #include <string.h>
 #include <math.h>
 #include <string>
+#include <stdlib.h>
 
 #include "mycobot_b200.h"
 
@@ -127,6 +128,7 @@ struct StepArgs {
   uint8_t *terminated, *truncated, *success;
   double* debug;             // optional debug dump of env debug_env
   int debug_env;
+  int canary_selftest;       // MCB_CANARY build + MCB_CANARY_SELFTEST=1 in the environment: every env writes one double past cpos[] on purpose
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,23 +137,43 @@ struct StepArgs {
 // table (10 envs per CTA); TIER 2: the last resort, one env per CTA, rows beyond its capacity are dropped and counted.
 template <int TIER>
 struct EnvS {
-  enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : 128, POOL = TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432, MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : 16,
+  // MCB_CANARY build (tests/test_gpu_canary.py; compute-sanitizer is closed on the GPU pool): guard words between the arrays of
+  // the record, set when an env is loaded and checked when it is stored; a hit is counted in stats[5] and reported.  The pools
+  // shrink by the guards' size, which only moves the point where an env changes tier (results do not depend on the tier).
+#ifdef MCB_CANARY
+#define GUARD(name) double name[2];
+#define MCB_NGUARD 8
+#else
+#define GUARD(name)
+#define MCB_NGUARD 0
+#endif
+  enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : 128, POOL = (TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432) - (MCB_NGUARD ? (TIER == 0 ? 10 : 2 * MCB_NGUARD) : 0),   // (tier 0: the row arrays must stay the union's largest member)
+         MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : 16,
          IS_BIG = TIER == 2 };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
+  GUARD(g0)
   double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
-  double M[NTRI + 1], H[NTRIP];          // H doubles as the factor storage of chol_solve_blk (padded rows, TRIP)
+  GUARD(g1)
+  double M[NTRI + 1];
+  GUARD(g2)
+  double H[NTRIP];          // H doubles as the factor storage of chol_solve_blk (padded rows, TRIP)
+  GUARD(g3)
   double qfrc_bias[NV], qfrc_smooth[NV], qacc_smooth[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], qfrc_con[NV];
+  GUARD(g4)
   double anchors[12];
   double qprev[6];   // arm qpos the frames in shared memory were computed from (the reference's stale site poses)
   double ik[14];     // IK controller: target position (3), target quaternion (4), pose error (6); mocap variant: weld residual (6)
   double mocap[8];   // mocap variant: data.mocap_pos (3) | data.mocap_quat (4)
   double quat5[4];   // mocap variant: orientation quaternion of the body carrying gripper_tcp (composed like mj_kinematics)
+  GUARD(g5)
   union {
     struct { union { double lR[NB * 9]; double buf[NV * 6]; }; double cinert[NB * 10], crb[NB * 10], cvel[NB * 6], cacc[NB * 6], cdof_dot[NV * 6]; };  // dead after velocity_rne (lR after fk)
     struct { double pool[POOL], eD[NROW], earef[NROW], eJaref[NROW], eJv[NROW]; };                                              // live from make_rows
     double cscr[152];                                                                                                           // collision scratch (between the two)
   };
+  GUARD(g6)
   double cdist[MAXC], cpos[MAXC * 3], cframe[MAXC * 9];
+  GUARD(g7)
   int cpair[MAXC], crow[MAXC];
   int rmeta[NROW];   // bits 0-7 index (eq / contact / dof), 8 sign, 9-11 sub-row, 12-14 kind (0 connect 1 joint-eq 2 limit 3 contact 4 weld), 16 inequality
   int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
@@ -1021,7 +1043,6 @@ __device__ __forceinline__ void row_dot2(S& s, int r, const double* v, const dou
 // and the reference acceleration of every row.  Returns false if the layout's capacity is exceeded.
 template <class S>
 __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nva) {
-  const double h = MDL.d.timestep;
   // connect anchors (lanes 0..3: constraint e = lane>>1, side = lane&1)
   if (lane < 4) {
     int e = lane >> 1, side = lane & 1;
@@ -2068,6 +2089,9 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
     for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
     if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; s.search[lane] = 0; s.Mv[lane] = 0; }
     if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = MDL.d.has_weld ? 13 : 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
+#ifdef MCB_CANARY
+    if (lane < 2) { const double c = __longlong_as_double(0x7ff8c0decafe0000ll + lane); s.g0[lane] = c; s.g1[lane] = c; s.g2[lane] = c; s.g3[lane] = c; s.g4[lane] = c; s.g5[lane] = c; s.g6[lane] = c; s.g7[lane] = c; }
+#endif
     __syncwarp();
     unsigned long long ctr = 0;
     if (valid) { load_state(s, a.state + (size_t)env * MCB_STATE_STRIDE, lane); ctr = a.rng_ctr[env]; }
@@ -2241,6 +2265,17 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
       }
     }
     __syncwarp();
+#ifdef MCB_CANARY
+    if (a.canary_selftest && lane == 0) s.cframe[S::MAXC * 9] = 1.0;      // one past the end: lands on guard g7
+    __syncwarp();
+    if (lane < 2) {
+      const long long c = 0x7ff8c0decafe0000ll + lane;
+      const double* g[8] = {s.g0, s.g1, s.g2, s.g3, s.g4, s.g5, s.g6, s.g7};
+      for (int k = 0; k < 8; k++)
+        if (__double_as_longlong(g[k][lane]) != c) { atomicAdd(a.stats + 5, 1.0e6); printf("MCB_CANARY: guard %d of env %d (tier %d) was overwritten\n", k, env, TIER); }
+    }
+    __syncwarp();
+#endif
     if (valid) {
       if (!ok) {
         // this tier's layout overflowed: leave the env untouched for the next tier's launch
@@ -2393,6 +2428,9 @@ static int launch(mcb_batch* b, StepArgs& a, cudaStream_t st) {
   a.state = b->state; a.elapsed = b->elapsed; a.ep_return = b->ep_return; a.rng_ctr = b->rng_ctr; a.stats = b->stats;
   a.redo_count = b->redo_count; a.redo_list = b->redo_list;
   a.lockstep_warps = b->lockstep_warps;
+#ifdef MCB_CANARY
+  { const char* st_ = getenv("MCB_CANARY_SELFTEST"); a.canary_selftest = (st_ && st_[0] == '1') ? 1 : 0; }
+#endif
   a.mid_threshold = b->mid_only ? -1 : 2 * b->big_grid;    // up to two waves of the last tier are cheaper than a middle-tier pass (profiles/README.md)
   CK(cudaMemsetAsync(b->redo_count, 0, 2 * sizeof(int), st));
   if (b->big_only) iota_kernel<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->redo_list + b->n_envs, b->redo_count + 1, b->n_envs);
