@@ -138,3 +138,39 @@ def test_mat2euler_roundtrip():
         Ry = np.array([[cy, 0, sy], [0, cy * 0 + 1, 0], [-sy, 0, cy]])
         Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
         np.testing.assert_allclose(mat2euler(Rx @ Ry @ Rz), e, atol=1e-12)  # rotations.euler2mat convention
+
+
+@pytest.mark.parametrize("which", ["joint", "mocap"])
+def test_invweight0_second_opinion_from_the_c_pipeline(which):
+    """body_invweight0 / dof_invweight0 / meaninertia set every constraint's regulariser (the weld's stiffness is
+    body_invweight0[gripper_tcp] directly).  mjcf.set_const computes them with its own numpy FK and mass matrix; here they are
+    recomputed from the C oracle's pipeline at qpos0 -- mj_kinematics / mj_comPos / mj_crb restated in C, mj_jac for the body
+    Jacobians at the inertial frame origins -- i.e. (1/3) tr(J M^-1 J') as mj_setConst defines them, with no code shared."""
+    from mycobotgym_b200 import mjcf
+
+    fm = mjcf.load_compiled(mjcf.COMPILED_MOCAP if which == "mocap" else mjcf.COMPILED_JOINT)
+    s = OracleSim(fm)
+    s.qpos[:] = fm["qpos0"]
+    s.forward()                                     # kinematics, comPos, crb at qpos0
+    M = s.M.copy()
+    nv = fm["nv"]
+    Minv = np.linalg.inv(M)
+    for b in range(1, fm["nbody"]):
+        if fm["body_weldid"][b] == 0:
+            assert np.all(fm["body_invweight0"][b] == 0)
+            continue
+        jp, jr = s.jac(b, s.xipos[b])
+        tran, rot = np.trace(jp @ Minv @ jp.T) / 3, np.trace(jr @ Minv @ jr.T) / 3
+        np.testing.assert_allclose(fm["body_invweight0"][b], [tran, rot], rtol=1e-10, err_msg=fm["body_names"][b])
+    d = np.diag(Minv)
+    for j in range(fm["njnt"]):
+        a = fm["jnt_dofadr"][j]
+        if fm["jnt_type"][j] == 0:                  # free joint: translational and rotational averages
+            np.testing.assert_allclose(fm["dof_invweight0"][a:a + 3], d[a:a + 3].mean(), rtol=1e-10)
+            np.testing.assert_allclose(fm["dof_invweight0"][a + 3:a + 6], d[a + 3:a + 6].mean(), rtol=1e-10)
+        else:
+            np.testing.assert_allclose(fm["dof_invweight0"][a], d[a], rtol=1e-10)
+    assert abs(fm["stat_meaninertia"] - np.trace(M) / nv) < 1e-12 * np.trace(M)
+    if which == "mocap":
+        tcp = list(fm["body_names"]).index("gripper_tcp")
+        assert abs(fm["body_invweight0"][tcp][0] - 0.394148058) < 1e-8      # the value the weld rows are regularised with
