@@ -261,6 +261,10 @@ def _orient(el):
 # ----------------------------------------------------------------------------------
 
 
+HULL_SIDE_KEYS = ("hull_vert",)
+HULL_SIDE_FILE = "mycobot280_hulls.npz"
+
+
 class FlatModel(dict):
     """dict of numpy arrays / scalars with attribute access; JSON round-trips exactly."""
 
@@ -276,8 +280,11 @@ class FlatModel(dict):
                 return float(v)
             return v
 
+        side = {k: v for k, v in self.items() if k in HULL_SIDE_KEYS}
+        if side:                                                # the hull vertex table is binary and shared by the model variants
+            np.savez_compressed(os.path.join(os.path.dirname(path), HULL_SIDE_FILE), **side)
         with open(path, "w") as f:
-            json.dump({k: enc(v) for k, v in self.items()}, f, indent=0, sort_keys=True)
+            json.dump({k: enc(v) for k, v in self.items() if k not in HULL_SIDE_KEYS}, f, indent=0, sort_keys=True)
 
     @staticmethod
     def from_json(path):
@@ -289,6 +296,11 @@ class FlatModel(dict):
                 m[k] = np.array(v["data"], dtype=v["dtype"]).reshape(v["shape"])
             else:
                 m[k] = v
+        side = os.path.join(os.path.dirname(path), HULL_SIDE_FILE)
+        if m.get("nhull") and os.path.exists(side):
+            z = np.load(side)
+            for k in HULL_SIDE_KEYS:
+                m[k] = z[k]
         return m
 
 
@@ -524,8 +536,45 @@ def compile_mjcf(xml_path, log=None):
 
     # ---- collision geoms: primitives only (plane, box); mesh hulls are a documented gap
     cg = [g for g in geoms if g["type"] in (GEOM_TYPES["plane"], GEOM_TYPES["box"]) and (g["contype"] or g["conaffinity"])]
-    ndropped = len(geoms) - len(cg)
-    log.append(f"{ndropped} mesh geoms not emitted as collision geoms (convex-hull narrowphase is out of round-1 scope)")
+    # ---- mesh geoms collide as convex hulls (MuJoCo: qhull at compile time, mjc_Convex / mjc_PlaneConvex at run time).  Identical
+    # mesh geoms of one body (every robot body carries the same mesh twice: a group-1 density-0 copy and a default one, both with
+    # contype = conaffinity = 1) are emitted once with a multiplicity.  Hull vertices are kept in the BODY frame.
+    hulls = {}
+    for g in geoms:
+        if g["type"] != GEOM_TYPES["mesh"] or not (g["contype"] or g["conaffinity"]):
+            continue
+        mp = mesh_props(g["mesh"])
+        if mp is None:
+            continue
+        key = (g["body"], g["mesh"], tuple(g["pos"]), tuple(g["quat"]), g["condim"], tuple(g["friction"]), tuple(g["solref"]), tuple(g["solimp"]))
+        if key in hulls:
+            hulls[key]["mult"] += 1
+            continue
+        from scipy.spatial import ConvexHull
+
+        v = read_stl(meshes[g["mesh"]]).reshape(-1, 3)
+        v = np.unique(v, axis=0)
+        hv = v[np.sort(ConvexHull(v).vertices)]
+        R = quat2mat(g["quat"])
+        hv = hv @ R.T + g["pos"]
+        center = g["pos"] + R @ mp[1]                              # geom frame origin after MuJoCo recentres the mesh at its COM
+        hulls[key] = dict(g=g, mult=1, vert=hv, center=center, rbound=float(np.linalg.norm(hv - center, axis=1).max()))
+    hl = list(hulls.values())
+    m["nhull"] = len(hl)
+    m["hull_names"] = [bodies[h["g"]["body"]]["name"] for h in hl]
+    m["hull_bodyid"] = np.array([h["g"]["body"] for h in hl], dtype=np.int32)
+    m["hull_mult"] = np.array([h["mult"] for h in hl], dtype=np.int32)
+    m["hull_vertnum"] = np.array([len(h["vert"]) for h in hl], dtype=np.int32)
+    m["hull_vertadr"] = np.concatenate(([0], np.cumsum(m["hull_vertnum"])[:-1])).astype(np.int32) if hl else np.zeros(0, dtype=np.int32)
+    m["hull_vert"] = np.concatenate([h["vert"] for h in hl]) if hl else np.zeros((0, 3))
+    m["hull_center"] = np.array([h["center"] for h in hl]).reshape(len(hl), 3)
+    m["hull_rbound"] = np.array([h["rbound"] for h in hl])
+    m["hull_condim"] = np.array([h["g"]["condim"] for h in hl], dtype=np.int32)
+    m["hull_friction"] = np.array([h["g"]["friction"] for h in hl]).reshape(len(hl), 3)
+    m["hull_solref"] = np.array([h["g"]["solref"] for h in hl]).reshape(len(hl), 2)
+    m["hull_solimp"] = np.array([h["g"]["solimp"] for h in hl]).reshape(len(hl), 5)
+    m["hull_solmix"] = np.array([h["g"]["solmix"] for h in hl])
+    log.append(f"{len(hl)} convex hulls ({int(m['hull_vertnum'].sum()) if hl else 0} vertices) from {sum(h['mult'] for h in hl)} mesh geoms")
     m["ngeom"] = len(cg)
     m["geom_names"] = [g["name"] or "" for g in cg]
     m["geom_type"] = np.array([g["type"] for g in cg], dtype=np.int32)
@@ -838,6 +887,44 @@ def flatmodel_from_mjmodel(mjm, mujoco=None):
                   ("geom_friction", np.float64), ("geom_solref", np.float64), ("geom_solimp", np.float64), ("geom_solmix", np.float64),
                   ("geom_margin", np.float64), ("geom_gap", np.float64), ("geom_rbound", np.float64)):
         m[k] = np.array(getattr(mjm, k), dtype=dt)[keep]
+    # convex hulls of the collidable mesh geoms: hull vertex ids from mesh_graph (numvert, numface, vert_edgeadr[numvert],
+    # vert_globalid[numvert], ...), vertices moved from the (recentred, principal-axes) mesh frame into the body frame with the
+    # geom's pose; identical copies on one body fold into a multiplicity like in compile_mjcf()
+    hulls = {}
+    for g in range(mjm.ngeom):
+        if mjm.geom_type[g] != GEOM_TYPES["mesh"] or not (mjm.geom_contype[g] or mjm.geom_conaffinity[g]):
+            continue
+        mid = int(mjm.geom_dataid[g])
+        key = (int(mjm.geom_bodyid[g]), mid, tuple(np.round(np.array(mjm.geom_pos[g]), 12)), tuple(np.round(np.array(mjm.geom_quat[g]), 12)))
+        if key in hulls:
+            hulls[key]["mult"] += 1
+            continue
+        va, vn = int(mjm.mesh_vertadr[mid]), int(mjm.mesh_vertnum[mid])
+        verts = np.array(mjm.mesh_vert[va:va + vn], dtype=np.float64).reshape(vn, 3)
+        ga = int(mjm.mesh_graphadr[mid])
+        if ga >= 0:
+            nvh = int(mjm.mesh_graph[ga])
+            ids = np.array(mjm.mesh_graph[ga + 2 + nvh:ga + 2 + 2 * nvh], dtype=np.int64)
+            verts = verts[np.sort(ids)]
+        R = quat2mat(np.array(mjm.geom_quat[g], dtype=np.float64))
+        pos = np.array(mjm.geom_pos[g], dtype=np.float64)
+        hv = verts @ R.T + pos
+        hulls[key] = dict(g=g, mult=1, vert=hv, center=pos, rbound=float(np.linalg.norm(hv - pos, axis=1).max()))
+    hl = list(hulls.values())
+    m["nhull"] = len(hl)
+    m["hull_names"] = [name(mujoco.mjtObj.mjOBJ_BODY, int(mjm.geom_bodyid[h["g"]])) for h in hl]
+    m["hull_bodyid"] = np.array([mjm.geom_bodyid[h["g"]] for h in hl], dtype=np.int32)
+    m["hull_mult"] = np.array([h["mult"] for h in hl], dtype=np.int32)
+    m["hull_vertnum"] = np.array([len(h["vert"]) for h in hl], dtype=np.int32)
+    m["hull_vertadr"] = np.concatenate(([0], np.cumsum(m["hull_vertnum"])[:-1])).astype(np.int32) if hl else np.zeros(0, dtype=np.int32)
+    m["hull_vert"] = np.concatenate([h["vert"] for h in hl]) if hl else np.zeros((0, 3))
+    m["hull_center"] = np.array([h["center"] for h in hl]).reshape(len(hl), 3)
+    m["hull_rbound"] = np.array([h["rbound"] for h in hl])
+    m["hull_condim"] = np.array([mjm.geom_condim[h["g"]] for h in hl], dtype=np.int32)
+    m["hull_friction"] = np.array([mjm.geom_friction[h["g"]] for h in hl], dtype=np.float64).reshape(len(hl), 3)
+    m["hull_solref"] = np.array([mjm.geom_solref[h["g"]] for h in hl], dtype=np.float64).reshape(len(hl), 2)
+    m["hull_solimp"] = np.array([mjm.geom_solimp[h["g"]] for h in hl], dtype=np.float64).reshape(len(hl), 5)
+    m["hull_solmix"] = np.array([mjm.geom_solmix[h["g"]] for h in hl], dtype=np.float64)
     m["nsite"] = int(mjm.nsite)
     m["site_names"] = [name(mujoco.mjtObj.mjOBJ_SITE, i) for i in range(mjm.nsite)]
     m["site_bodyid"] = np.array(mjm.site_bodyid, dtype=np.int32)

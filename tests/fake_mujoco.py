@@ -25,9 +25,9 @@ def mj_id2name(model, objtype, i):
     return table[i] or None
 
 
-def model_from_flat(f, n_mesh_geoms=3):
-    """MjModel-shaped object carrying the FlatModel's content; `n_mesh_geoms` unnamed mesh geoms are interleaved with the
-    primitive geoms (the real model has 30), which the loader must drop."""
+def model_from_flat(f):
+    """MjModel-shaped object carrying the FlatModel's content, mesh geoms (two identical ones per robot body, like the real
+    model) and their meshes included."""
     m = types.SimpleNamespace()
     for k in ("nq", "nv", "nbody", "njnt", "nsite", "ntendon", "neq", "nu", "nkey", "nmocap", "nM"):
         setattr(m, k, int(f[k]))
@@ -42,28 +42,49 @@ def model_from_flat(f, n_mesh_geoms=3):
               "actuator_ctrllimited", "actuator_ctrlrange", "actuator_forcelimited", "actuator_forcerange"):
         setattr(m, k, np.array(f[k]))
     m._body_names, m._jnt_names, m._site_names = list(f["body_names"]), list(f["jnt_names"]), list(f["site_names"])
-    # geoms: primitives of the table + mesh geoms in between (type 7, collidable, no name)
-    ng = int(f["ngeom"])
-    order = []
-    for g in range(ng):
-        order.append(g)
-        if g < n_mesh_geoms:
-            order.append(-1)
+    # geoms: the primitives of the table, then every hull as `mult` identical mesh geoms (type 7, collidable, no name) whose
+    # mesh holds the hull vertices + three interior points the loader must discard through mesh_graph's vert_globalid
+    ng, nh = int(f["ngeom"]), int(f["nhull"])
+    order = [("p", g) for g in range(ng)]
+    for h in range(nh):
+        order += [("h", h)] * int(np.array(f["hull_mult"])[h])
     m.ngeom = len(order)
-    m._geom_names = [f["geom_names"][g] if g >= 0 else "" for g in order]
+    m._geom_names = [f["geom_names"][i] if kind == "p" else "" for kind, i in order]
+    hull_src = {"geom_bodyid": "hull_bodyid", "geom_condim": "hull_condim", "geom_friction": "hull_friction", "geom_solref": "hull_solref",
+                "geom_solimp": "hull_solimp", "geom_solmix": "hull_solmix"}
 
     def geom_field(k, fill):
         src = np.array(f[k])
         out = np.zeros((len(order),) + src.shape[1:], dtype=src.dtype)
-        for i, g in enumerate(order):
-            out[i] = src[g] if g >= 0 else fill
+        for i, (kind, g) in enumerate(order):
+            if kind == "p":
+                out[i] = src[g]
+            elif k in hull_src:
+                out[i] = np.array(f[hull_src[k]])[g]
+            elif k == "geom_pos":
+                out[i] = np.array(f["hull_center"])[g]        # MuJoCo puts the mesh geom's frame at the mesh's centre
+            else:
+                out[i] = fill
         return out
 
     m.geom_type = geom_field("geom_type", GEOM_MESH)
-    for k, fill in (("geom_bodyid", 4), ("geom_contype", 1), ("geom_conaffinity", 1), ("geom_condim", 3), ("geom_pos", 0.0), ("geom_quat", 0.0),
+    for k, fill in (("geom_bodyid", 4), ("geom_contype", 1), ("geom_conaffinity", 1), ("geom_condim", 3), ("geom_pos", 0.0), ("geom_quat", [1.0, 0, 0, 0]),
                     ("geom_size", 0.01), ("geom_friction", 1.0), ("geom_solref", 0.02), ("geom_solimp", 0.9), ("geom_solmix", 1.0),
                     ("geom_margin", 0.0), ("geom_gap", 0.0), ("geom_rbound", 0.05)):
         setattr(m, k, geom_field(k, fill))
+    m.geom_dataid = np.array([-1 if kind == "p" else g for kind, g in order], dtype=np.int32)
+    vert, vadr, vnum, graph, gadr = [], [], [], [], []
+    for h in range(nh):
+        a, n = int(np.array(f["hull_vertadr"])[h]), int(np.array(f["hull_vertnum"])[h])
+        hv = np.array(f["hull_vert"])[a:a + n] - np.array(f["hull_center"])[h]         # mesh frame = geom frame
+        inner = np.zeros((3, 3)) + hv.mean(0)
+        allv = np.concatenate([inner[:1], hv, inner[1:]])                                # hull vertices are ids 1 .. n
+        vadr.append(sum(len(x) for x in vert)); vnum.append(len(allv)); vert.append(allv)
+        gadr.append(len(graph))
+        graph += [n, 0] + [0] * n + list(range(1, n + 1))
+    m.mesh_vert = np.concatenate(vert).astype(np.float64) if vert else np.zeros((0, 3))
+    m.mesh_vertadr, m.mesh_vertnum = np.array(vadr, dtype=np.int32), np.array(vnum, dtype=np.int32)
+    m.mesh_graph, m.mesh_graphadr = np.array(graph, dtype=np.int32), np.array(gadr, dtype=np.int32)
     m.exclude_signature = np.array([(int(a) << 16) + int(b) for a, b in np.array(f["exclude"])], dtype=np.int64)
     # fixed tendons as wrap arrays
     adr, num, wtype, wobj, wprm = [], [], [], [], []

@@ -145,9 +145,10 @@ def test_live_mjmodel_loader_path_executes(which):
 
     compiled = mjcf.load_compiled(mjcf.COMPILED_MOCAP if which == "mocap" else mjcf.COMPILED_JOINT)
     mjm = fake_mujoco.model_from_flat(compiled)
-    assert mjm.ngeom == compiled["ngeom"] + 3                       # mesh geoms are present in the "live" model ...
+    assert mjm.ngeom == compiled["ngeom"] + 2 * compiled["nhull"]   # two mesh geoms per robot body in the "live" model ...
     live = mjcf.flatmodel_from_mjmodel(mjm, mujoco=fake_mujoco)
-    assert live["ngeom"] == compiled["ngeom"] and live["geom_names"] == compiled["geom_names"]      # ... and dropped by the loader
+    assert live["ngeom"] == compiled["ngeom"] and live["geom_names"] == compiled["geom_names"]      # ... become one hull each
+    assert live["nhull"] == 14 and np.all(live["hull_mult"] == 2)
     assert mjcf.diff_flatmodels(compiled, live) == {}
     a, b = flatten.reduce_model(compiled), flatten.reduce_model(live)
     assert bytes(ctypes.string_at(ctypes.addressof(a), ctypes.sizeof(a))) == bytes(ctypes.string_at(ctypes.addressof(b), ctypes.sizeof(b)))
