@@ -64,11 +64,16 @@ typedef struct {
   const double *actuator_moment, *actuator_gain, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange;
   const int *actuator_ctrllimited, *actuator_forcelimited;
   const double *qpos0;
+  /* convex hulls of the mesh geoms (mjcf.py: body frame, identical copies folded into hull_mult) */
+  int nhull, mesh_collision;
+  const int *hull_bodyid, *hull_mult, *hull_vertadr, *hull_vertnum, *hull_condim;
+  const double *hull_vert, *hull_center, *hull_rbound, *hull_friction, *hull_solref, *hull_solimp, *hull_solmix;
 } omodel;
 
 typedef struct {
   double dist, pos[3], frame[9], friction[5], solref[2], solimp[5], includemargin;
-  int dim, geom1, geom2, efc_address;
+  int dim, geom1, geom2, efc_address;   /* geom ids >= ngeom are hulls (ngeom + hull index) */
+  int mult;                             /* identical contacts MuJoCo would generate here (twin mesh geoms): scales D */
 } ocontact;
 
 typedef struct {
@@ -567,6 +572,170 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
   return cnt;
 }
 
+/* ------------------------------------------------------------------ convex hulls: engine_collision_convex.c (mjc_Convex, mjc_PlaneConvex)
+ * MuJoCo hands hull pairs to libccd's ccdMPRPenetration (Minkowski Portal Refinement, mpr_tolerance 1e-6, 50 iterations) with
+ * support mappings over the mesh vertices / the box corners and the geom centres as interior points; one contact per pair.
+ * libccd is absent from /root/reference (a MuJoCo dependency): the published algorithm (mpr.c: discoverPortal, refinePortal,
+ * findPenetr, findPos) is restated here.  PARITY UNPINNED like the rest of the physics. */
+typedef struct { int is_box; const double *pos, *mat, *verts, *size; int n; double center[3]; } cvx;   /* pos / mat: world pose of the vertex frame */
+typedef struct { double v[3], v1[3], v2[3]; } mpt;
+#define CCD_EPS 2.220446049250313e-16
+static int ccd_zero(double x) { return fabs(x) < CCD_EPS; }
+static int ccd_eq(double a, double b) {
+  double ab = fabs(a - b);
+  if (ab < CCD_EPS) return 1;
+  a = fabs(a); b = fabs(b);
+  return b > a ? ab < CCD_EPS * b : ab < CCD_EPS * a;
+}
+static void cvx_support(const cvx* o, const double* dir, double* out) {
+  double ld[3], best[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) ld[k] = o->mat[k] * dir[0] + o->mat[3 + k] * dir[1] + o->mat[6 + k] * dir[2];   /* mat' dir */
+  if (o->is_box) { for (int k = 0; k < 3; k++) best[k] = ld[k] > 0 ? o->size[k] : -o->size[k]; }
+  else {
+    double bd = -1e300;
+    for (int i = 0; i < o->n; i++) {
+      const double* v = o->verts + 3 * i;
+      double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
+      if (t > bd) { bd = t; best[0] = v[0]; best[1] = v[1]; best[2] = v[2]; }
+    }
+  }
+  mulmatvec3(out, o->mat, best);
+  for (int k = 0; k < 3; k++) out[k] += o->pos[k];
+}
+static void mpr_support(const cvx* a, const cvx* b, const double* dir, mpt* p) {   /* Minkowski difference A - B */
+  double nd[3] = {-dir[0], -dir[1], -dir[2]};
+  cvx_support(a, dir, p->v1);
+  cvx_support(b, nd, p->v2);
+  for (int k = 0; k < 3; k++) p->v[k] = p->v1[k] - p->v2[k];
+}
+static void portal_dir(const mpt* P, double* dir) {
+  double a[3], b[3];
+  for (int k = 0; k < 3; k++) { a[k] = P[2].v[k] - P[1].v[k]; b[k] = P[3].v[k] - P[1].v[k]; }
+  cross3(dir, a, b);
+  normalize3(dir);
+}
+static int portal_reach_tol(const mpt* P, const mpt* v4, const double* dir, double tol) {
+  double dv4 = dot3(v4->v, dir);
+  double d1 = dv4 - dot3(P[1].v, dir), d2 = dv4 - dot3(P[2].v, dir), d3 = dv4 - dot3(P[3].v, dir);
+  d1 = fmin(d1, fmin(d2, d3));
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+static void expand_portal(mpt* P, const mpt* v4) {
+  double v4v0[3];
+  cross3(v4v0, v4->v, P[0].v);
+  if (dot3(P[1].v, v4v0) > 0) { if (dot3(P[2].v, v4v0) > 0) P[1] = *v4; else P[3] = *v4; }
+  else { if (dot3(P[3].v, v4v0) > 0) P[2] = *v4; else P[1] = *v4; }
+}
+/* squared distance of the origin to triangle (a, b, c); closest point in w (Ericson, Real-Time Collision Detection 5.1.5) */
+static double origin_tri_dist2(const double* a, const double* b, const double* c, double* w) {
+  double ab[3], ac[3], ap[3], bp[3], cp[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = -a[k]; bp[k] = -b[k]; cp[k] = -c[k]; }
+  double d1 = dot3(ab, ap), d2 = dot3(ac, ap), d3 = dot3(ab, bp), d4 = dot3(ac, bp), d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  double u, v;
+  if (d1 <= 0 && d2 <= 0) { u = 0; v = 0; }
+  else if (d3 >= 0 && d4 <= d3) { u = 1; v = 0; }
+  else if (d1 * d4 - d3 * d2 <= 0 && d1 >= 0 && d3 <= 0) { u = d1 / (d1 - d3); v = 0; }
+  else if (d6 >= 0 && d5 <= d6) { u = 0; v = 1; }
+  else if (d5 * d2 - d1 * d6 <= 0 && d2 >= 0 && d6 <= 0) { u = 0; v = d2 / (d2 - d6); }
+  else if (d3 * d6 - d5 * d4 <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { v = (d4 - d3) / ((d4 - d3) + (d5 - d6)); u = 1 - v; }
+  else { double va = d3 * d6 - d5 * d4, vb = d5 * d2 - d1 * d6, vc = d1 * d4 - d3 * d2, den = 1 / (va + vb + vc); u = vb * den; v = vc * den; }
+  for (int k = 0; k < 3; k++) w[k] = a[k] + u * ab[k] + v * ac[k];
+  return dot3(w, w);
+}
+/* returns 1 and (depth, dir from A to B, pos) if the hulls intersect */
+static int mpr_penetration(const cvx* A, const cvx* B, double* depth, double* dir, double* pos) {
+  const double tol = 1e-6; const int maxiter = 50;
+  mpt P[4], v4;
+  double d[3], va[3], vb[3], dot;
+  /* discoverPortal */
+  for (int k = 0; k < 3; k++) { P[0].v1[k] = A->center[k]; P[0].v2[k] = B->center[k]; P[0].v[k] = P[0].v1[k] - P[0].v2[k]; }
+  if (ccd_zero(P[0].v[0]) && ccd_zero(P[0].v[1]) && ccd_zero(P[0].v[2])) P[0].v[0] += CCD_EPS * 10;
+  for (int k = 0; k < 3; k++) d[k] = -P[0].v[k];
+  normalize3(d);
+  mpr_support(A, B, d, &P[1]);
+  dot = dot3(P[1].v, d);
+  if (ccd_zero(dot) || dot < 0) return 0;
+  cross3(d, P[0].v, P[1].v);
+  if (ccd_zero(dot3(d, d))) {
+    /* origin on the segment v0-v1 (or on v1): findPenetrSegment / findPenetrTouch */
+    *depth = sqrt(dot3(P[1].v, P[1].v));
+    for (int k = 0; k < 3; k++) { dir[k] = P[1].v[k]; pos[k] = 0.5 * (P[1].v1[k] + P[1].v2[k]); }
+    normalize3(dir);
+    return 1;
+  }
+  normalize3(d);
+  mpr_support(A, B, d, &P[2]);
+  dot = dot3(P[2].v, d);
+  if (ccd_zero(dot) || dot < 0) return 0;
+  for (int k = 0; k < 3; k++) { va[k] = P[1].v[k] - P[0].v[k]; vb[k] = P[2].v[k] - P[0].v[k]; }
+  cross3(d, va, vb);
+  normalize3(d);
+  if (dot3(d, P[0].v) > 0) { mpt t = P[1]; P[1] = P[2]; P[2] = t; for (int k = 0; k < 3; k++) d[k] = -d[k]; }
+  for (int guard = 0; guard < 100; guard++) {
+    mpr_support(A, B, d, &P[3]);
+    dot = dot3(P[3].v, d);
+    if (ccd_zero(dot) || dot < 0) return 0;
+    int cont = 0;
+    cross3(va, P[1].v, P[3].v);
+    dot = dot3(va, P[0].v);
+    if (dot < 0 && !ccd_zero(dot)) { P[2] = P[3]; cont = 1; }
+    if (!cont) {
+      cross3(va, P[3].v, P[2].v);
+      dot = dot3(va, P[0].v);
+      if (dot < 0 && !ccd_zero(dot)) { P[1] = P[3]; cont = 1; }
+    }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = P[1].v[k] - P[0].v[k]; vb[k] = P[2].v[k] - P[0].v[k]; }
+    cross3(d, va, vb);
+    normalize3(d);
+    if (guard == 99) return 0;
+  }
+  /* refinePortal */
+  for (int guard = 0;; guard++) {
+    portal_dir(P, d);
+    dot = dot3(d, P[1].v);
+    if (ccd_zero(dot) || dot > 0) break;                      /* portalEncapsulesOrigin */
+    mpr_support(A, B, d, &v4);
+    dot = dot3(v4.v, d);
+    if (!(ccd_zero(dot) || dot > 0) || portal_reach_tol(P, &v4, d, tol)) return 0;
+    expand_portal(P, &v4);
+    if (guard > 1000) return 0;
+  }
+  /* findPenetr */
+  for (int it = 0;; it++) {
+    portal_dir(P, d);
+    mpr_support(A, B, d, &v4);
+    if (portal_reach_tol(P, &v4, d, tol) || it > maxiter) {
+      double w[3];
+      *depth = sqrt(origin_tri_dist2(P[1].v, P[2].v, P[3].v, w));
+      if (ccd_zero(w[0]) && ccd_zero(w[1]) && ccd_zero(w[2])) { for (int k = 0; k < 3; k++) dir[k] = d[k]; *depth = 0; }
+      else { for (int k = 0; k < 3; k++) dir[k] = w[k]; normalize3(dir); }
+      /* findPos: barycentric coordinates of the origin in the portal tetrahedron */
+      double b[4], t[3], sum;
+      cross3(t, P[1].v, P[2].v); b[0] = dot3(t, P[3].v);
+      cross3(t, P[3].v, P[2].v); b[1] = dot3(t, P[0].v);
+      cross3(t, P[0].v, P[1].v); b[2] = dot3(t, P[3].v);
+      cross3(t, P[2].v, P[1].v); b[3] = dot3(t, P[0].v);
+      sum = b[0] + b[1] + b[2] + b[3];
+      if (ccd_zero(sum) || sum < 0) {
+        b[0] = 0;
+        cross3(t, P[2].v, P[3].v); b[1] = dot3(t, d);
+        cross3(t, P[3].v, P[1].v); b[2] = dot3(t, d);
+        cross3(t, P[1].v, P[2].v); b[3] = dot3(t, d);
+        sum = b[1] + b[2] + b[3];
+      }
+      double inv = 1.0 / sum;
+      for (int k = 0; k < 3; k++) {
+        double p1 = b[0] * P[0].v1[k] + b[1] * P[1].v1[k] + b[2] * P[2].v1[k] + b[3] * P[3].v1[k];
+        double p2 = b[0] * P[0].v2[k] + b[1] * P[1].v2[k] + b[2] * P[2].v2[k] + b[3] * P[3].v2[k];
+        pos[k] = 0.5 * (p1 + p2) * inv;
+      }
+      return 1;
+    }
+    expand_portal(P, &v4);
+  }
+}
+
 static int body_filter(const omodel* m, int b1, int b2) {
   int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
   if (w1 == w2) return 1;
@@ -575,6 +744,86 @@ static int body_filter(const omodel* m, int b1, int b2) {
     if (m->exclude[2 * e] == lo && m->exclude[2 * e + 1] == hi) return 1;
   if (w1 && w2 && (m->body_weldid[m->body_parentid[w1]] == w2 || m->body_weldid[m->body_parentid[w2]] == w1)) return 1;
   return 0;
+}
+
+static int con_body(const omodel* m, int g) { return g < m->ngeom ? m->geom_bodyid[g] : m->hull_bodyid[g - m->ngeom]; }
+/* mj_contactParam (same priority): condim max, friction max, solref mixed (or min for direct stiffness), solimp mixed */
+static void mix_params(ocontact* con, int cd1, const double* fr1, const double* ra, const double* ia, double sa,
+                       int cd2, const double* fr2, const double* rb, const double* ib, double sb) {
+  con->dim = cd1 > cd2 ? cd1 : cd2;
+  double fr[3];
+  for (int k = 0; k < 3; k++) fr[k] = fmax(fr1[k], fr2[k]);
+  con->friction[0] = fr[0]; con->friction[1] = fr[0]; con->friction[2] = fr[1]; con->friction[3] = fr[2]; con->friction[4] = fr[2];
+  double mix;
+  if (sa >= MINVAL && sb >= MINVAL) mix = sa / (sa + sb);
+  else if (sa < MINVAL && sb < MINVAL) mix = 0.5;
+  else if (sa < MINVAL) mix = 0.0; else mix = 1.0;
+  if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) con->solref[k] = mix * ra[k] + (1 - mix) * rb[k];
+  else for (int k = 0; k < 2; k++) con->solref[k] = fmin(ra[k], rb[k]);
+  for (int k = 0; k < 5; k++) con->solimp[k] = mix * ia[k] + (1 - mix) * ib[k];
+}
+static void hull_cvx(const omodel* m, const odata* d, int h, cvx* o) {
+  int b = m->hull_bodyid[h];
+  o->is_box = 0; o->pos = d->xpos + 3 * b; o->mat = d->xmat + 9 * b; o->verts = m->hull_vert + 3 * m->hull_vertadr[h]; o->n = m->hull_vertnum[h]; o->size = NULL;
+  mulmatvec3(o->center, o->mat, m->hull_center + 3 * h);
+  for (int k = 0; k < 3; k++) o->center[k] += o->pos[k];
+}
+static void add_convex_contact(const omodel* m, odata* d, int g1, int g2, double dist, const double* pos, const double* nrm, int mult) {
+  if (d->ncon >= MAXCON) return;
+  ocontact* con = d->contact + d->ncon++;
+  con->dist = dist;
+  memcpy(con->pos, pos, sizeof con->pos);
+  memcpy(con->frame, nrm, 3 * sizeof(double));
+  make_frame(con->frame);
+  con->geom1 = g1; con->geom2 = g2; con->mult = mult; con->includemargin = 0; con->efc_address = -1;
+  const int h1 = g1 - m->ngeom, h2 = g2 - m->ngeom;
+  const int cd1 = h1 >= 0 ? m->hull_condim[h1] : m->geom_condim[g1], cd2 = h2 >= 0 ? m->hull_condim[h2] : m->geom_condim[g2];
+  const double* f1 = h1 >= 0 ? m->hull_friction + 3 * h1 : m->geom_friction + 3 * g1; const double* f2 = h2 >= 0 ? m->hull_friction + 3 * h2 : m->geom_friction + 3 * g2;
+  const double* r1 = h1 >= 0 ? m->hull_solref + 2 * h1 : m->geom_solref + 2 * g1; const double* r2 = h2 >= 0 ? m->hull_solref + 2 * h2 : m->geom_solref + 2 * g2;
+  const double* i1 = h1 >= 0 ? m->hull_solimp + 5 * h1 : m->geom_solimp + 5 * g1; const double* i2 = h2 >= 0 ? m->hull_solimp + 5 * h2 : m->geom_solimp + 5 * g2;
+  mix_params(con, cd1, f1, r1, i1, h1 >= 0 ? m->hull_solmix[h1] : m->geom_solmix[g1], cd2, f2, r2, i2, h2 >= 0 ? m->hull_solmix[h2] : m->geom_solmix[g2]);
+}
+/* hull x {plane, box, hull}: mjc_PlaneConvex / mjc_Convex, one contact per pair, after the primitive pairs */
+static void collide_hulls(const omodel* m, odata* d) {
+  for (int h = 0; h < m->nhull; h++) {
+    cvx A; hull_cvx(m, d, h, &A);
+    const int bh = m->hull_bodyid[h];
+    const double rh = m->hull_rbound[h];
+    for (int g = 0; g < m->ngeom; g++) {                      /* primitive first: geom type order plane < box < mesh */
+      int bg = m->geom_bodyid[g];
+      if (body_filter(m, bg, bh)) continue;
+      if (m->disable_cube && m->body_dofnum[bg] == 6) continue;
+      const double *pg = d->geom_xpos + 3 * g, *Rg = d->geom_xmat + 9 * g;
+      if (m->geom_type[g] == GEOM_PLANE) {
+        double nrm[3] = {Rg[2], Rg[5], Rg[8]}, nn[3] = {-Rg[2], -Rg[5], -Rg[8]}, dif[3], p[3];
+        for (int k = 0; k < 3; k++) dif[k] = A.center[k] - pg[k];
+        if (dot3(dif, nrm) > rh) continue;
+        cvx_support(&A, nn, p);
+        for (int k = 0; k < 3; k++) dif[k] = p[k] - pg[k];
+        double dist = dot3(dif, nrm);
+        if (dist > 0) continue;
+        for (int k = 0; k < 3; k++) p[k] -= 0.5 * dist * nrm[k];
+        add_convex_contact(m, d, g, m->ngeom + h, dist, p, nrm, m->hull_mult[h]);
+      } else {
+        double dif[3], bound = rh + m->geom_rbound[g];
+        for (int k = 0; k < 3; k++) dif[k] = A.center[k] - pg[k];
+        if (dot3(dif, dif) > bound * bound) continue;
+        cvx B; B.is_box = 1; B.pos = pg; B.mat = Rg; B.size = m->geom_size + 3 * g; B.verts = NULL; B.n = 0;
+        for (int k = 0; k < 3; k++) B.center[k] = pg[k];
+        double depth, dir[3], pos[3];
+        if (mpr_penetration(&B, &A, &depth, dir, pos)) add_convex_contact(m, d, g, m->ngeom + h, -depth, pos, dir, m->hull_mult[h]);
+      }
+    }
+    for (int h2 = h + 1; h2 < m->nhull; h2++) {
+      if (body_filter(m, bh, m->hull_bodyid[h2])) continue;
+      cvx B; hull_cvx(m, d, h2, &B);
+      double dif[3], bound = rh + m->hull_rbound[h2];
+      for (int k = 0; k < 3; k++) dif[k] = A.center[k] - B.center[k];
+      if (dot3(dif, dif) > bound * bound) continue;
+      double depth, dir[3], pos[3];
+      if (mpr_penetration(&A, &B, &depth, dir, pos)) add_convex_contact(m, d, m->ngeom + h, m->ngeom + h2, -depth, pos, dir, m->hull_mult[h] * m->hull_mult[h2]);
+    }
+  }
 }
 
 void o_collision(const omodel* m, odata* d) {
@@ -610,23 +859,14 @@ void o_collision(const omodel* m, odata* d) {
         memcpy(con->frame, rc[c].normal, 3 * sizeof(double));
         make_frame(con->frame);
         con->geom1 = a; con->geom2 = b;
-        con->dim = m->geom_condim[a] > m->geom_condim[b] ? m->geom_condim[a] : m->geom_condim[b];
-        double fr[3];
-        for (int k = 0; k < 3; k++) fr[k] = fmax(m->geom_friction[3 * a + k], m->geom_friction[3 * b + k]);
-        con->friction[0] = fr[0]; con->friction[1] = fr[0]; con->friction[2] = fr[1]; con->friction[3] = fr[2]; con->friction[4] = fr[2];
-        double mix;
-        double sa = m->geom_solmix[a], sb = m->geom_solmix[b];
-        if (sa >= MINVAL && sb >= MINVAL) mix = sa / (sa + sb);
-        else if (sa < MINVAL && sb < MINVAL) mix = 0.5;
-        else if (sa < MINVAL) mix = 0.0; else mix = 1.0;
-        const double *ra = m->geom_solref + 2 * a, *rb = m->geom_solref + 2 * b;
-        if (ra[0] > 0 && rb[0] > 0) for (int k = 0; k < 2; k++) con->solref[k] = mix * ra[k] + (1 - mix) * rb[k];
-        else for (int k = 0; k < 2; k++) con->solref[k] = fmin(ra[k], rb[k]);
-        for (int k = 0; k < 5; k++) con->solimp[k] = mix * m->geom_solimp[5 * a + k] + (1 - mix) * m->geom_solimp[5 * b + k];
+        con->mult = 1;
+        mix_params(con, m->geom_condim[a], m->geom_friction + 3 * a, m->geom_solref + 2 * a, m->geom_solimp + 5 * a, m->geom_solmix[a],
+                   m->geom_condim[b], m->geom_friction + 3 * b, m->geom_solref + 2 * b, m->geom_solimp + 5 * b, m->geom_solmix[b]);
         con->includemargin = margin - gap;
         con->efc_address = -1;
       }
     }
+  if (m->mesh_collision && m->nhull > 0) collide_hulls(m, d);
 }
 
 /* ------------------------------------------------------------------ engine_core_constraint.c */
@@ -751,7 +991,7 @@ void o_make_constraint(const omodel* m, odata* d) {
   for (int c = 0; c < d->ncon; c++) {
     ocontact* con = d->contact + c;
     if (con->dist >= con->includemargin) continue;
-    int b1 = m->geom_bodyid[con->geom1], b2 = m->geom_bodyid[con->geom2];
+    int b1 = con_body(m, con->geom1), b2 = con_body(m, con->geom2);
     int dim = con->dim;
     o_jac(m, d, jp1, jr1, con->pos, b1);
     o_jac(m, d, jp2, jr2, con->pos, b2);
@@ -824,6 +1064,7 @@ void o_make_constraint(const omodel* m, odata* d) {
       double mu = con->friction[0] / sqrt(m->impratio);
       double Rpy = 2 * mu * mu * d->efc_R[i];
       int n = 2 * (con->dim - 1);
+      Rpy /= (double)con->mult;      /* `mult` identical contacts (twin mesh geoms) == one contact with mult x the D of each */
       for (int j = 0; j < n; j++) d->efc_R[i + j] = Rpy;
       i += n - 1;
     }
@@ -1237,6 +1478,15 @@ void o_contact(odata* d, int i, double* out /* dist, pos3, frame9, geom1, geom2,
   ocontact* c = d->contact + i;
   out[0] = c->dist; memcpy(out + 1, c->pos, 3 * sizeof(double)); memcpy(out + 4, c->frame, 9 * sizeof(double));
   out[13] = c->geom1; out[14] = c->geom2; out[15] = c->dim;
+}
+
+/* test hook: MPR on two vertex sets given in world coordinates (interior points = vertex means); out = depth, dir[3], pos[3] */
+int o_test_mpr(const double* va, int na, const double* vb, int nb, double* out) {
+  static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
+  cvx A = {0, Z3, I3, va, NULL, na, {0, 0, 0}}, B = {0, Z3, I3, vb, NULL, nb, {0, 0, 0}};
+  for (int i = 0; i < na; i++) for (int k = 0; k < 3; k++) A.center[k] += va[3 * i + k] / na;
+  for (int i = 0; i < nb; i++) for (int k = 0; k < 3; k++) B.center[k] += vb[3 * i + k] / nb;
+  return mpr_penetration(&A, &B, out, out + 1, out + 4);
 }
 
 /* ------------------------------------------------------------------ batched CPU rollout used as the bench cpu_baseline ("port") */

@@ -38,11 +38,19 @@ _PTRS = [
     ("i", ["actuator_ctrllimited", "actuator_forcelimited"]),
     ("d", ["qpos0"]),
 ]
+# appended to the struct after the pointer block above: the convex hulls of the mesh geoms
+_HULL_INTS = ["nhull", "mesh_collision"]
+_HULL_PTRS = [("i", ["hull_bodyid", "hull_mult", "hull_vertadr", "hull_vertnum", "hull_condim"]),
+              ("d", ["hull_vert", "hull_center", "hull_rbound", "hull_friction", "hull_solref", "hull_solimp", "hull_solmix"])]
 
 
 def _fields():
     f = [(n, C.c_int) for n in _INT_SCALARS] + [(n, C.c_double) for n in _DBL_SCALARS] + [("gravity", C.c_double * 3)]
     for kind, names in _PTRS:
+        for n in names:
+            f.append((n, C.POINTER(C.c_int if kind == "i" else C.c_double)))
+    f += [(n, C.c_int) for n in _HULL_INTS]
+    for kind, names in _HULL_PTRS:
         for n in names:
             f.append((n, C.POINTER(C.c_int if kind == "i" else C.c_double)))
     return f
@@ -82,7 +90,9 @@ def lib():
 class OracleSim:
     """One environment of the CPU restatement."""
 
-    def __init__(self, flat, disable_cube=False):
+    def __init__(self, flat, disable_cube=False, mesh_collision=None):
+        """`mesh_collision`: collide the convex hulls of the mesh geoms too (mjc_Convex / mjc_PlaneConvex restated as MPR);
+        default: the model's own "mesh_collision" entry (absent = off)."""
         self.flat = flat
         self.L = lib()
         self._keep = []
@@ -102,6 +112,14 @@ class OracleSim:
                 a = np.ascontiguousarray(flat[n], dtype=np.int32 if kind == "i" else np.float64)
                 self._keep.append(a)
                 setattr(om, n, a.ctypes.data_as(C.POINTER(C.c_int if kind == "i" else C.c_double)))
+        om.nhull = int(flat.get("nhull", 0))
+        om.mesh_collision = int(bool(flat.get("mesh_collision", False) if mesh_collision is None else mesh_collision)) if om.nhull else 0
+        if om.nhull:
+            for kind, names in _HULL_PTRS:
+                for n in names:
+                    a = np.ascontiguousarray(flat[n], dtype=np.int32 if kind == "i" else np.float64)
+                    self._keep.append(a)
+                    setattr(om, n, a.ctypes.data_as(C.POINTER(C.c_int if kind == "i" else C.c_double)))
         self.om = om
         self.nq, self.nv, self.nu = int(flat["nq"]), int(flat["nv"]), int(flat["nu"])
         self.buf = C.create_string_buffer(self.L.o_sizeof_data())
