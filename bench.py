@@ -226,7 +226,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     kw, per_gpu, flop_per_step = WORKLOADS[args.workload]
     n = args.envs_per_gpu or per_gpu
-    env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, lockstep_warps=int(os.environ.get("MCB_LOCKSTEP", "0")), **kw)
+    env = MyCobotVectorEnv(num_envs=n, device=f"cuda:{local}", seed=1000 + rank, lockstep_warps=int(os.environ.get("MCB_LOCKSTEP", "0")),
+                           mesh_collision=bool(int(os.environ.get("MCB_MESH", "0"))), **kw)
     env.reset()
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev)

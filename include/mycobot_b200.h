@@ -34,6 +34,8 @@ extern "C" {
 #define MCB_NHINGE 12
 #define MCB_NGEOM 5   /* plane, table box, right/left finger-layer boxes, cube box */
 #define MCB_MAXPAIR 12
+#define MCB_MAXHULL 16   /* convex hulls of the mesh geoms (14 in the myCobot model; base_link.STL is absent from the reference) */
+#define MCB_MAXHPAIR 192 /* candidate pairs hull x {hull, box, plane} after MuJoCo's static filters */
 #define MCB_OBS_OBJECT 25
 #define MCB_OBS_REACH 10
 #define MCB_STATE_STRIDE 80 /* doubles per env in the resident state record: qpos19 qvel18 ctrl7 warm18 goal3 qprev6 mocap7 pad2 */
@@ -147,6 +149,9 @@ typedef struct mcb_task_cfg {
                                   model variant); mycobot.py:36,90-103,134-193 */
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */
   int32_t control_steps;       /* IK: DLS solves per env-step, each followed by frame_skip substeps (5; mycobot.py:35,162) */
+  int32_t mesh_collision;      /* 1: the convex hulls registered with mcb_model_set_hulls collide too (mjc_Convex / mjc_PlaneConvex: one MPR
+                                * contact per pair); 0: plane / box primitives only */
+  int32_t reserved1_;
   int32_t lockstep_warps;      /* scheduling only, results do not depend on it: warps per lockstep group of the step kernel
                                 * (1 free-running ... 16 whole CTA); 0 = free-running until the caller runs mcb_autotune() */
   double distance_threshold;   /* 0.01 */
@@ -163,6 +168,23 @@ int32_t mcb_task_cfg_size(void);
 /* replaces mujoco.MjModel.from_xml_path + MyCobotEnv._env_setup (mycobot.py:69-82,450-481) */
 int32_t mcb_model_create(const mcb_model_desc* host_desc, int32_t device, mcb_model** out);
 int32_t mcb_model_destroy(mcb_model* m);
+
+/* Convex hulls of the model's mesh geoms (mycobot280_main.xml:105-250: two identical mesh geoms per robot body; MuJoCo collides
+ * their qhull hulls with mjc_Convex = libccd MPR and mjc_PlaneConvex).  All arrays are HOST pointers and are copied.
+ * Hull h: jointed body index (or -1: static) `body[h]`, vertices `vert[vadr[h] .. vadr[h] + vnum[h])` (x, y, z in that body's
+ * frame), interior point `center[h]` (the mesh geom's frame origin), bounding radius about it, `mult[h]` identical geoms,
+ * contact parameters of the geoms.  Pairs: object ids < MCB_NGEOM name a primitive geom of the model, MCB_NGEOM + h a hull;
+ * a pair lists the primitive first.  Call once, before mcb_batch_create. */
+typedef struct mcb_hull_desc {
+  int32_t nhull, npair, nvert, reserved_;
+  int32_t body[MCB_MAXHULL], vadr[MCB_MAXHULL], vnum[MCB_MAXHULL], mult[MCB_MAXHULL], condim[MCB_MAXHULL];
+  double center[MCB_MAXHULL][3], rbound[MCB_MAXHULL], friction[MCB_MAXHULL][3], solref[MCB_MAXHULL][2], solimp[MCB_MAXHULL][5],
+         solmix[MCB_MAXHULL], invweight[MCB_MAXHULL][2];
+  uint8_t pair_a[MCB_MAXHPAIR], pair_b[MCB_MAXHPAIR];
+  const double* vert;
+} mcb_hull_desc;
+int32_t mcb_hull_desc_size(void);
+int32_t mcb_model_set_hulls(mcb_model* m, const mcb_hull_desc* hulls);
 
 /* replaces constructing n_envs MyCobotEnv instances (train.py:80-85) */
 int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, uint64_t seed, mcb_batch** out);

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 import subprocess
 
-from .flatten import ModelDesc, TaskCfg
+from .flatten import HullDesc, ModelDesc, TaskCfg
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
@@ -28,7 +28,7 @@ EXPORTS = [
     "mcb_reset", "mcb_step", "mcb_step_host", "mcb_get_state", "mcb_set_state", "mcb_forward",
     "mcb_compute_reward", "mcb_stats", "mcb_debug_forward", "mcb_last_step_launches", "mcb_fp64_peak_probe",
     "mcb_autotune", "mcb_batch_lockstep_warps", "mcb_last_fallback_envs", "mcb_her_create", "mcb_her_destroy", "mcb_her_add", "mcb_her_size", "mcb_her_episode_table",
-    "mcb_her_sample", "mcb_reset_host", "mcb_seed", "mcb_get_rng_state", "mcb_set_rng_state", "mcb_last_fallback_list", "mcb_total_launches",
+    "mcb_her_sample", "mcb_reset_host", "mcb_seed", "mcb_get_rng_state", "mcb_set_rng_state", "mcb_last_fallback_list", "mcb_total_launches", "mcb_hull_desc_size", "mcb_model_set_hulls",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
     L.mcb_last_error.restype = C.c_char_p
     L.mcb_model_create.argtypes = [C.POINTER(ModelDesc), i32, C.POINTER(vp)]
     L.mcb_model_destroy.argtypes = [vp]
+    L.mcb_model_set_hulls.argtypes = [vp, C.POINTER(HullDesc)]
     L.mcb_batch_create.argtypes = [vp, i32, C.POINTER(TaskCfg), u64, C.POINTER(vp)]
     L.mcb_batch_destroy.argtypes = [vp]
     L.mcb_batch_num_envs.argtypes = [vp]
@@ -115,6 +116,7 @@ def load():
     L.mcb_her_sample.argtypes = [vp, i32] + [vp] * 13
     assert L.mcb_model_desc_size() == C.sizeof(ModelDesc), (L.mcb_model_desc_size(), C.sizeof(ModelDesc))
     assert L.mcb_task_cfg_size() == C.sizeof(TaskCfg), (L.mcb_task_cfg_size(), C.sizeof(TaskCfg))
+    assert L.mcb_hull_desc_size() == C.sizeof(HullDesc), (L.mcb_hull_desc_size(), C.sizeof(HullDesc))
     _lib = L
     return L
 

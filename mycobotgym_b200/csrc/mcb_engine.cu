@@ -41,6 +41,7 @@
 #include <string.h>
 #include <math.h>
 #include <string>
+#include <vector>
 #include <stdlib.h>
 
 #include "mycobot_b200.h"
@@ -76,11 +77,12 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
 
 struct PairParam {
-  int g1, g2, dim, ptype;  // ptype: 0 rows touch robot dofs only, 1 cube dofs only, 2 both
+  int g1, g2, dim, ptype;  // ptype: 0 rows touch robot dofs only, 1 cube dofs only, 2 both; g: object ids (>= MCB_NGEOM: hull)
+  int b1, b2;              // jointed bodies carrying the two geoms (-1: static)
   double friction[3];
   double KB[2];            // on the device: (K, B) of mj_makeImpedance (the host fills the mixed solref here first, row_constants() converts)
   double solimp[5];        // clamped once at model creation
-  double tran, pyr2;       // body_invweight0 sum (translational), 2 mu^2 / impratio (the pyramid's regulariser scale)
+  double tran, pyr2;       // body_invweight0 sum (translational), 2 mu^2 / impratio / multiplicity (the pyramid's regulariser scale)
 };
 
 struct DevModel {
@@ -92,6 +94,14 @@ struct DevModel {
   unsigned char mnz_i[NMNZ_MAX], mnz_j[NMNZ_MAX];
   unsigned char tri_i[176], tri_j[176];   // packed lower-triangle index e -> (row, column)
   PairParam pair[MCB_MAXPAIR];
+  // convex hulls of the mesh geoms (mcb_model_set_hulls): what the broad phase needs is staged with the model, vertices and
+  // the per-pair contact parameters stay in global memory (read only when a hull pair is actually close)
+  int nhull, nhpair;
+  int hull_body[MCB_MAXHULL], hull_vadr[MCB_MAXHULL], hull_vnum[MCB_MAXHULL];
+  double hull_center[MCB_MAXHULL][3], hull_rbound[MCB_MAXHULL];
+  unsigned char hpair_a[MCB_MAXHPAIR], hpair_b[MCB_MAXHPAIR];
+  const double* hull_vert;          // [nvert][3], body frames
+  const PairParam* hpair_param;     // [nhpair]
 };
 
 // The flattened model is staged into the CTA's shared memory (offset 0 of the dynamic segment, before the per-env
@@ -100,6 +110,8 @@ struct DevModel {
 extern __shared__ __align__(16) unsigned char smem_raw[];
 #define MODEL_BYTES ((sizeof(DevModel) + 15) / 16 * 16)
 #define MDL (*reinterpret_cast<const DevModel*>(smem_raw))
+// contact -> its pair's parameters: primitive pairs from the staged table, hull pairs (ids >= MCB_MAXPAIR) from global memory
+#define PP(cp) ((cp) < MCB_MAXPAIR ? MDL.pair[cp] : MDL.hpair_param[(cp) - MCB_MAXPAIR])
 
 static_assert(sizeof(DevModel) % sizeof(double) == 0, "DevModel must be a whole number of doubles");
 
@@ -176,8 +188,8 @@ struct EnvS {
   GUARD(g7)
   int cpair[MAXC], crow[MAXC];
   int rmeta[NROW];   // bits 0-7 index (eq / contact / dof), 8 sign, 9-11 sub-row, 12-14 kind (0 connect 1 joint-eq 2 limit 3 contact 4 weld), 16 inequality
-  int omap[NROW];    // position of the row in MuJoCo's ordering (equality, limits, contacts) -- debug taps only
   int nR, nC, nF, nU, nefc, ncon, overflow, iters;
+  int mesh, pad_[3];   // mesh: the batch collides the convex hulls too (cfg.mesh_collision)
 };
 static_assert(offsetof(EnvS<0>, H) % 16 == 0 && offsetof(EnvS<1>, H) % 16 == 0 && offsetof(EnvS<2>, H) % 16 == 0, "factor storage must be 16-byte aligned (128-bit loads)");
 static_assert(sizeof(EnvS<0>) % 16 == 0 && sizeof(EnvS<1>) % 16 == 0 && sizeof(EnvS<2>) % 16 == 0, "per-env records must keep 16-byte alignment");
@@ -894,8 +906,307 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
   return ncon + total;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Convex hulls (mesh geoms): mjc_Convex / mjc_PlaneConvex.  MuJoCo hands hull pairs to libccd's ccdMPRPenetration (Minkowski
+// Portal Refinement, tolerance 1e-6, 50 iterations) with support mappings over the hull vertices / box corners and the geom
+// centres as interior points; one contact per pair.  The portal algebra is scalar and runs uniformly on every lane (the portal
+// lives in the collision scratch, reads are broadcasts); the support mapping is the parallel part: lanes stride over the hull's
+// vertices in global memory and an arg-max butterfly picks the winner (lowest index on ties, like the oracle's first maximum).
+#define HS_CEN 0        // world centres of the hulls [MCB_MAXHULL][3]
+#define HS_P 48         // portal: 4 points x (v, v1, v2)
+#define HS_V4 84        // candidate point (v, v1, v2)
+#define CCD_EPS 2.220446049250313e-16
+struct CvxObj { int kind; int body; const double* verts; int n; const double* size; double pos[3], mat[9]; };   // kind 0 hull, 1 box; pos / mat: world pose of the vertex frame
+
 template <class S>
-__device__ __noinline__ void collide(S& s, int lane, int nba) {
+__device__ void cvx_support(const S& s, const CvxObj& o, const double* dir, double* out, int lane) {
+  double ld[3], best[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ld[k] = o.mat[k] * dir[0] + o.mat[3 + k] * dir[1] + o.mat[6 + k] * dir[2];
+  if (o.kind == 1) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) best[k] = ld[k] > 0 ? o.size[k] : -o.size[k];
+  } else {
+    // the lowest-index vertex within 1e-11 of the maximum (two passes): coplanar hull vertices tie up to rounding, see the oracle
+    double bd = -1e300;
+    for (int i = lane; i < o.n; i += 32) {
+      const double* v = o.verts + 3 * i;
+      const double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
+      if (t > bd) bd = t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const double od = shfl_xor_d(bd, off); if (od > bd) bd = od; }
+    int bi = 0x7fffffff;
+    for (int i = lane; i < o.n; i += 32) {
+      const double* v = o.verts + 3 * i;
+      const double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
+      if (t >= bd - 1e-11) { bi = i; break; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const int oi = __shfl_xor_sync(FULLMASK, bi, off); if (oi < bi) bi = oi; }
+    const double* v = o.verts + 3 * bi;
+    best[0] = v[0]; best[1] = v[1]; best[2] = v[2];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) out[r] = o.pos[r] + o.mat[3 * r] * best[0] + o.mat[3 * r + 1] * best[1] + o.mat[3 * r + 2] * best[2];
+}
+// support of the Minkowski difference A - B into a 9-double slot (v, v1, v2) of the scratch
+template <class S>
+__device__ void mpr_support(S& s, const CvxObj& A, const CvxObj& B, const double* dir, double* slot, int lane) {
+  double nd[3] = {-dir[0], -dir[1], -dir[2]}, p1[3], p2[3];
+  cvx_support(s, A, dir, p1, lane);
+  cvx_support(s, B, nd, p2, lane);
+  __syncwarp();
+  if (lane == 0) { for (int k = 0; k < 3; k++) { slot[k] = p1[k] - p2[k]; slot[3 + k] = p1[k]; slot[6 + k] = p2[k]; } }
+  __syncwarp();
+}
+__device__ __forceinline__ bool ccd_zero(double x) { return fabs(x) < CCD_EPS; }
+__device__ __forceinline__ bool ccd_eq(double a, double b) {
+  double ab = fabs(a - b);
+  if (ab < CCD_EPS) return true;
+  a = fabs(a); b = fabs(b);
+  return b > a ? ab < CCD_EPS * b : ab < CCD_EPS * a;
+}
+__device__ __forceinline__ void normalize3_d(double* v) {
+  const double n = sqrt(dot3(v, v));
+  if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; } else { v[0] /= n; v[1] /= n; v[2] /= n; }
+}
+__device__ __forceinline__ void copy9(double* d, const double* sarr, int lane) { __syncwarp(); if (lane < 9) d[lane] = sarr[lane]; __syncwarp(); }
+__device__ __forceinline__ void portal_dir(const double* P, double* dir) {
+  double a[3], b[3];
+  for (int k = 0; k < 3; k++) { a[k] = P[18 + k] - P[9 + k]; b[k] = P[27 + k] - P[9 + k]; }
+  cross3(dir, a, b);
+  normalize3_d(dir);
+}
+__device__ __forceinline__ bool portal_reach_tol(const double* P, const double* v4, const double* dir, double tol) {
+  const double dv4 = dot3(v4, dir);
+  double d1 = dv4 - dot3(P + 9, dir), d2 = dv4 - dot3(P + 18, dir), d3 = dv4 - dot3(P + 27, dir);
+  d1 = fmin(d1, fmin(d2, d3));
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+__device__ __forceinline__ void expand_portal(double* P, const double* v4, int lane) {
+  double v4v0[3];
+  cross3(v4v0, v4, P);
+  int slot;
+  if (dot3(P + 9, v4v0) > 0) slot = dot3(P + 18, v4v0) > 0 ? 1 : 3;
+  else slot = dot3(P + 27, v4v0) > 0 ? 2 : 1;
+  copy9(P + 9 * slot, v4, lane);
+}
+// squared distance of the origin to triangle (a, b, c), closest point in w (Ericson 5.1.5; same branches as the oracle)
+__device__ double origin_tri_dist2(const double* a, const double* b, const double* c, double* w) {
+  double ab[3], ac[3], ap[3], bp[3], cp[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = -a[k]; bp[k] = -b[k]; cp[k] = -c[k]; }
+  const double d1 = dot3(ab, ap), d2 = dot3(ac, ap), d3 = dot3(ab, bp), d4 = dot3(ac, bp), d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  double u, v;
+  if (d1 <= 0 && d2 <= 0) { u = 0; v = 0; }
+  else if (d3 >= 0 && d4 <= d3) { u = 1; v = 0; }
+  else if (d1 * d4 - d3 * d2 <= 0 && d1 >= 0 && d3 <= 0) { u = d1 / (d1 - d3); v = 0; }
+  else if (d6 >= 0 && d5 <= d6) { u = 0; v = 1; }
+  else if (d5 * d2 - d1 * d6 <= 0 && d2 >= 0 && d6 <= 0) { u = 0; v = d2 / (d2 - d6); }
+  else if (d3 * d6 - d5 * d4 <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { v = (d4 - d3) / ((d4 - d3) + (d5 - d6)); u = 1 - v; }
+  else { const double va = d3 * d6 - d5 * d4, vb = d5 * d2 - d1 * d6, vc = d1 * d4 - d3 * d2, den = 1 / (va + vb + vc); u = vb * den; v = vc * den; }
+  for (int k = 0; k < 3; k++) w[k] = a[k] + u * ab[k] + v * ac[k];
+  return dot3(w, w);
+}
+// ccdMPRPenetration: true and (depth, dir from A to B, pos) if the two convex objects intersect.  Uniform on all lanes.
+template <class S>
+__device__ __noinline__ bool mpr_penetration(S& s, const CvxObj& A, const CvxObj& B, const double* cA, const double* cB, double& depth, double* dir, double* pos, int lane) {
+  const double tol = 1e-6; const int maxiter = 50;
+  double* P = s.cscr + HS_P;
+  double* V4 = s.cscr + HS_V4;
+  double d[3], va[3], vb[3], dot;
+  __syncwarp();
+  if (lane < 3) { P[3 + lane] = cA[lane]; P[6 + lane] = cB[lane]; P[lane] = cA[lane] - cB[lane]; }
+  __syncwarp();
+  if (ccd_zero(P[0]) && ccd_zero(P[1]) && ccd_zero(P[2])) { __syncwarp(); if (lane == 0) P[0] += CCD_EPS * 10; __syncwarp(); }
+  for (int k = 0; k < 3; k++) d[k] = -P[k];
+  normalize3_d(d);
+  mpr_support(s, A, B, d, P + 9, lane);
+  dot = dot3(P + 9, d);
+  if (ccd_zero(dot) || dot < 0) return false;
+  cross3(d, P, P + 9);
+  if (ccd_zero(dot3(d, d))) {
+    depth = sqrt(dot3(P + 9, P + 9));
+    for (int k = 0; k < 3; k++) { dir[k] = P[9 + k]; pos[k] = 0.5 * (P[12 + k] + P[15 + k]); }
+    normalize3_d(dir);
+    return true;
+  }
+  normalize3_d(d);
+  mpr_support(s, A, B, d, P + 18, lane);
+  dot = dot3(P + 18, d);
+  if (ccd_zero(dot) || dot < 0) return false;
+  for (int k = 0; k < 3; k++) { va[k] = P[9 + k] - P[k]; vb[k] = P[18 + k] - P[k]; }
+  cross3(d, va, vb);
+  normalize3_d(d);
+  if (dot3(d, P) > 0) {
+    __syncwarp();
+    double t = 0;
+    if (lane < 9) t = P[9 + lane];
+    __syncwarp();
+    if (lane < 9) { P[9 + lane] = P[18 + lane]; }
+    __syncwarp();
+    if (lane < 9) P[18 + lane] = t;
+    __syncwarp();
+    for (int k = 0; k < 3; k++) d[k] = -d[k];
+  }
+  for (int guard = 0; guard < 100; guard++) {
+    mpr_support(s, A, B, d, P + 27, lane);
+    dot = dot3(P + 27, d);
+    if (ccd_zero(dot) || dot < 0) return false;
+    bool cont = false;
+    cross3(va, P + 9, P + 27);
+    dot = dot3(va, P);
+    if (dot < 0 && !ccd_zero(dot)) { copy9(P + 18, P + 27, lane); cont = true; }
+    if (!cont) {
+      cross3(va, P + 27, P + 18);
+      dot = dot3(va, P);
+      if (dot < 0 && !ccd_zero(dot)) { copy9(P + 9, P + 27, lane); cont = true; }
+    }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = P[9 + k] - P[k]; vb[k] = P[18 + k] - P[k]; }
+    cross3(d, va, vb);
+    normalize3_d(d);
+    if (guard == 99) return false;
+  }
+  for (int guard = 0;; guard++) {                       // refinePortal
+    portal_dir(P, d);
+    dot = dot3(d, P + 9);
+    if (ccd_zero(dot) || dot > 0) break;
+    mpr_support(s, A, B, d, V4, lane);
+    dot = dot3(V4, d);
+    if (!(ccd_zero(dot) || dot > 0) || portal_reach_tol(P, V4, d, tol)) return false;
+    expand_portal(P, V4, lane);
+    if (guard > 1000) return false;
+  }
+  for (int it = 0;; it++) {                             // findPenetr
+    portal_dir(P, d);
+    mpr_support(s, A, B, d, V4, lane);
+    if (portal_reach_tol(P, V4, d, tol) || it > maxiter) {
+      double w[3];
+      depth = sqrt(origin_tri_dist2(P + 9, P + 18, P + 27, w));
+      if (ccd_zero(w[0]) && ccd_zero(w[1]) && ccd_zero(w[2])) { for (int k = 0; k < 3; k++) dir[k] = d[k]; depth = 0; }
+      else { for (int k = 0; k < 3; k++) dir[k] = w[k]; normalize3_d(dir); }
+      double b[4], t[3], sum;
+      cross3(t, P + 9, P + 18); b[0] = dot3(t, P + 27);
+      cross3(t, P + 27, P + 18); b[1] = dot3(t, P);
+      cross3(t, P, P + 9); b[2] = dot3(t, P + 27);
+      cross3(t, P + 18, P + 9); b[3] = dot3(t, P);
+      sum = b[0] + b[1] + b[2] + b[3];
+      if (ccd_zero(sum) || sum < 0) {
+        b[0] = 0;
+        cross3(t, P + 18, P + 27); b[1] = dot3(t, d);
+        cross3(t, P + 27, P + 9); b[2] = dot3(t, d);
+        cross3(t, P + 9, P + 18); b[3] = dot3(t, d);
+        sum = b[1] + b[2] + b[3];
+      }
+      const double inv = 1.0 / sum;
+      for (int k = 0; k < 3; k++) {
+        const double p1 = b[0] * P[3 + k] + b[1] * P[12 + k] + b[2] * P[21 + k] + b[3] * P[30 + k];
+        const double p2 = b[0] * P[6 + k] + b[1] * P[15 + k] + b[2] * P[24 + k] + b[3] * P[33 + k];
+        pos[k] = 0.5 * (p1 + p2) * inv;
+      }
+      return true;
+    }
+    expand_portal(P, V4, lane);
+  }
+}
+// hull x {plane, box, hull} for the statically filtered pairs, after the primitive pairs (the oracle's order)
+template <class S>
+__device__ __noinline__ int collide_hulls(S& s, int lane, int nba, int ncon) {
+  double* cen = s.cscr + HS_CEN;
+  __syncwarp();
+  for (int w = lane; w < MDL.nhull * 3; w += 32) {
+    const int h = w / 3, r = w - 3 * h, b = MDL.hull_body[h];
+    const double* c = MDL.hull_center[h];
+    const double* R = s.xmat + b * 9;
+    cen[w] = s.xpos[b * 3 + r] + R[3 * r] * c[0] + R[3 * r + 1] * c[1] + R[3 * r + 2] * c[2];
+  }
+  __syncwarp();
+  for (int base = 0; base < MDL.nhpair; base += 32) {
+    const int p = base + lane;
+    bool near = false;
+    if (p < MDL.nhpair) {
+      const int oa = MDL.hpair_a[p], ob = MDL.hpair_b[p], hb = ob - MCB_NGEOM;
+      if (oa < MCB_NGEOM) {
+        const int g = oa, bg = MDL.d.geom_body[g];
+        if (!(nba <= CUBE && bg == CUBE)) {
+          double pg[3];
+          const double* gp = MDL.d.geom_pos[g];
+          if (bg < 0) { pg[0] = gp[0]; pg[1] = gp[1]; pg[2] = gp[2]; }
+          else { const double* R = s.xmat + bg * 9; for (int r = 0; r < 3; r++) pg[r] = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+          const double dif[3] = {cen[hb * 3] - pg[0], cen[hb * 3 + 1] - pg[1], cen[hb * 3 + 2] - pg[2]};
+          if (MDL.d.geom_type[g] == 0) { const double* gm = MDL.d.geom_mat[g]; const double nrm[3] = {gm[2], gm[5], gm[8]}; near = dot3(dif, nrm) <= MDL.hull_rbound[hb]; }
+          else { const double bound = MDL.hull_rbound[hb] + MDL.d.geom_rbound[g]; near = dot3(dif, dif) <= bound * bound; }
+        }
+      } else {
+        const int ha = oa - MCB_NGEOM;
+        const double dif[3] = {cen[ha * 3] - cen[hb * 3], cen[ha * 3 + 1] - cen[hb * 3 + 1], cen[ha * 3 + 2] - cen[hb * 3 + 2]};
+        const double bound = MDL.hull_rbound[ha] + MDL.hull_rbound[hb];
+        near = dot3(dif, dif) <= bound * bound;
+      }
+    }
+    unsigned todo = __ballot_sync(FULLMASK, near);
+    while (todo) {
+      const int q = base + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int oa = MDL.hpair_a[q], ob = MDL.hpair_b[q], hb = ob - MCB_NGEOM;
+      CvxObj B;
+      B.kind = 0; B.body = MDL.hull_body[hb]; B.verts = MDL.hull_vert + 3 * (size_t)MDL.hull_vadr[hb]; B.n = MDL.hull_vnum[hb]; B.size = nullptr;
+      for (int k = 0; k < 3; k++) B.pos[k] = s.xpos[B.body * 3 + k];
+      for (int k = 0; k < 9; k++) B.mat[k] = s.xmat[B.body * 9 + k];
+      bool hit = false; double dist = 0, nrm[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
+      if (oa < MCB_NGEOM && MDL.d.geom_type[oa] == 0) {
+        // mjc_PlaneConvex: the hull's support point against the plane normal (planes are static)
+        const double* gm = MDL.d.geom_mat[oa];
+        const double* gp = MDL.d.geom_pos[oa];
+        const double n[3] = {gm[2], gm[5], gm[8]}, nn[3] = {-gm[2], -gm[5], -gm[8]};
+        double sp[3];
+        cvx_support(s, B, nn, sp, lane);
+        const double dif[3] = {sp[0] - gp[0], sp[1] - gp[1], sp[2] - gp[2]};
+        dist = dot3(dif, n);
+        if (!(dist > 0)) { hit = true; for (int k = 0; k < 3; k++) { nrm[k] = n[k]; pos[k] = sp[k] - 0.5 * dist * n[k]; } }
+      } else {
+        CvxObj A;
+        double cA[3];
+        if (oa < MCB_NGEOM) {
+          const int g = oa, bg = MDL.d.geom_body[g];
+          A.kind = 1; A.body = bg; A.verts = nullptr; A.n = 0; A.size = MDL.d.geom_size[g];
+          const double* gp = MDL.d.geom_pos[g];
+          const double* gm = MDL.d.geom_mat[g];
+          if (bg < 0) { for (int k = 0; k < 3; k++) A.pos[k] = gp[k]; for (int k = 0; k < 9; k++) A.mat[k] = gm[k]; }
+          else {
+            const double* R = s.xmat + bg * 9;
+            for (int r = 0; r < 3; r++) {
+              A.pos[r] = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
+              for (int c = 0; c < 3; c++) A.mat[3 * r + c] = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c];
+            }
+          }
+          for (int k = 0; k < 3; k++) cA[k] = A.pos[k];
+        } else {
+          const int ha = oa - MCB_NGEOM;
+          A.kind = 0; A.body = MDL.hull_body[ha]; A.verts = MDL.hull_vert + 3 * (size_t)MDL.hull_vadr[ha]; A.n = MDL.hull_vnum[ha]; A.size = nullptr;
+          for (int k = 0; k < 3; k++) { A.pos[k] = s.xpos[A.body * 3 + k]; cA[k] = cen[ha * 3 + k]; }
+          for (int k = 0; k < 9; k++) A.mat[k] = s.xmat[A.body * 9 + k];
+        }
+        const double cB[3] = {cen[hb * 3], cen[hb * 3 + 1], cen[hb * 3 + 2]};
+        double depth = 0;
+        hit = mpr_penetration(s, A, B, cA, cB, depth, nrm, pos, lane);
+        dist = -depth;
+      }
+      if (hit) {
+        __syncwarp();
+        if (lane == 0 && ncon < S::MAXC) emit_contact(s, ncon, MCB_MAXPAIR + q, dist, pos, nrm);
+        ncon++;
+        __syncwarp();
+      }
+    }
+  }
+  return ncon;
+}
+
+template <class S>
+__device__ __noinline__ void collide(S& s, int lane, int nba, bool mesh) {
   // broad phase: lane = candidate pair
   bool near = false;
   if (lane < MDL.d.npair) {
@@ -936,6 +1247,7 @@ __device__ __noinline__ void collide(S& s, int lane, int nba) {
     else ncon = box_box_coop(s, lane, p, ncon, p1, R1, MDL.d.geom_size[g1], p2, R2, MDL.d.geom_size[g2]);
     __syncwarp();
   }
+  if (mesh && MDL.nhull > 0) ncon = collide_hulls(s, lane, nba, ncon);
   if (lane == 0) {
     if (ncon > S::MAXC) { s.overflow += ncon - S::MAXC; ncon = S::MAXC; }
     s.ncon = ncon;
@@ -1066,7 +1378,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     const int ne0 = MDL.d.has_weld ? 13 : 7;
     int nc = s.ncon;
     int pt = -1, rows = 0;
-    if (lane < nc) { const PairParam& pp = MDL.pair[s.cpair[lane]]; pt = pp.ptype; rows = 2 * (pp.dim - 1); }
+    if (lane < nc) { const PairParam& pp = PP(s.cpair[lane]); pt = pp.ptype; rows = 2 * (pp.dim - 1); }
     unsigned m0 = __ballot_sync(FULLMASK, pt == 0), m1 = __ballot_sync(FULLMASK, pt == 1), m2 = __ballot_sync(FULLMASK, pt == 2);
     unsigned m6 = __ballot_sync(FULLMASK, rows == 6);
     auto count = [&](unsigned m) { return 4 * __popc(m) + 2 * __popc(m & m6); };
@@ -1089,20 +1401,18 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       const unsigned mg = pt == 0 ? m0 : pt == 1 ? m1 : m2;
       const int start = pt == 0 ? ne0 : pt == 1 ? nR : nR + nC;
       s.crow[lane] = start + count(mg & lt);
-      s.cscr[lane] = (double)(ne0 + nU + count((m0 | m1 | m2) & lt));   // collision scratch is free again: contact's first row in MuJoCo's ordering
     }
     if (lane == 0) { s.nR = nR; s.nC = nC; s.nF = nF; s.nU = nU; s.nefc = nR + nC + nF + nU; }
   }
   __syncwarp();
   const int ne0 = MDL.d.has_weld ? 13 : 7, eq0 = ne0 - 7;      // equality rows: [weld (6)] connect (3 + 3) joint coupling (1)
-  if (lane < 7) { s.rmeta[eq0 + lane] = lane < 6 ? ((lane / 3) | ((lane % 3) << 9)) : (1 << 12); s.omap[eq0 + lane] = eq0 + lane; }
-  if (lane < eq0) { s.rmeta[lane] = (lane << 9) | (4 << 12); s.omap[lane] = lane; }
+  if (lane < 7) { s.rmeta[eq0 + lane] = lane < 6 ? ((lane / 3) | ((lane % 3) << 9)) : (1 << 12); }
+  if (lane < eq0) { s.rmeta[lane] = (lane << 9) | (4 << 12); }
   for (int w = lane; w < s.ncon * 6; w += 32) {
     int c = w / 6, k = w % 6;
-    if (k < 2 * (MDL.pair[s.cpair[c]].dim - 1)) {
+    if (k < 2 * (PP(s.cpair[c]).dim - 1)) {
       int r = s.crow[c] + k;
       s.rmeta[r] = c | (k << 9) | (3 << 12) | RM_INEQ;
-      s.omap[r] = (int)s.cscr[c] + k;
     }
   }
   __syncwarp();     // cscr aliases the first pool rows, which the equality fill below overwrites
@@ -1110,7 +1420,6 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     int u = __popc(bal & ((1u << lane) - 1));
     int r = s.nR + s.nC + s.nF + u;
     s.rmeta[r] = lane | (neg << 8) | (2 << 12) | RM_INEQ;
-    s.omap[r] = ne0 + u;
   }
   // equality Jacobian rows (robot block): item = (connect e, dof j) -> its three rows
   for (int w = lane; w < 2 * NH; w += 32) {
@@ -1180,9 +1489,9 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
     const int ncol = pt == 0 ? NH : pt == 1 ? 6 : NV, j0 = pt == 1 ? NH : 0;
     for (int w = lane; w < ncon * ncol; w += 32) {
       int c = w / ncol, j = j0 + w % ncol;
-      const PairParam& pp = MDL.pair[s.cpair[c]];
+      const PairParam& pp = PP(s.cpair[c]);
       if (pp.ptype != pt) continue;
-      int b1 = MDL.d.geom_body[pp.g1], b2 = MDL.d.geom_body[pp.g2];
+      int b1 = pp.b1, b2 = pp.b2;
       const double* pt3 = s.cpos + c * 3;
       const double* f = s.cframe + c * 9;
       double l1[3], r1[3], l2[3], r2[3];
@@ -1237,7 +1546,7 @@ __device__ bool make_rows(S& s, const DevModel* __restrict__ m, int lane, int nv
       pos = (meta & 0x100) ? MDL.d.jnt_range[idx][1] - v : v - MDL.d.jnt_range[idx][0];
       KB = MDL.d.jnt_solref[idx]; solimp = MDL.d.jnt_solimp[idx]; diag = MDL.d.dof_invweight0[idx];
     } else {
-      const PairParam& pp = MDL.pair[s.cpair[idx]];
+      const PairParam& pp = PP(s.cpair[idx]);
       double mu = pp.friction[0];
       pos = s.cdist[idx];
       KB = pp.KB; solimp = pp.solimp;
@@ -1658,7 +1967,7 @@ __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int l
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
   FSYNC();
-  collide(s, lane, nba);
+  collide(s, lane, nba, s.mesh != 0);
   FSYNC();
   bool ok = make_rows(s, m, lane, nva);
   FSYNC();
@@ -1988,6 +2297,18 @@ __device__ __noinline__ bool reset_env(S& s, const StepArgs& a, const DevModel* 
   return ok;
 }
 
+// position of row r in MuJoCo's ordering (equality, limits, contacts in detection order) -- debug taps only
+template <class S>
+__device__ int row_order(const S& s, int r) {
+  const int ne0 = MDL.d.has_weld ? 13 : 7;
+  const int meta = s.rmeta[r], kind = (meta >> 12) & 7;
+  if (kind == 2) return ne0 + (r - (s.nR + s.nC + s.nF));
+  if (kind != 3) return r;
+  const int c = meta & 0xff, k = (meta >> 9) & 7;
+  int o = ne0 + s.nU;
+  for (int q = 0; q < c; q++) o += 2 * (PP(s.cpair[q]).dim - 1);
+  return o + k;
+}
 template <class S>
 __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
   // layout (doubles): [0] nefc [1] ncon [2] iters [3] overflow | M(18*18) | bias smooth qacc_smooth qacc qfrc_con | xpos(39) xmat(117)
@@ -2014,10 +2335,10 @@ __device__ void debug_dump(S& s, const StepArgs& a, int lane, int nva) {
     else if (r < s.nR + s.nC) v = j >= NH ? row_c(s, r)[j - NH] : 0.0;
     else if (r < s.nR + s.nC + s.nF) v = row_f(s, r)[j];
     else { int meta = s.rmeta[r]; v = ((meta & 0xff) == j) ? ((meta & 0x100) ? -1.0 : 1.0) : 0.0; }
-    o[s.omap[r] * NV + j] = v;
+    o[row_order(s, r) * NV + j] = v;
   }
   o += nefc * NV;
-  for (int w = lane; w < nefc; w += 32) { o[s.omap[w]] = s.earef[w]; o[nefc + s.omap[w]] = s.eD[w]; }
+  for (int w = lane; w < nefc; w += 32) { const int q = row_order(s, w); o[q] = s.earef[w]; o[nefc + q] = s.eD[w]; }
   o += 2 * nefc;
   for (int w = lane; w < s.ncon; w += 32) {
     o[w * 7] = s.cdist[w];
@@ -2088,7 +2409,7 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
     for (int w = lane; w < NB * 3; w += 32) s.xpos[w] = 0;
     for (int w = lane; w < NV * 6; w += 32) { s.cdof[w] = 0; s.cdof_dot[w] = 0; }
     if (lane < NV) { s.qfrc_bias[lane] = 0; s.qfrc_con[lane] = 0; s.qacc[lane] = 0; s.qacc_smooth[lane] = 0; s.qfrc_smooth[lane] = 0; s.Ma[lane] = 0; s.grad[lane] = 0; s.search[lane] = 0; s.Mv[lane] = 0; }
-    if (lane == 0) { s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = MDL.d.has_weld ? 13 : 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
+    if (lane == 0) { s.mesh = a.cfg.mesh_collision; s.overflow = 0; s.iters = 0; s.nefc = 0; s.ncon = 0; s.nR = MDL.d.has_weld ? 13 : 7; s.nC = s.nF = s.nU = 0; s.refcube[0] = s.refcube[1] = s.refcube[2] = 0; }
 #ifdef MCB_CANARY
     if (lane < 2) { const double c = __longlong_as_double(0x7ff8c0decafe0000ll + lane); s.g0[lane] = c; s.g1[lane] = c; s.g2[lane] = c; s.g3[lane] = c; s.g4[lane] = c; s.g5[lane] = c; s.g6[lane] = c; s.g7[lane] = c; }
 #endif
@@ -2231,7 +2552,7 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
           double r_reach = (1 - tanh(sqrt(gx * gx + gy * gy + gz * gz))) * 0.2;
           bool tr = false, tl = false;
           for (int c = 0; c < s.ncon; c++) {
-            const PairParam& pp = MDL.pair[s.cpair[c]];
+            const PairParam& pp = PP(s.cpair[c]);
             bool hasobj = pp.g1 == MDL.d.geom_object || pp.g2 == MDL.d.geom_object;
             if (hasobj && (pp.g1 == MDL.d.geom_finger_r || pp.g2 == MDL.d.geom_finger_r)) tr = true;
             if (hasobj && (pp.g1 == MDL.d.geom_finger_l || pp.g2 == MDL.d.geom_finger_l)) tl = true;
@@ -2404,6 +2725,8 @@ struct mcb_model {
   int device;
   DevModel* dev;
   DevModel host;
+  double* d_hull_vert = nullptr;
+  PairParam* d_hpair = nullptr;
 };
 
 struct mcb_batch {
@@ -2497,6 +2820,7 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
     int g1 = d->pair_g1[p], g2 = d->pair_g2[p];
     PairParam& pp = h.pair[p];
     pp.g1 = g1; pp.g2 = g2;
+    pp.b1 = d->geom_body[g1]; pp.b2 = d->geom_body[g2];
     pp.dim = d->geom_condim[g1] > d->geom_condim[g2] ? d->geom_condim[g1] : d->geom_condim[g2];
     if (pp.dim != 3 && pp.dim != 4) { delete m; return fail("mcb_model_create: only condim 3 and 4 are supported"); }
     double fr[3];
@@ -2549,9 +2873,87 @@ int32_t mcb_model_create(const mcb_model_desc* d, int32_t device, mcb_model** ou
   return 0;
 }
 
+int32_t mcb_hull_desc_size(void) { return (int32_t)sizeof(mcb_hull_desc); }
+
+int32_t mcb_model_set_hulls(mcb_model* m, const mcb_hull_desc* hd) {
+  if (!m || !hd) return fail("mcb_model_set_hulls: null argument");
+  if (hd->nhull < 0 || hd->nhull > MCB_MAXHULL || hd->npair < 0 || hd->npair > MCB_MAXHPAIR || hd->nvert < 0 || (hd->nvert > 0 && !hd->vert))
+    return fail("mcb_model_set_hulls: counts out of range");
+  DevGuard guard(m->device);
+  if (!guard.ok) return fail("mcb_model_set_hulls: cannot select the model's device", cudaGetLastError());
+  DevModel& h = m->host;
+  const mcb_model_desc& d = h.d;
+  std::vector<PairParam> pps((size_t)hd->npair);
+  for (int hq = 0; hq < hd->nhull; hq++) {
+    if (hd->body[hq] < 0 || hd->body[hq] >= NB || hd->vadr[hq] < 0 || hd->vnum[hq] <= 0 || hd->vadr[hq] + hd->vnum[hq] > hd->nvert || hd->mult[hq] < 1 ||
+        (hd->condim[hq] != 3 && hd->condim[hq] != 4))
+      return fail("mcb_model_set_hulls: bad hull (hulls must ride on jointed bodies, condim 3 or 4)");
+    h.hull_body[hq] = hd->body[hq]; h.hull_vadr[hq] = hd->vadr[hq]; h.hull_vnum[hq] = hd->vnum[hq];
+    for (int k = 0; k < 3; k++) h.hull_center[hq][k] = hd->center[hq][k];
+    h.hull_rbound[hq] = hd->rbound[hq];
+  }
+  auto clamp_solimp = [](double* si) {
+    si[0] = fmin(MAXIMP, fmax(MINIMP, si[0])); si[1] = fmin(MAXIMP, fmax(MINIMP, si[1])); si[2] = fmax(0.0, si[2]) <= MINVAL ? 0.0 : 1.0 / si[2];
+    si[3] = fmin(MAXIMP, fmax(MINIMP, si[3])); si[4] = fmax(1.0, si[4]);
+  };
+  for (int p = 0; p < hd->npair; p++) {
+    const int oa = hd->pair_a[p], ob = hd->pair_b[p];
+    if (ob < MCB_NGEOM || ob >= MCB_NGEOM + hd->nhull || oa >= MCB_NGEOM + hd->nhull || (oa >= MCB_NGEOM && oa >= ob)) return fail("mcb_model_set_hulls: bad pair");
+    h.hpair_a[p] = (unsigned char)oa; h.hpair_b[p] = (unsigned char)ob;
+    const int hb = ob - MCB_NGEOM, ha = oa - MCB_NGEOM;
+    // object a: primitive geom or hull; object b: always a hull (mj_contactParam, same priority)
+    const int cd1 = ha >= 0 ? hd->condim[ha] : d.geom_condim[oa];
+    const double* f1 = ha >= 0 ? hd->friction[ha] : d.geom_friction[oa];
+    const double* r1 = ha >= 0 ? hd->solref[ha] : d.geom_solref[oa];
+    const double* i1 = ha >= 0 ? hd->solimp[ha] : d.geom_solimp[oa];
+    const double s1 = ha >= 0 ? hd->solmix[ha] : d.geom_solmix[oa];
+    const double* w1 = ha >= 0 ? hd->invweight[ha] : d.geom_invweight[oa];
+    const int m1 = ha >= 0 ? hd->mult[ha] : 1;
+    const int bo1 = ha >= 0 ? hd->body[ha] : d.geom_body[oa];
+    PairParam& pp = pps[(size_t)p];
+    memset(&pp, 0, sizeof pp);
+    pp.g1 = oa; pp.g2 = ob; pp.b1 = bo1; pp.b2 = hd->body[hb];
+    pp.dim = cd1 > hd->condim[hb] ? cd1 : hd->condim[hb];
+    if (pp.dim != 3 && pp.dim != 4) return fail("mcb_model_set_hulls: only condim 3 and 4 are supported");
+    for (int k = 0; k < 3; k++) pp.friction[k] = fmax(f1[k], hd->friction[hb][k]);
+    const double sa = s1, sb = hd->solmix[hb];
+    double mix;
+    if (sa >= MINVAL && sb >= MINVAL) mix = sa / (sa + sb);
+    else if (sa < MINVAL && sb < MINVAL) mix = 0.5;
+    else if (sa < MINVAL) mix = 0.0; else mix = 1.0;
+    const double* r2 = hd->solref[hb];
+    if (r1[0] > 0 && r2[0] > 0) for (int k = 0; k < 2; k++) pp.KB[k] = mix * r1[k] + (1 - mix) * r2[k];
+    else for (int k = 0; k < 2; k++) pp.KB[k] = fmin(r1[k], r2[k]);
+    for (int k = 0; k < 5; k++) pp.solimp[k] = mix * i1[k] + (1 - mix) * hd->solimp[hb][k];
+    { const bool c1 = pp.b1 == CUBE, c2 = pp.b2 == CUBE, q1 = pp.b1 >= 0 && !c1, q2 = pp.b2 >= 0 && !c2;
+      pp.ptype = ((c1 || c2) && (q1 || q2)) ? 2 : ((c1 || c2) ? 1 : 0); }
+    pp.tran = w1[0] + hd->invweight[hb][0];
+    clamp_solimp(pp.solimp);
+    { double sr0 = pp.KB[0], sr1 = pp.KB[1];        // (K, B) from the mixed solref, refsafe applied -- as for the primitive pairs
+      if (sr0 > 0) sr0 = fmax(sr0, 2 * d.timestep);
+      const double dmax = pp.solimp[1];
+      if (sr0 > 0) { pp.KB[0] = 1 / fmax(MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); pp.KB[1] = 2 / fmax(MINVAL, dmax * sr0); }
+      else { pp.KB[0] = -sr0 / fmax(MINVAL, dmax * dmax); pp.KB[1] = -sr1 / fmax(MINVAL, dmax); } }
+    const double pyr = pp.friction[0] / sqrt(d.impratio);
+    pp.pyr2 = 2 * pyr * pyr / (double)(m1 * hd->mult[hb]);      // `mult` identical contacts (twin mesh geoms) == one contact with R / mult
+  }
+  cudaFree(m->d_hull_vert); cudaFree(m->d_hpair); m->d_hull_vert = nullptr; m->d_hpair = nullptr;
+  if (hd->nvert > 0) {
+    CK(cudaMalloc(&m->d_hull_vert, (size_t)hd->nvert * 3 * sizeof(double)));
+    CK(cudaMemcpy(m->d_hull_vert, hd->vert, (size_t)hd->nvert * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (hd->npair > 0) {
+    CK(cudaMalloc(&m->d_hpair, (size_t)hd->npair * sizeof(PairParam)));
+    CK(cudaMemcpy(m->d_hpair, pps.data(), (size_t)hd->npair * sizeof(PairParam), cudaMemcpyHostToDevice));
+  }
+  h.nhull = hd->nhull; h.nhpair = hd->npair; h.hull_vert = m->d_hull_vert; h.hpair_param = m->d_hpair;
+  CK(cudaMemcpy(m->dev, &h, sizeof(DevModel), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int32_t mcb_model_destroy(mcb_model* m) {
   if (!m) return 0;
-  cudaFree(m->dev);
+  cudaFree(m->dev); cudaFree(m->d_hull_vert); cudaFree(m->d_hpair);
   delete m;
   return 0;
 }
@@ -2563,6 +2965,7 @@ int32_t mcb_batch_create(mcb_model* m, int32_t n_envs, const mcb_task_cfg* cfg, 
   if (cfg->controller_type < 0 || cfg->controller_type > 2) return fail("mcb_batch_create: controller_type must be 0 (joint), 1 (IK) or 2 (mocap)");
   if ((cfg->controller_type == 2) != (m->host.d.has_weld != 0)) return fail("mcb_batch_create: the mocap controller needs the mocap model variant, the other controllers the joint variant");
   if (cfg->fetch_env && cfg->controller_type == 0) return fail("mcb_batch_create: joint controller is not supported for fetch envs (mycobot.py:96)");
+  if (cfg->mesh_collision && m->host.nhull == 0) return fail("mcb_batch_create: mesh_collision needs mcb_model_set_hulls first");
   if (cfg->controller_type == 1 && (cfg->control_steps < 1 || cfg->control_steps > 50)) return fail("mcb_batch_create: control_steps out of range");
   if (cfg->reward_type < 0 || cfg->reward_type > 2) return fail("mcb_batch_create: reward_type must be 0 (sparse), 1 (dense) or 2 (reward_shaping)");
   DevGuard guard(m->device);

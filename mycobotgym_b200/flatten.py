@@ -17,6 +17,7 @@ from . import mjcf
 from .mjcf import quat2mat, quat_mul
 
 NB, NV, NQ, NU, NHINGE, NGEOM, MAXPAIR = 13, 18, 19, 7, 12, 5, 12
+MAXHULL, MAXHPAIR = 16, 192
 
 _d = C.c_double
 _i = C.c_int32
@@ -61,8 +62,21 @@ class TaskCfg(C.Structure):
     _fields_ = [
         ("has_object", _i), ("block_gripper", _i), ("target_in_the_air", _i), ("reward_type", _i),
         ("max_episode_steps", _i), ("frame_skip", _i), ("auto_reset", _i), ("nefc_max", _i),
-        ("controller_type", _i), ("fetch_env", _i), ("control_steps", _i), ("lockstep_warps", _i),
+        ("controller_type", _i), ("fetch_env", _i), ("control_steps", _i), ("mesh_collision", _i), ("reserved1_", _i),
+        ("lockstep_warps", _i),
         ("distance_threshold", _d),
+    ]
+
+
+class HullDesc(C.Structure):
+    """mcb_hull_desc (include/mycobot_b200.h): convex hulls of the mesh geoms in the frames of the REDUCED model's bodies."""
+    _fields_ = [
+        ("nhull", _i), ("npair", _i), ("nvert", _i), ("reserved_", _i),
+        ("body", _i * MAXHULL), ("vadr", _i * MAXHULL), ("vnum", _i * MAXHULL), ("mult", _i * MAXHULL), ("condim", _i * MAXHULL),
+        ("center", _d * 3 * MAXHULL), ("rbound", _d * MAXHULL), ("friction", _d * 3 * MAXHULL), ("solref", _d * 2 * MAXHULL),
+        ("solimp", _d * 5 * MAXHULL), ("solmix", _d * MAXHULL), ("invweight", _d * 2 * MAXHULL),
+        ("pair_a", C.c_uint8 * MAXHPAIR), ("pair_b", C.c_uint8 * MAXHPAIR),
+        ("vert", C.POINTER(_d)),
     ]
 
 
@@ -311,3 +325,55 @@ def reduce_model(m) -> ModelDesc:
     _set(d.key_qpos, m["key_qpos"][0])
     _set(d.key_ctrl, padu(m["key_ctrl"][0]))
     return d
+
+
+def reduce_hulls(m):
+    """Convex hulls of the mesh geoms -> `mcb_hull_desc`: vertices / interior points moved into the frame of the jointed body the
+    mesh's body is welded to (flange and gripper_base ride on link6), candidate pairs after MuJoCo's static filters (same weld
+    body, parent-child unless one side is welded to the world, <contact><exclude>; all contype / conaffinity are 1).  Returns
+    (desc, vertex array) -- the array must stay alive until mcb_model_set_hulls has copied it."""
+    nh = int(m.get("nhull", 0))
+    d = HullDesc()
+    assert nh <= MAXHULL
+    jointed = [b for b in range(int(m["nbody"])) if m["body_jntnum"][b] > 0]
+    jidx = {b: k for k, b in enumerate(jointed)}
+    verts = np.zeros((int(m["hull_vertnum"].sum()) if nh else 0, 3))
+    d.nhull, d.nvert = nh, len(verts)
+    for h in range(nh):
+        hb = int(m["hull_bodyid"][h])
+        w = int(m["body_weldid"][hb])
+        pos, quat = _rel_pose(m, hb, w if w != 0 else 0)
+        R = quat2mat(quat)
+        a, n = int(m["hull_vertadr"][h]), int(m["hull_vertnum"][h])
+        verts[a:a + n] = m["hull_vert"][a:a + n] @ R.T + pos
+        d.body[h] = jidx[w] if w != 0 else -1
+        d.vadr[h], d.vnum[h], d.mult[h], d.condim[h] = a, n, int(m["hull_mult"][h]), int(m["hull_condim"][h])
+        _set(d.center[h], R @ m["hull_center"][h] + pos)
+        d.rbound[h] = float(m["hull_rbound"][h])
+        _set(d.friction[h], m["hull_friction"][h]); _set(d.solref[h], m["hull_solref"][h]); _set(d.solimp[h], m["hull_solimp"][h])
+        d.solmix[h] = float(m["hull_solmix"][h])
+        _set(d.invweight[h], m["body_invweight0"][hb])
+    excl = {tuple(e) for e in m["exclude"].tolist()}
+    par, weld = m["body_parentid"], m["body_weldid"]
+
+    def filtered(b1, b2):
+        w1, w2 = int(weld[b1]), int(weld[b2])
+        if w1 == w2 or (min(b1, b2), max(b1, b2)) in excl:
+            return True
+        return bool(w1 and w2 and (weld[par[w1]] == w2 or weld[par[w2]] == w1))
+
+    pairs = []
+    for h in range(nh):                       # the oracle's order: hull h against every primitive, then against the later hulls
+        for g in range(int(m["ngeom"])):
+            if not filtered(int(m["geom_bodyid"][g]), int(m["hull_bodyid"][h])):
+                pairs.append((g, NGEOM + h))
+        for h2 in range(h + 1, nh):
+            if not filtered(int(m["hull_bodyid"][h]), int(m["hull_bodyid"][h2])):
+                pairs.append((NGEOM + h, NGEOM + h2))
+    assert len(pairs) <= MAXHPAIR, len(pairs)
+    d.npair = len(pairs)
+    for i, (a, b) in enumerate(pairs):
+        d.pair_a[i], d.pair_b[i] = a, b
+    verts = np.ascontiguousarray(verts)
+    d.vert = verts.ctypes.data_as(C.POINTER(_d))
+    return d, verts

@@ -149,6 +149,11 @@ def _device_model(device_index, variant="joint"):
                 desc.geom_size[desc.geom_object][k] = 0.0
         h = C.c_void_p()
         _lib.check(L.mcb_model_create(C.byref(desc), device_index, C.byref(h)))       # restores the caller's current device
+        if int(flat.get("nhull", 0)):
+            # convex hulls of the mesh geoms: registered always, collided only by batches created with mesh_collision=True
+            hd, verts = flatten.reduce_hulls(flat)
+            _lib.check(L.mcb_model_set_hulls(h, C.byref(hd)))
+            del verts
         _MODEL_CACHE[key] = (h, desc, flat)
     return _MODEL_CACHE[key]
 
@@ -164,12 +169,14 @@ class MyCobotVectorEnv:
                  control_steps=5, controller_type="joint", obj_range=0.1, target_in_the_air=True,
                  distance_threshold=0.01, initial_qpos=None, fetch_env=False, reward_type="sparse", frame_skip=20,
                  max_episode_steps=50, device="cuda:0", seed=0, auto_reset=True, goal_source="device", nefc_max=0,
-                 lockstep_warps=0, autotune=True, **kwargs):
+                 lockstep_warps=0, autotune=True, mesh_collision=False, **kwargs):
         """Constructor kwargs are the reference's (mycobot.py:30-46).  `obj_range` and `initial_qpos` are accepted and only
         stored, exactly like the reference does (mycobot.py:54,56 assign them; nothing reads them: the cube is placed by
         `generate_random_point_inside_rectangle`, mycobot.py:220-222, and the start pose is qpos0 / keyframe 0).
         `lockstep_warps=0, autotune=True`: the first full `reset()` ends with one explicit `mcb_autotune` call (it
-        synchronises and is never hidden inside `step`); `autotune=False` keeps the free-running default."""
+        synchronises and is never hidden inside `step`); `autotune=False` keeps the free-running default.
+        `mesh_collision=True`: the convex hulls of the 28 mesh geoms collide too (MuJoCo: mjc_Convex / mjc_PlaneConvex; here one
+        MPR contact per hull pair); off, only the plane / box primitives collide."""
         if controller_type not in ("joint", "IK", "mocap"):
             raise ValueError(f"unknown controller_type {controller_type!r}")
         if fetch_env and controller_type == "joint":
@@ -193,6 +200,7 @@ class MyCobotVectorEnv:
         self._want_autotune = bool(autotune) and int(lockstep_warps) == 0 and int(nefc_max) == 0
         self.max_episode_steps = int(max_episode_steps)
         self.goal_source = goal_source
+        self.mesh_collision = bool(mesh_collision)
         self.auto_reset = bool(auto_reset)
         self._L = _lib.load()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -204,6 +212,7 @@ class MyCobotVectorEnv:
             reward_type={"sparse": 0, "dense": 1, "reward_shaping": 2}[reward_type], max_episode_steps=self.max_episode_steps,
             frame_skip=self.frame_skip, auto_reset=int(self.auto_reset and goal_source == "device"), nefc_max=int(nefc_max),
             controller_type={"joint": 0, "IK": 1, "mocap": 2}[controller_type], fetch_env=int(bool(fetch_env)), control_steps=int(control_steps),
+            mesh_collision=int(bool(mesh_collision)),
             lockstep_warps=int(lockstep_warps), distance_threshold=self.distance_threshold)
         self._cfg = cfg
         with torch.cuda.device(dev_index):

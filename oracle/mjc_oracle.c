@@ -580,6 +580,7 @@ static int box_box(rawcon* out, const double* p1, const double* R1, const double
 typedef struct { int is_box; const double *pos, *mat, *verts, *size; int n; double center[3]; } cvx;   /* pos / mat: world pose of the vertex frame */
 typedef struct { double v[3], v1[3], v2[3]; } mpt;
 #define CCD_EPS 2.220446049250313e-16
+#define SUPPORT_TIE 1e-11
 static int ccd_zero(double x) { return fabs(x) < CCD_EPS; }
 static int ccd_eq(double a, double b) {
   double ab = fabs(a - b);
@@ -592,11 +593,19 @@ static void cvx_support(const cvx* o, const double* dir, double* out) {
   for (int k = 0; k < 3; k++) ld[k] = o->mat[k] * dir[0] + o->mat[3 + k] * dir[1] + o->mat[6 + k] * dir[2];   /* mat' dir */
   if (o->is_box) { for (int k = 0; k < 3; k++) best[k] = ld[k] > 0 ? o->size[k] : -o->size[k]; }
   else {
+    /* the FIRST vertex within SUPPORT_TIE of the maximum: hull faces carry many coplanar vertices (cylinder caps, flat sides), whose
+       support values tie up to rounding; with a plain arg-max the winner -- and with it the portal MPR ends on -- would be decided
+       by the last bit, differently on every platform */
     double bd = -1e300;
     for (int i = 0; i < o->n; i++) {
       const double* v = o->verts + 3 * i;
       double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
-      if (t > bd) { bd = t; best[0] = v[0]; best[1] = v[1]; best[2] = v[2]; }
+      if (t > bd) bd = t;
+    }
+    for (int i = 0; i < o->n; i++) {
+      const double* v = o->verts + 3 * i;
+      double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
+      if (t >= bd - SUPPORT_TIE) { best[0] = v[0]; best[1] = v[1]; best[2] = v[2]; break; }
     }
   }
   mulmatvec3(out, o->mat, best);

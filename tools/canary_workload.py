@@ -27,6 +27,9 @@ CASES = [
     ("ik", dict(has_object=True, reward_type="sparse", controller_type="IK", lockstep_warps=16), 1024, 7, 8),
     ("fetch ik", dict(has_object=True, reward_type="dense", controller_type="IK", fetch_env=True), 256, 4, 6),
     ("mocap", dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml", lockstep_warps=16), 1024, 8, 12),
+    ("mocap + hull collisions", dict(has_object=True, reward_type="sparse", controller_type="mocap", model_path="./assets/mycobot280_mocap.xml", lockstep_warps=16,
+                                     mesh_collision=True), 128, 8, 10),
+    ("push + hull collisions", dict(has_object=True, block_gripper=True, target_in_the_air=False, reward_type="sparse", mesh_collision=True), 128, 7, 8),
     ("fetch mocap", dict(has_object=True, reward_type="dense", controller_type="mocap", fetch_env=True, model_path="./assets/mycobot280_mocap.xml"), 256, 4, 6),
 ]
 for name, kw, n, adim, steps in CASES:
