@@ -161,7 +161,7 @@ struct EnvS {
 #endif
   enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : 128, POOL = (TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432) - (MCB_NGUARD ? (TIER == 0 ? 10 : 2 * MCB_NGUARD) : 0),   // (tier 0: the row arrays must stay the union's largest member)
          MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : 16,
-         IS_BIG = TIER == 2 };
+         IS_BIG = TIER == 2, TIER_ID = TIER };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
   GUARD(g0)
   double xpos[NB * 3], xmat[NB * 9], cdof[NV * 6], refcube[4];
@@ -917,7 +917,8 @@ __device__ int box_box_coop(S& s, int lane, int pair, int ncon, const double* p1
 #define HS_P 48         // portal: 4 points x (v, v1, v2)
 #define HS_V4 84        // candidate point (v, v1, v2)
 #define CCD_EPS 2.220446049250313e-16
-struct CvxObj { int kind; int body; const double* verts; int n; const double* size; double pos[3], mat[9]; };   // kind 0 hull, 1 box; pos / mat: world pose of the vertex frame
+#define HS_POSE 96      // world poses (pos 3, mat 9) of the pair's two vertex frames: kept in the scratch, not on the threads' stacks
+struct CvxObj { int kind; int body; const double* verts; int n; const double* size; const double *pos, *mat; };   // kind 0 hull, 1 box; pos / mat: world pose of the vertex frame
 
 template <class S>
 __device__ void cvx_support(const S& s, const CvxObj& o, const double* dir, double* out, int lane) {
@@ -1111,9 +1112,9 @@ __device__ __noinline__ bool mpr_penetration(S& s, const CvxObj& A, const CvxObj
     expand_portal(P, V4, lane);
   }
 }
-// hull x {plane, box, hull} for the statically filtered pairs, after the primitive pairs (the oracle's order)
+// world centres of the hulls into the scratch
 template <class S>
-__device__ __noinline__ int collide_hulls(S& s, int lane, int nba, int ncon) {
+__device__ __forceinline__ void hull_centres(S& s, int lane) {
   double* cen = s.cscr + HS_CEN;
   __syncwarp();
   for (int w = lane; w < MDL.nhull * 3; w += 32) {
@@ -1123,38 +1124,61 @@ __device__ __noinline__ int collide_hulls(S& s, int lane, int nba, int ncon) {
     cen[w] = s.xpos[b * 3 + r] + R[3 * r] * c[0] + R[3 * r + 1] * c[1] + R[3 * r + 2] * c[2];
   }
   __syncwarp();
+}
+// bounding-sphere test of candidate hull pair p (lane-local)
+template <class S>
+__device__ __forceinline__ bool hull_pair_near(const S& s, int p, int nba) {
+  const double* cen = s.cscr + HS_CEN;
+  const int oa = MDL.hpair_a[p], ob = MDL.hpair_b[p], hb = ob - MCB_NGEOM;
+  if (oa < MCB_NGEOM) {
+    const int g = oa, bg = MDL.d.geom_body[g];
+    if (nba <= CUBE && bg == CUBE) return false;
+    double pg[3];
+    const double* gp = MDL.d.geom_pos[g];
+    if (bg < 0) { pg[0] = gp[0]; pg[1] = gp[1]; pg[2] = gp[2]; }
+    else { const double* R = s.xmat + bg * 9; for (int r = 0; r < 3; r++) pg[r] = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+    const double dif[3] = {cen[hb * 3] - pg[0], cen[hb * 3 + 1] - pg[1], cen[hb * 3 + 2] - pg[2]};
+    if (MDL.d.geom_type[g] == 0) { const double* gm = MDL.d.geom_mat[g]; const double nrm[3] = {gm[2], gm[5], gm[8]}; return dot3(dif, nrm) <= MDL.hull_rbound[hb]; }
+    const double bound = MDL.hull_rbound[hb] + MDL.d.geom_rbound[g];
+    return dot3(dif, dif) <= bound * bound;
+  }
+  const int ha = oa - MCB_NGEOM;
+  const double dif[3] = {cen[ha * 3] - cen[hb * 3], cen[ha * 3 + 1] - cen[hb * 3 + 1], cen[ha * 3 + 2] - cen[hb * 3 + 2]};
+  const double bound = MDL.hull_rbound[ha] + MDL.hull_rbound[hb];
+  return dot3(dif, dif) <= bound * bound;
+}
+// common-layout tier: broad phase only.  An env with any hull pair inside its bounding spheres leaves for the next tier, whose
+// kernel carries the narrow phase -- the MPR code (and its registers / stack) stays out of the kernel every env runs first.
+template <class S>
+__device__ __noinline__ bool hull_any_near(S& s, int lane, int nba) {
+  hull_centres(s, lane);
+  bool any = false;
   for (int base = 0; base < MDL.nhpair; base += 32) {
     const int p = base + lane;
-    bool near = false;
-    if (p < MDL.nhpair) {
-      const int oa = MDL.hpair_a[p], ob = MDL.hpair_b[p], hb = ob - MCB_NGEOM;
-      if (oa < MCB_NGEOM) {
-        const int g = oa, bg = MDL.d.geom_body[g];
-        if (!(nba <= CUBE && bg == CUBE)) {
-          double pg[3];
-          const double* gp = MDL.d.geom_pos[g];
-          if (bg < 0) { pg[0] = gp[0]; pg[1] = gp[1]; pg[2] = gp[2]; }
-          else { const double* R = s.xmat + bg * 9; for (int r = 0; r < 3; r++) pg[r] = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
-          const double dif[3] = {cen[hb * 3] - pg[0], cen[hb * 3 + 1] - pg[1], cen[hb * 3 + 2] - pg[2]};
-          if (MDL.d.geom_type[g] == 0) { const double* gm = MDL.d.geom_mat[g]; const double nrm[3] = {gm[2], gm[5], gm[8]}; near = dot3(dif, nrm) <= MDL.hull_rbound[hb]; }
-          else { const double bound = MDL.hull_rbound[hb] + MDL.d.geom_rbound[g]; near = dot3(dif, dif) <= bound * bound; }
-        }
-      } else {
-        const int ha = oa - MCB_NGEOM;
-        const double dif[3] = {cen[ha * 3] - cen[hb * 3], cen[ha * 3 + 1] - cen[hb * 3 + 1], cen[ha * 3 + 2] - cen[hb * 3 + 2]};
-        const double bound = MDL.hull_rbound[ha] + MDL.hull_rbound[hb];
-        near = dot3(dif, dif) <= bound * bound;
-      }
-    }
+    any |= (p < MDL.nhpair) && hull_pair_near(s, p, nba);
+  }
+  return __any_sync(FULLMASK, any);
+}
+// hull x {plane, box, hull} for the statically filtered pairs, after the primitive pairs (the oracle's order)
+template <class S>
+__device__ __noinline__ int collide_hulls(S& s, int lane, int nba, int ncon) {
+  double* cen = s.cscr + HS_CEN;
+  hull_centres(s, lane);
+  for (int base = 0; base < MDL.nhpair; base += 32) {
+    const int p = base + lane;
+    bool near = (p < MDL.nhpair) && hull_pair_near(s, p, nba);
     unsigned todo = __ballot_sync(FULLMASK, near);
     while (todo) {
       const int q = base + __ffs(todo) - 1;
       todo &= todo - 1;
       const int oa = MDL.hpair_a[q], ob = MDL.hpair_b[q], hb = ob - MCB_NGEOM;
-      CvxObj B;
+      CvxObj A, B;
+      double* poseA = s.cscr + HS_POSE;
+      double* poseB = s.cscr + HS_POSE + 12;
       B.kind = 0; B.body = MDL.hull_body[hb]; B.verts = MDL.hull_vert + 3 * (size_t)MDL.hull_vadr[hb]; B.n = MDL.hull_vnum[hb]; B.size = nullptr;
-      for (int k = 0; k < 3; k++) B.pos[k] = s.xpos[B.body * 3 + k];
-      for (int k = 0; k < 9; k++) B.mat[k] = s.xmat[B.body * 9 + k];
+      B.pos = s.xpos + B.body * 3; B.mat = s.xmat + B.body * 9;
+      A.kind = 0; A.body = -1; A.verts = nullptr; A.n = 0; A.size = nullptr; A.pos = poseA; A.mat = poseA + 3;
+      (void)poseB;
       bool hit = false; double dist = 0, nrm[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
       if (oa < MCB_NGEOM && MDL.d.geom_type[oa] == 0) {
         // mjc_PlaneConvex: the hull's support point against the plane normal (planes are static)
@@ -1167,27 +1191,30 @@ __device__ __noinline__ int collide_hulls(S& s, int lane, int nba, int ncon) {
         dist = dot3(dif, n);
         if (!(dist > 0)) { hit = true; for (int k = 0; k < 3; k++) { nrm[k] = n[k]; pos[k] = sp[k] - 0.5 * dist * n[k]; } }
       } else {
-        CvxObj A;
         double cA[3];
         if (oa < MCB_NGEOM) {
           const int g = oa, bg = MDL.d.geom_body[g];
-          A.kind = 1; A.body = bg; A.verts = nullptr; A.n = 0; A.size = MDL.d.geom_size[g];
+          A.kind = 1; A.body = bg; A.size = MDL.d.geom_size[g];
           const double* gp = MDL.d.geom_pos[g];
           const double* gm = MDL.d.geom_mat[g];
-          if (bg < 0) { for (int k = 0; k < 3; k++) A.pos[k] = gp[k]; for (int k = 0; k < 9; k++) A.mat[k] = gm[k]; }
-          else {
-            const double* R = s.xmat + bg * 9;
-            for (int r = 0; r < 3; r++) {
-              A.pos[r] = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2];
-              for (int c = 0; c < 3; c++) A.mat[3 * r + c] = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c];
+          __syncwarp();
+          if (lane < 12) {
+            double v;
+            if (bg < 0) v = lane < 3 ? gp[lane] : gm[lane - 3];
+            else {
+              const double* R = s.xmat + bg * 9;
+              if (lane < 3) { const int r = lane; v = s.xpos[bg * 3 + r] + R[3 * r] * gp[0] + R[3 * r + 1] * gp[1] + R[3 * r + 2] * gp[2]; }
+              else { const int r = (lane - 3) / 3, c = (lane - 3) % 3; v = R[3 * r] * gm[c] + R[3 * r + 1] * gm[3 + c] + R[3 * r + 2] * gm[6 + c]; }
             }
+            poseA[lane] = v;
           }
-          for (int k = 0; k < 3; k++) cA[k] = A.pos[k];
+          __syncwarp();
+          for (int k = 0; k < 3; k++) cA[k] = poseA[k];
         } else {
           const int ha = oa - MCB_NGEOM;
-          A.kind = 0; A.body = MDL.hull_body[ha]; A.verts = MDL.hull_vert + 3 * (size_t)MDL.hull_vadr[ha]; A.n = MDL.hull_vnum[ha]; A.size = nullptr;
-          for (int k = 0; k < 3; k++) { A.pos[k] = s.xpos[A.body * 3 + k]; cA[k] = cen[ha * 3 + k]; }
-          for (int k = 0; k < 9; k++) A.mat[k] = s.xmat[A.body * 9 + k];
+          A.kind = 0; A.body = MDL.hull_body[ha]; A.verts = MDL.hull_vert + 3 * (size_t)MDL.hull_vadr[ha]; A.n = MDL.hull_vnum[ha];
+          A.pos = s.xpos + A.body * 3; A.mat = s.xmat + A.body * 9;
+          for (int k = 0; k < 3; k++) cA[k] = cen[ha * 3 + k];
         }
         const double cB[3] = {cen[hb * 3], cen[hb * 3 + 1], cen[hb * 3 + 2]};
         double depth = 0;
@@ -1247,7 +1274,10 @@ __device__ __noinline__ void collide(S& s, int lane, int nba, bool mesh) {
     else ncon = box_box_coop(s, lane, p, ncon, p1, R1, MDL.d.geom_size[g1], p2, R2, MDL.d.geom_size[g2]);
     __syncwarp();
   }
-  if (mesh && MDL.nhull > 0) ncon = collide_hulls(s, lane, nba, ncon);
+  if (mesh && MDL.nhull > 0) {
+    if (S::TIER_ID == 0) { if (hull_any_near(s, lane, nba) && lane == 0) s.overflow += 1; }
+    else ncon = collide_hulls(s, lane, nba, ncon);
+  }
   if (lane == 0) {
     if (ncon > S::MAXC) { s.overflow += ncon - S::MAXC; ncon = S::MAXC; }
     s.ncon = ncon;
