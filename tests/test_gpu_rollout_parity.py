@@ -204,3 +204,23 @@ def test_one_step_from_rollout_states_ik_and_mocap(workload):
     print(f"\n{workload}: {len(chosen)} envs compared ({len(left)} left the common layout, rows dropped in the last tier: {dropped}), "
           f"worst |qpos gpu - oracle| {worst:.2e}, {loose} envs with a sensitivity-scaled bound above 1e-7")
     assert not failures, f"{workload}: {len(failures)} of {len(chosen)} out of bounds (env, qpos, obs, one-ulp sensitivity): {failures[:8]}"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_second_gpu_gives_the_same_step():
+    """Multi-GPU: the path shards by env with no data-path collective, so the per-rank check is that another device computes the
+    same step -- reach, 4096 envs, one step from the same rollout state on cuda:0 and cuda:1, compared bit for bit."""
+    from mycobotgym_b200.vector_env import MyCobotVectorEnv
+
+    kw, n = WORK["reach"]
+    outs = []
+    acts = (torch.rand(8, n, 7, generator=torch.Generator().manual_seed(3)) * 2 - 1)
+    for dev in ("cuda:0", "cuda:1"):
+        env = MyCobotVectorEnv(num_envs=n, seed=3, autotune=False, device=dev, **kw)
+        env.reset(seed=11)
+        for t in range(8):
+            obs, rew, *_ = env.step(acts[t].to(dev))
+        outs.append((env.get_state()["qpos"].cpu(), obs["observation"].cpu(), rew.cpu()))
+        env.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)

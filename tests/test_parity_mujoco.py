@@ -54,7 +54,33 @@ def test_mini_compiler_matches_mjmodel(pair):
     mjm, ours, live = pair
     diff = mjcf.diff_flatmodels(ours, live, rtol=1e-9)
     diff.pop("M0", None)                      # derived; compared through the inertias below
+    for k in ("hull_vert", "hull_vertnum", "hull_vertadr", "hull_center", "hull_rbound"):
+        diff.pop(k, None)                     # hull vertex order / count may differ (qhull options, float32 mesh storage): compared as point sets below
     assert not diff, diff
+    assert ours["nhull"] == live["nhull"]
+    for h in range(int(ours["nhull"])):
+        a = ours["hull_vert"][ours["hull_vertadr"][h]:ours["hull_vertadr"][h] + ours["hull_vertnum"][h]]
+        b = live["hull_vert"][live["hull_vertadr"][h]:live["hull_vertadr"][h] + live["hull_vertnum"][h]]
+        d_ab = np.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1))
+        assert d_ab.min(1).max() < 1e-5 and d_ab.min(0).max() < 1e-5, (ours["hull_names"][h], d_ab.min(1).max(), d_ab.min(0).max())
+        np.testing.assert_allclose(ours["hull_center"][h], live["hull_center"][h], atol=1e-6)
+
+
+def test_reference_keyframes_are_equilibria_of_mujoco():
+    """The premise of tests/test_keyframe_equilibria.py (the oracle's weld rows were chosen so that the mocap keyframe is an
+    equilibrium): MuJoCo itself must be at rest there, and must rest the cube 1.9e-5 m deep."""
+    path = os.path.join(_assets_dir(), "mycobot280_mocap.xml")
+    mjm = mujoco.MjModel.from_xml_path(path)
+    mjd = mujoco.MjData(mjm)
+    mujoco.mj_resetDataKeyframe(mjm, mjd, 0)
+    mujoco.mj_forward(mjm, mjd)
+    assert np.abs(mjd.qacc[:6]).max() < 0.5, mjd.qacc[:6]
+    for _ in range(3000):
+        mujoco.mj_step(mjm, mjd)
+    tcp = mujoco.mj_name2id(mjm, mujoco.mjtObj.mjOBJ_BODY, "gripper_tcp")
+    off = mjd.xpos[tcp] - mjd.mocap_pos[0]
+    assert abs(np.linalg.norm(off) - 1.1486e-3) < 2e-5, off
+    assert abs(mjd.qpos[14] - 0.209981) < 1e-6, mjd.qpos[14]
 
 
 def _no_mesh_contacts(mjm):
