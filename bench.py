@@ -344,7 +344,8 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {n} envs/GPU x {world} GPU, {kw.get('controller_type', 'joint')} controller, "
                                    f"{100 if kw.get('controller_type') == 'IK' else 20} substeps/step, uniform random actions "
                                    f"U[-1,1]^{env.action_dim} float32, 50-step TimeLimit (episode clocks staggered, {args.preroll}-step untimed pre-roll), auto-reset with on-device goal resampling",
-                       "envs_per_gpu": n, "lockstep_warps": env.lockstep_warps, "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
+                       "envs_per_gpu": n, "lockstep_warps": env.lockstep_warps,
+                       "mesh_collision": env.mesh_collision,     # False: plane / box primitives only; MCB_MESH=1 turns the hulls on "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": K * env.last_step_launches,
