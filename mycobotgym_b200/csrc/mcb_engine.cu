@@ -927,7 +927,7 @@ __device__ void cvx_support(const S& s, const CvxObj& o, const double* dir, doub
   for (int k = 0; k < 3; k++) ld[k] = o.mat[k] * dir[0] + o.mat[3 + k] * dir[1] + o.mat[6 + k] * dir[2];
   if (o.kind == 1) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) best[k] = ld[k] > 0 ? o.size[k] : -o.size[k];
+    for (int k = 0; k < 3; k++) best[k] = ld[k] >= -1e-11 ? o.size[k] : -o.size[k];      // components within 1e-11 of zero count as positive (see the oracle)
   } else {
     // the lowest-index vertex within 1e-11 of the maximum (two passes): coplanar hull vertices tie up to rounding, see the oracle
     double bd = -1e300;

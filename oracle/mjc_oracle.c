@@ -591,7 +591,9 @@ static int ccd_eq(double a, double b) {
 static void cvx_support(const cvx* o, const double* dir, double* out) {
   double ld[3], best[3] = {0, 0, 0};
   for (int k = 0; k < 3; k++) ld[k] = o->mat[k] * dir[0] + o->mat[3 + k] * dir[1] + o->mat[6 + k] * dir[2];   /* mat' dir */
-  if (o->is_box) { for (int k = 0; k < 3; k++) best[k] = ld[k] > 0 ? o->size[k] : -o->size[k]; }
+  /* box: the corner by the signs of the local direction; a component within SUPPORT_TIE of zero (a direction along a face normal:
+     all four corners of the face tie) counts as positive, so that rounding noise does not pick the corner */
+  if (o->is_box) { for (int k = 0; k < 3; k++) best[k] = ld[k] >= -SUPPORT_TIE ? o->size[k] : -o->size[k]; }
   else {
     /* the FIRST vertex within SUPPORT_TIE of the maximum: hull faces carry many coplanar vertices (cylinder caps, flat sides), whose
        support values tie up to rounding; with a plain arg-max the winner -- and with it the portal MPR ends on -- would be decided

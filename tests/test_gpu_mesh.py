@@ -41,12 +41,11 @@ def test_hull_contacts_match_the_oracle_stage_by_stage():
         d = env.debug_forward(0)
         assert d["ncon"] == sim.ncon and d["nefc"] == sim.nefc, (trial, d["ncon"], sim.ncon, d["nefc"], sim.nefc)
         oc = sim.contacts()
-        # mpr_tolerance 1e-6 bounds the portal refinement, not the depth itself: two runs that end on different portal triangles
-        # (FMA vs no FMA flips a support arg-max now and then) differ by up to ~1e-5 on a 6 mm penetration
-        np.testing.assert_allclose(d["contact_dist"], [c["dist"] for c in oc], atol=3e-5)
-        np.testing.assert_allclose(d["contact_normal"], [c["frame"][0] for c in oc], atol=2e-3)
-        np.testing.assert_allclose(d["contact_pos"], [c["pos"] for c in oc], atol=2e-3)             # the portal (hence the witness point) may differ
-        np.testing.assert_allclose(d["efc_D"], sim.efc("D"), rtol=1e-3)
+        # same portals on both sides (see the tie rules in test_one_step_with_hull_contacts): contacts agree to rounding
+        np.testing.assert_allclose(d["contact_dist"], [c["dist"] for c in oc], atol=1e-9)
+        np.testing.assert_allclose(d["contact_normal"], [c["frame"][0] for c in oc], atol=1e-8)
+        np.testing.assert_allclose(d["contact_pos"], [c["pos"] for c in oc], atol=1e-8)
+        np.testing.assert_allclose(d["efc_D"], sim.efc("D"), rtol=1e-9)
         if found >= 12:
             break
     assert found >= 12, found
@@ -105,10 +104,18 @@ def test_one_step_with_hull_contacts(workload):
         oe.sim.qpos[:] = st["qpos"][i]
         oe.goal = st["goal"][i].copy()
         oe.elapsed = int(st["elapsed"][i])
+        peak = [0]
+        orig = oe.sim.step
+
+        def step_tracked(nstep, orig=orig, peak=peak, sim=oe.sim):
+            for _ in range(nstep):
+                orig(1)
+                peak[0] = max(peak[0], sim.ncon)
+        oe.sim.step = step_tracked
         oe.step(acts[i])
         with_hull += 1
-        if oe.sim.ncon > 16:
-            continue
+        if peak[0] > 16:
+            continue                                   # more contacts than the last tier holds at some substep: the kernel drops (and counts) rows there
         compared += 1
         errs.append(np.abs(after["qpos"][i] - oe.sim.qpos).max())
         if compared >= 64:
@@ -117,9 +124,8 @@ def test_one_step_with_hull_contacts(workload):
     frac = float((errs <= 1e-5).mean())
     print(f"\n{workload}: {with_hull} envs with hull contacts, {compared} compared; |qpos gpu - oracle| median {np.median(errs):.1e}, "
           f"90 % {np.quantile(errs, 0.9):.1e}, max {errs.max():.1e}; within 1e-5: {100 * frac:.0f} %; rows dropped in the batch {dropped}")
-    # MPR's zero tests sit at machine epsilon (libccd's CCD_EPS): on the gripper's mirror-symmetric contacts (push) whole branches
-    # of the portal search are decided by the last bit, so two implementations of the SAME algorithm end on different portals --
-    # a normal a few degrees off, a witness point millimetres away.  What is asserted is therefore a distribution, not a bound
-    # per env: the step stays bounded everywhere and most envs agree to the with-contact tolerance where the geometry is generic.
+    # Both sides break support ties the same way (lowest-index hull vertex within 1e-11 of the maximum; box components within 1e-11
+    # of zero count as positive), which is what makes two implementations of MPR follow the same portal: before that rule the
+    # gripper's flat pads (direction along a face normal: four corners tie) sent 72 % of the push envs onto different portals.
     assert compared >= 8, (with_hull, compared)
-    assert errs.max() < 2e-2 and np.median(errs) < (1e-5 if workload == "mocap" else 1e-3), (np.median(errs), errs.max())
+    assert errs.max() < 1e-5, (frac, errs.max())          # the north star's with-contact bound, every compared env
