@@ -930,19 +930,24 @@ __device__ void cvx_support(const S& s, const CvxObj& o, const double* dir, doub
     for (int k = 0; k < 3; k++) best[k] = ld[k] >= -1e-11 ? o.size[k] : -o.size[k];      // components within 1e-11 of zero count as positive (see the oracle)
   } else {
     // the lowest-index vertex within 1e-11 of the maximum (two passes): coplanar hull vertices tie up to rounding, see the oracle
+    // (both scans are written without early exits and unrolled, so that several vertex loads are in flight: the vertices come
+    // from global memory / L2 and a hull has up to 1531 of them)
     double bd = -1e300;
+#pragma unroll 4
     for (int i = lane; i < o.n; i += 32) {
       const double* v = o.verts + 3 * i;
       const double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
-      if (t > bd) bd = t;
+      bd = t > bd ? t : bd;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { const double od = shfl_xor_d(bd, off); if (od > bd) bd = od; }
     int bi = 0x7fffffff;
+    const double thr = bd - 1e-11;
+#pragma unroll 4
     for (int i = lane; i < o.n; i += 32) {
       const double* v = o.verts + 3 * i;
       const double t = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
-      if (t >= bd - 1e-11) { bi = i; break; }
+      bi = (t >= thr && i < bi) ? i : bi;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { const int oi = __shfl_xor_sync(FULLMASK, bi, off); if (oi < bi) bi = oi; }
