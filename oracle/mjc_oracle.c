@@ -10,9 +10,12 @@
  * following in-tree reference lines.
  *
  * PARITY UNPINNED against MuJoCo itself: no mujoco wheel is available offline.  The
- * oracle is pinned only by (a) the reference's own known-answer values (FK of the EEF
- * site at qpos0 = mocap.xml:3, at the keyframe = mycobot280_mocap.xml:8), (b) physics
- * identities (tests/test_oracle_physics.py), see SURVEY.md Appendix B.9/C.
+ * oracle is pinned by (a) the reference's own known-answer values (FK of the EEF site at
+ * qpos0 = mocap.xml:3, at the keyframe = mycobot280_mocap.xml:8), (b) the reference's two
+ * recorded keyframes as equilibria (tests/test_keyframe_equilibria.py: the mocap keyframe fixes
+ * the weld rows -- one impedance per weld at the residual norm, translational inverse weight on
+ * all six rows; the cube's recorded rest depth, 1.9e-5 m, is NOT reproduced: 0.96e-5),
+ * (c) physics identities (tests/test_oracle_physics.py), see SURVEY.md Appendix B.9/C.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The CUDA product never links or calls it.

@@ -2,8 +2,9 @@
 
 `OracleSim` wraps one (model, data) pair of the C restatement; `OracleEnv` restates the
 reference's task logic (mycobotgym/envs/mycobot.py:132-133,190-306,342-400,450-481,506-514 and
-mycobotgym/utils.py:14-26) on top of it, joint controller only.  PARITY UNPINNED vs MuJoCo
-2.3.2 (not installable here); pinned by the reference's FK known answers and sampler protocol.
+mycobotgym/utils.py:14-26, 469-556) on top of it (joint, IK and mocap controllers).  PARITY UNPINNED vs MuJoCo
+2.3.2 (not installable here); pinned by the reference's FK known answers, sampler protocol and recorded keyframes
+(tests/test_keyframe_equilibria.py).
 """
 from __future__ import annotations
 
