@@ -78,6 +78,7 @@ def test_airborne_cubes_follow_the_damped_ballistic_law():
     gen.manual_seed(5)
     qpos, qvel = st["qpos"].clone(), torch.zeros_like(st["qvel"])
     qpos[:, 12:14] = (torch.rand(N, 2, device="cuda", dtype=torch.float64, generator=gen) - 0.5) * 0.2
+    qpos[:, 12] += 0.5                               # half a metre beside the robot: nothing to touch
     qpos[:, 14] = 0.6
     qvel[:, 12:15] = (torch.rand(N, 3, device="cuda", dtype=torch.float64, generator=gen) - 0.5) * 0.5
     env.set_state(qpos=qpos, qvel=qvel)
