@@ -22,6 +22,7 @@ WORK = {
 for name, (kw, n, adim) in WORK.items():
     env = MyCobotVectorEnv(num_envs=n, seed=1, **kw)
     env.reset()
+    env.set_state(elapsed=torch.arange(n, dtype=torch.int32) % 50)      # staggered episode clocks: resets spread over the steps
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1)
     k = steps if name != "ik" else max(50, steps // 5)
