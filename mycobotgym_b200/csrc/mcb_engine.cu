@@ -2424,9 +2424,9 @@ __global__ void __launch_bounds__(TIER == 0 ? ENV_LB_THREADS : TIER == 1 ? 32 * 
     if (blockIdx.x == 0 && threadIdx.x == 0) a.redo_count[1] = nwork;
     return;
   }
-  // the middle tier follows the batch's grouping when it is the whole CTA (its ten warps then share instruction-cache lines the
-  // same way; sub-groups would not divide ten warps evenly), and so do the five warps of a last-tier CTA
-  const int lockstep = (TIER == 0 && a.lockstep_warps > 1) ? a.lockstep_warps : (TIER >= 1 && a.lockstep_warps >= WPB_SMALL_) ? WPB_SMALL_ : 0;
+  // the upper tiers always run their CTA in lockstep (their envs are the divergent, contact-rich ones: free-running they stall on
+  // instruction fetch -- held grasp 59 -> 20 ms/step); the batch's grouping (mcb_autotune) only concerns the common-layout kernel
+  const int lockstep = TIER == 0 ? (a.lockstep_warps > 1 ? a.lockstep_warps : 0) : WPB_SMALL_;
 
   // Tier 0: CTA b takes the 16 consecutive envs [16 b, 16 b + 16).  Tier 1: the list is dealt round-robin over the CTAs
   // (item = slot * gridDim.x + b), so a list shorter than one full wave spreads over all SMs with few warps each instead of
