@@ -1976,7 +1976,7 @@ struct Newton {
 // share instruction-cache lines -- the kernel is thousands of straight-line instructions per substep and
 // independent warps drifting apart made instruction fetch the top stall (profiles/r01c).  Every path through
 // forward() executes exactly NSYNC_FWD barriers when sync is set.
-#define NSYNC_FWD 6
+#define NSYNC_FWD __builtin_popcount(MCB_SYNC_MASK)
 // Lockstep groups: `lw` consecutive warps of the CTA share one named barrier (ids 1..), so the CTA runs 16 / lw groups
 // that drift against each other (different stages -> different pipes busy at the same time) while the warps inside a
 // group still share instruction-cache lines.  lw = 1: free-running warps, no barriers.  Which grouping wins depends on
@@ -1987,25 +1987,28 @@ __device__ __forceinline__ void group_sync(int lw) {
   if (lw >= WPB_SMALL_) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / lw), "r"(32 * lw) : "memory");
 }
-#define FSYNC() do { if (sync) group_sync(sync); } while (0)
+#ifndef MCB_SYNC_MASK
+#define MCB_SYNC_MASK 0x3f      // which of forward()'s six stage boundaries carry a barrier (tuning experiments, profiles/README.md)
+#endif
+#define FSYNC(k) do { if (((MCB_SYNC_MASK) >> (k) & 1) && sync) group_sync(sync); } while (0)
 template <class S>
 __device__ __noinline__ bool forward(S& s, const DevModel* __restrict__ m, int lane, int nba, int nva, int sync) {
-  FSYNC();
+  FSYNC(0);
   fk(s, m, lane, nba);
   cinert_cdof(s, m, lane, nba, nva);
-  FSYNC();
+  FSYNC(1);
   crb_mass(s, m, lane, nba, nva);
   velocity_rne(s, m, lane, nba, nva);
-  FSYNC();
+  FSYNC(2);
   actuation_smooth(s, m, lane, nva);
   double qs = factor_solve_M<true>(s.M, s.H, s.qfrc_smooth, s.Mv, 0.0, lane, nva);
   if (lane < nva) s.qacc_smooth[lane] = qs;
   __syncwarp();
-  FSYNC();
+  FSYNC(3);
   collide(s, lane, nba, s.mesh != 0);
-  FSYNC();
+  FSYNC(4);
   bool ok = make_rows(s, m, lane, nva);
-  FSYNC();
+  FSYNC(5);
   if (!ok && !S::IS_BIG) return false;
   Newton<S> nw{s, m, lane, nva, s.nefc};
   nw.solve();
