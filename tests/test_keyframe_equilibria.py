@@ -10,7 +10,8 @@
 * `mycobot280.xml:6-8` (joint variant): a snapshot of the arm *inside* its actuator chatter (kv h / I >> 2) with
   qvel typed as zeros -- no equilibrium, but its `ctrl - qpos` of up to 0.052 rad can only persist in the bang-bang regime,
   and its gripper angles must lie inside the envelope the chatter shakes them through.
-* both: cube z = 0.209981, i.e. 1.9e-5 m rest depth.  NOT reproduced (0.96e-5): see `test_cube_rest_depth_open_question`.
+* both: cube z = 0.209981, i.e. 1.9e-5 m rest depth.  NOT reproduced (0.96e-5): see `test_cube_rest_depth_open_question`, and
+  `test_keyframes_predate_the_current_cube_element` for why the datum is most likely stale.
 
 The keyframe numbers below are typed from the reference XML (CPU test; /root/reference is not read at run time).
 """
@@ -113,6 +114,29 @@ def test_cube_rest_depth_formula_family():
             hits.append((rn, im, dim, ncon, mu))
     assert abs(ours - 0.959e-5) < 2e-8
     assert hits and all(h[0] == "mix" and h[1] == "mix" and h[3] * (h[2] - 1) == 6 for h in hits), hits
+
+
+def test_keyframes_predate_the_current_cube_element():
+    """Why the recorded depth need not be reproducible at all: the keyframes were saved under an earlier edit of the cube's
+    XML element.  (1) The joint keyframe holds an UNTOUCHED cube (y = -8e-16, quaternion 1 to 1e-14) at x = 0.1 exactly, and the
+    mocap keyframe a nudged one at x = 0.0914 -- but `mycobot280_main.xml:260` now places the body at x = -0.05, and neither the
+    viewer nor the env (which draws the cube's xy at random, mycobot.py:216-227) puts an untouched cube at exactly 0.1.  So the
+    `<body name="object0">` element was edited after the keyframes were recorded; its geom's contact attributes sit on the next
+    two lines.  (2) Under the very same formulas that give 0.959e-5 today, ordinary earlier attribute sets rest the cube at the
+    recorded depth, e.g. condim 3 with solref 0.004 (= 2 timestep) and today's solimp 0.999.  This is a plausibility
+    argument, not a fit: nothing in the oracle or the kernel was changed for it, and the strict xfail above stays."""
+    fm = mjcf.load_compiled(mjcf.COMPILED_JOINT)
+    cube = list(fm["body_names"]).index("object0")
+    assert abs(fm["body_pos"][cube][0] - (-0.05)) < 1e-12 and abs(fm["body_pos"][cube][2] - 0.21) < 1e-12
+    assert JOINT_QPOS[12] == 0.1 and abs(JOINT_QPOS[13]) < 1e-12 and np.abs(JOINT_QPOS[16:]).max() < 1e-12
+    g, table_ref, table_imp = 9.81, 0.02, (0.9, 0.95)
+    def depth(dim, tc_cube, d0_cube, dmax_cube, mu_cube):
+        tc = max(0.5 * (tc_cube + table_ref), 2 * 0.002)
+        d0, dm, mu = 0.5 * (d0_cube + table_imp[0]), 0.5 * (dmax_cube + table_imp[1]), max(1.0, mu_cube)
+        return g * 2 * mu * mu * (1 + mu * mu) * (1 - d0) * dm * dm * tc * tc / (d0 * d0 * 4 * 2 * (dim - 1))
+    assert abs(depth(4, 0.001, 0.999, 0.999, 0.95) - 0.959e-5) < 2e-8             # today's element
+    recorded = lambda d: abs(round(0.21 - d, 6) - 0.209981) < 1e-9                # what the keyframe's six digits print
+    assert recorded(depth(3, 0.004, 0.999, 0.999, 0.95)) and recorded(depth(3, 0.004, 0.998, 0.998, 0.95)) and recorded(depth(4, 0.004, 0.95, 0.99, 0.95))
 
 
 def test_joint_keyframe_is_a_chatter_snapshot():
