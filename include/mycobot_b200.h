@@ -144,7 +144,7 @@ typedef struct mcb_task_cfg {
   int32_t frame_skip;          /* 20 */
   int32_t auto_reset;          /* 1: reset inside mcb_step when terminated|truncated */
   int32_t nefc_max;            /* 0 (default): tiered shared-memory layouts (48-row common case, 88-row middle tier for contact-rich envs,
-                                * 128-row last tier), one launch each; 88 / 128: start in the middle / last tier (tests) */
+                                * 176-row last tier), one launch each; 88 / 128: start in the middle / last tier (tests) */
   int32_t controller_type;     /* 0 joint (action 7), 1 IK (7, or 4 with fetch_env), 2 mocap (8, or 4 with fetch_env; needs the mocap
                                   model variant); mycobot.py:36,90-103,134-193 */
   int32_t fetch_env;           /* mycobot.py:41: keyframe start, fixed target orientation, 4-d action (IK only) */

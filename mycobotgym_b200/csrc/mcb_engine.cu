@@ -14,7 +14,7 @@
 //     constraint Jacobian is stored BLOCKED by row type (robot rows: 12 columns, cube rows: 6, coupled rows: 18,
 //     joint-limit rows: none);
 //   * capacity comes in three tiers (EnvS<TIER>): 48 rows for the common case, 88 rows / 10 envs per CTA for
-//     contact-rich envs (a grasp), 128 rows / one env per CTA as the last resort.  An env that does not fit its tier
+//     contact-rich envs (a grasp), 176 rows / five envs per CTA as the last resort.  An env that does not fit its tier
 //     aborts untouched, is queued on a device list and is redone by the next tier's launch;
 //   * the block structure robot(12) + cube(6) is used everywhere: M's cube block never couples, H couples
 //     only through finger-cube contact rows, so the usual factorizations are 12x12 and 6x6, fully unrolled, as
@@ -147,6 +147,10 @@ struct StepArgs {
 // per-env shared-memory working set, one layout per capacity tier (see the table in DESIGN.md section 3).
 // TIER 0: the common case (16 envs per CTA); TIER 1: contact-rich envs -- a grasp, pushing, the gripper resting on the
 // table (10 envs per CTA); TIER 2: the last resort, one env per CTA, rows beyond its capacity are dropped and counted.
+// last tier: both finger pads flat on the table (8 box-box points each) plus the cube's four corners are 20 condim-4 contacts
+// = 120 rows on top of the 13 equality rows and the joint limits -- the IK / mocap soak runs dropped rows at 16 contacts / 128 rows
+#define NROW_LAST 176
+#define MAXC_LAST 24
 template <int TIER>
 struct EnvS {
   // MCB_CANARY build (tests/test_gpu_canary.py; compute-sanitizer is closed on the GPU pool): guard words between the arrays of
@@ -159,8 +163,8 @@ struct EnvS {
 #define GUARD(name)
 #define MCB_NGUARD 0
 #endif
-  enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : 128, POOL = (TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432) - (MCB_NGUARD ? (TIER == 0 ? 10 : 2 * MCB_NGUARD) : 0),   // (tier 0: the row arrays must stay the union's largest member)
-         MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : 16,
+  enum { NROW = TIER == 0 ? 48 : TIER == 1 ? 88 : NROW_LAST, POOL = (TIER == 0 ? 460 : TIER == 1 ? 1230 : 2432) - (MCB_NGUARD ? (TIER == 0 ? 10 : 2 * MCB_NGUARD) : 0),   // (tier 0: the row arrays must stay the union's largest member)
+         MAXC = TIER == 0 ? 8 : TIER == 1 ? 14 : MAXC_LAST,
          IS_BIG = TIER == 2, TIER_ID = TIER };
   double qpos[20], qvel[NV], ctrl[8], warm[NV], goal[4];
   GUARD(g0)
@@ -2747,7 +2751,7 @@ __global__ void iota_kernel(int* list, int* count, int n) {
   if (i == 0) *count = n;
 }
 
-#define DEBUG_DOUBLES (4 + NV * NV + 5 * NV + NB * 12 + 128 * NV + 2 * 128 + 7 * 16)
+#define DEBUG_DOUBLES (4 + NV * NV + 5 * NV + NB * 12 + NROW_LAST * NV + 2 * NROW_LAST + 7 * MAXC_LAST)
 
 }  // namespace
 

@@ -442,7 +442,7 @@ class MyCobotVectorEnv:
 
     def debug_forward(self, env=0):
         """Stage-level tap for parity tests: runs forward and returns intermediate quantities of one env."""
-        cap = 4 + 18 * 18 + 5 * 18 + 13 * 12 + 128 * 18 + 2 * 128 + 7 * 16
+        cap = 4 + 18 * 18 + 5 * 18 + 13 * 12 + 256 * 18 + 2 * 256 + 7 * 32      # at least the library's dump (176 rows, 24 contacts)
         buf = np.zeros(cap)
         with torch.cuda.device(self._dev_index):
             _lib.check(self._L.mcb_debug_forward(self._batch, int(env), 0, buf.ctypes.data_as(C.c_void_p), cap, self._stream()))
